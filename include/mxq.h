@@ -1,0 +1,150 @@
+/*
+ * mxq.h -- C ABI of the B200-native MX quantize / dequantize / block-scaled GEMM library
+ *          (libmxq.so, built from torchmx_b200/csrc by `python -m torchmx_b200.build`).
+ *
+ * This is the drop-in boundary for torchmx's hot path.  The reference implements the path as
+ * two Python `torch.library.custom_op`s plus an aten override table; the entry points below are
+ * what those op bodies bind to (see INTEGRATION.md for the ctypes stub a maintainer would add to
+ * the reference).  Citations are relative to the reference repository root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - all pointers are DEVICE pointers on `device` unless the name says `host`;
+ *   - nothing is allocated or owned by the library: outputs are caller-allocated;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and the call returns without synchronising;
+ *   - `device` is the CUDA device ordinal the pointers live on (-1 = the calling thread's
+ *     current device); the library saves/restores the thread's current device around the call,
+ *     it never changes it for the caller (the reference is called from arbitrary Python
+ *     threads: examples/quantized_llama_chat.py:123-129);
+ *   - return value 0 = success; non-zero = error, message from mxq_last_error() (thread-local).
+ *     The library never throws, aborts or exits.
+ */
+#ifndef MXQ_H_
+#define MXQ_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MXQ_API __attribute__((visibility("default")))
+#else
+#define MXQ_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Element formats: torchmx/dtypes.py:34-92, looked up by name through
+ * dtypes.STR_TO_SUPPORTED_ELEM_DTYPE (dtypes.py:161) because the op schemas carry a string
+ * (torchmx/mx_tensor.py:39,52).  MXQ_E5M2 is an extension the reference does not have. */
+typedef enum {
+    MXQ_ELEM_E4M3 = 0, /* float8_e4m3  1 byte / element                                  */
+    MXQ_ELEM_E3M2 = 1, /* float6_e3m2  1 byte / element, code in bits [5:0]               */
+    MXQ_ELEM_E2M3 = 2, /* float6_e2m3  1 byte / element, code in bits [5:0]               */
+    MXQ_ELEM_E2M1 = 3, /* float4_e2m1  2 elements / byte, even element in the HIGH nibble
+                          (torchmx/utils.py:120-145)                                     */
+    MXQ_ELEM_INT8 = 4, /* int8         1 byte / element, two's complement                 */
+    MXQ_ELEM_E5M2 = 5  /* float8_e5m2  extension, parity unpinned                         */
+} mxq_elem_t;
+
+typedef enum {
+    MXQ_HP_BF16 = 0, /* the only input dtype the reference accepts (mx_tensor.py:59-61)      */
+    MXQ_HP_F32 = 1   /* dequantize target (mx_tensor.py:456-472); quantize input = extension */
+} mxq_hp_t;
+
+/* flags for mxq_quantize */
+#define MXQ_FLAG_HW_EXACT 1u /* env MX_HARDWARE_EXACT_QUANTIZATION == "True"
+                                (torchmx/env_variables.py:16, mx_tensor.py:80-90).  Only
+                                observable in NaN-scale blocks: see DESIGN.md "hw_exact quirk" */
+
+/*
+ * quantize  <->  torchmx::quantize_mx  (torchmx/mx_tensor.py:36-96)
+ *   + get_e8m0_shared_exponent                          (torchmx/mx_quantization_utils.py:502-558)
+ *   + quantize_mx_with_e8m0_shared_exponent_{simulated,hw_exact}   (:435-499, :253-412)
+ *   + pack_uint4 for float4_e2m1                        (torchmx/utils.py:120-145)
+ *
+ * src    : n_blocks * block_size contiguous high-precision elements, blocks along the
+ *          innermost (contiguous) axis -- the reference requires a contiguous tensor whose last
+ *          dim is a multiple of block_size (mx_tensor.py:62, 68-70), so the tensor is a flat
+ *          run of blocks.
+ * codes  : n_blocks*block_size bytes (n_blocks*block_size/2 for MXQ_ELEM_E2M1; the total element
+ *          count must then be even, utils.py:143).  int8 codes are two's complement bytes.
+ * scales : n_blocks E8M0 bytes; 255 = NaN (dtypes.py:183).
+ */
+MXQ_API int mxq_quantize(const void *src, int src_dtype /* mxq_hp_t */, int64_t n_blocks, int block_size,
+                 int elem /* mxq_elem_t */, unsigned flags, void *codes, uint8_t *scales,
+                 int device, void *stream);
+
+/*
+ * dequantize (flat)  <->  torchmx::dequantize_mx with block_dim == last dim and contiguous
+ * operands (torchmx/mx_tensor.py:123-164; decode mx_quantization_utils.py:93-146; scale
+ * :415-432).  dst: n_blocks*block_size elements of dst_dtype.
+ */
+MXQ_API int mxq_dequantize(const void *codes, const uint8_t *scales, int64_t n_blocks, int block_size,
+                   int elem, int dst_dtype /* mxq_hp_t */, void *dst, int device, void *stream);
+
+/*
+ * dequantize (strided)  <->  the same op for every other case the reference accepts: `data_lp`
+ * a permuted / expanded view, `block_dim` != last (mx_tensor.py:157-162; exercised by
+ * tests/test_mx_tensor.py:195-356).
+ *   ndim          : 1..MXQ_MAX_DIMS
+ *   sizes         : LOGICAL (unpacked) element counts per dim
+ *   code_strides  : strides of data_lp in BYTES-OF-CODE units per dim; for MXQ_ELEM_E2M1 the
+ *                   blocked dim is packed, i.e. logical index i along block_dim lives in byte
+ *                   i/2 (high nibble when i is even)
+ *   scale_strides : strides of shared_exp_e8m0 per dim (its size along block_dim is
+ *                   sizes[block_dim]/block_size)
+ *   dst           : C-contiguous in the logical shape (what FromMXConstrFunc returns,
+ *                   mx_tensor.py:323)
+ */
+#define MXQ_MAX_DIMS 6
+MXQ_API int mxq_dequantize_strided(const void *codes, const uint8_t *scales, int ndim, const int64_t *sizes,
+                           const int64_t *code_strides, const int64_t *scale_strides, int block_dim,
+                           int block_size, int elem, int dst_dtype, void *dst, int device,
+                           void *stream);
+
+/*
+ * MX matmul  <->  the aten overrides torchmx/ops.py:29-41 (linear), :60-68 (mm / matmul),
+ * :99-107 (bmm), :110-119 (addmm): D[b] = A[b] * B[b]^T (+ bias), A: [M,K] codes, B: [N,K]
+ * codes, both blocked along K with block_size 32 and E8M0 scales [M,K/32] / [N,K/32];
+ * D: [M,N] bf16.  The reference dequantizes both operands and calls a bf16 GEMM; this entry
+ * point runs a tcgen05 block-scaled MMA (kind::mxf8f6f4) instead.
+ *   a_codes / b_codes : K-major, one byte per element holding an E4M3-container code (fp6 / fp4
+ *                       reference codes are transcoded exactly with mxq_transcode_to_e4m3)
+ *   lda / ldb         : row strides in bytes (multiples of 16); batch strides in bytes
+ *   sfa / sfb         : row-major [rows, K/32] E8M0, row stride ld_sf, batch stride given
+ *   bias              : NULL or N bf16 values added to every row (aten.addmm / linear bias)
+ *   d                 : bf16 [M,N], row stride ldd elements, batch stride in elements
+ * Returns MXQ_ERR_UNSUPPORTED_SHAPE (2) when the shape cannot run on the tensor-core path
+ * (K % 128 != 0, misaligned strides); the caller then uses the dequantize path.
+ */
+typedef struct {
+    const void *a_codes; const uint8_t *sfa; int64_t lda, ld_sfa, a_batch_stride, sfa_batch_stride;
+    const void *b_codes; const uint8_t *sfb; int64_t ldb, ld_sfb, b_batch_stride, sfb_batch_stride;
+    const void *bias;
+    void *d; int64_t ldd, d_batch_stride;
+    int64_t batch, M, N, K;
+} mxq_gemm_args_t;
+MXQ_API int mxq_gemm(const mxq_gemm_args_t *args, int device, void *stream);
+
+/* exact re-encoding of reference-layout element codes as E4M3 bytes (every e3m2 / e2m3 / e2m1
+ * value is representable in e4m3): n elements in, n bytes out; MXQ_ELEM_E2M1 input is packed. */
+MXQ_API int mxq_transcode_to_e4m3(const void *codes, int elem, int64_t n_elements, void *out_e4m3,
+                          int device, void *stream);
+
+#define MXQ_OK 0
+#define MXQ_ERR_INVALID 1
+#define MXQ_ERR_UNSUPPORTED_SHAPE 2
+#define MXQ_ERR_CUDA 3
+
+MXQ_API const char *mxq_last_error(void);
+MXQ_API int mxq_version(void);
+/* compiled-for architecture as an integer (1000 for sm_100a) -- lets the host refuse to run a
+ * library that was built for something else instead of failing inside a launch. */
+MXQ_API int mxq_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MXQ_H_ */

@@ -1,0 +1,77 @@
+"""ctypes binding of libmxq.so (C ABI: include/mxq.h).  There is no CPU or PyTorch fallback: if the
+library is missing or cannot be loaded every op raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmxq.so")
+
+OK, ERR_INVALID, ERR_UNSUPPORTED_SHAPE, ERR_CUDA = 0, 1, 2, 3
+HP_BF16, HP_F32 = 0, 1
+FLAG_HW_EXACT = 1
+MAX_DIMS = 6
+
+EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_transcode_to_e4m3",
+           "mxq_last_error", "mxq_version", "mxq_arch")
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("a_codes", ctypes.c_void_p), ("sfa", ctypes.c_void_p), ("lda", ctypes.c_int64), ("ld_sfa", ctypes.c_int64),
+        ("a_batch_stride", ctypes.c_int64), ("sfa_batch_stride", ctypes.c_int64),
+        ("b_codes", ctypes.c_void_p), ("sfb", ctypes.c_void_p), ("ldb", ctypes.c_int64), ("ld_sfb", ctypes.c_int64),
+        ("b_batch_stride", ctypes.c_int64), ("sfb_batch_stride", ctypes.c_int64),
+        ("bias", ctypes.c_void_p),
+        ("d", ctypes.c_void_p), ("ldd", ctypes.c_int64), ("d_batch_stride", ctypes.c_int64),
+        ("batch", ctypes.c_int64), ("M", ctypes.c_int64), ("N", ctypes.c_int64), ("K", ctypes.c_int64),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"torchmx_b200: {LIB_PATH} is missing. Build it with `python -m torchmx_b200.build` "
+                "(needs nvcc; sm_100a). There is no CPU / PyTorch fallback for the MX kernels.")
+        L = ctypes.CDLL(LIB_PATH)
+        i64, i32, vp, u32 = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint
+        L.mxq_last_error.restype = ctypes.c_char_p
+        L.mxq_last_error.argtypes = []
+        L.mxq_version.restype = i32
+        L.mxq_arch.restype = i32
+        L.mxq_quantize.restype = i32
+        L.mxq_quantize.argtypes = [vp, i32, i64, i32, i32, u32, vp, vp, i32, vp]
+        L.mxq_dequantize.restype = i32
+        L.mxq_dequantize.argtypes = [vp, vp, i64, i32, i32, i32, vp, i32, vp]
+        L.mxq_dequantize_strided.restype = i32
+        L.mxq_dequantize_strided.argtypes = [vp, vp, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64),
+                                             i32, i32, i32, i32, vp, i32, vp]
+        L.mxq_gemm.restype = i32
+        L.mxq_gemm.argtypes = [ctypes.POINTER(GemmArgs), i32, vp]
+        L.mxq_transcode_to_e4m3.restype = i32
+        L.mxq_transcode_to_e4m3.argtypes = [vp, i32, i64, vp, i32, vp]
+        if L.mxq_arch() != 1000:
+            raise RuntimeError(f"torchmx_b200: libmxq.so was built for arch {L.mxq_arch()}, expected sm_100a")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise RuntimeError(f"{what} failed (status {rc}): {lib().mxq_last_error().decode()}")
+
+
+def i64_array(values):
+    return (ctypes.c_int64 * len(values))(*[int(v) for v in values])

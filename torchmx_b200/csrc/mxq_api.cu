@@ -1,0 +1,156 @@
+// extern "C" surface of libmxq.so (declared in include/mxq.h).  Validates arguments, pins the CUDA
+// device for the duration of the call, launches on the caller's stream, never synchronises.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "mxq_common.cuh"
+
+namespace mxq {
+cudaError_t launch_quantize(const void*, int, int64_t, int, int, unsigned, void*, uint8_t*, int, int, cudaStream_t);
+cudaError_t launch_dequantize(const void*, const uint8_t*, int64_t, int, int, int, void*, int, cudaStream_t);
+cudaError_t launch_dequantize_strided(const void*, const uint8_t*, int, const int64_t*, const int64_t*, const int64_t*, int, int, int, int,
+                                      void*, cudaStream_t);
+cudaError_t launch_transcode(const void*, int, int64_t, void*, int, cudaStream_t);
+int launch_gemm(const mxq_gemm_args_t*, int, cudaStream_t, char*, size_t);
+}  // namespace mxq
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char* what) {
+    return fail(MXQ_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+// Pins `device` as the calling thread's current device for the scope, restores the previous one.
+struct DeviceScope {
+    int prev = -1, cur = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceScope(int device) {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) return;
+        cur = device < 0 ? prev : device;
+        if (cur != prev) err = cudaSetDevice(cur);
+    }
+    ~DeviceScope() {
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int sm_count_of(int device) {
+    static int cache[64];
+    if (device >= 0 && device < 64 && cache[device]) return cache[device];
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    if (device >= 0 && device < 64) cache[device] = n;
+    return n;
+}
+
+bool valid_elem(int e) { return e >= MXQ_ELEM_E4M3 && e <= MXQ_ELEM_E5M2; }
+
+// developer knobs (not part of the reference-facing contract): MXQ_QUANT_EPT = 8 | 16 | 32
+int quant_ept_override() {
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("MXQ_QUANT_EPT");
+        v = s ? atoi(s) : 0;
+        if (v != 8 && v != 16 && v != 32) v = 0;
+    }
+    return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mxq_last_error(void) { return g_err; }
+int mxq_version(void) { return 1; }
+int mxq_arch(void) { return 1000; }
+
+int mxq_quantize(const void* src, int src_dtype, int64_t n_blocks, int block_size, int elem, unsigned flags, void* codes, uint8_t* scales,
+                 int device, void* stream) {
+    if (!valid_elem(elem)) return fail(MXQ_ERR_INVALID, "mxq_quantize: unknown element type %d", elem);
+    if (src_dtype != MXQ_HP_BF16 && src_dtype != MXQ_HP_F32) return fail(MXQ_ERR_INVALID, "mxq_quantize: unsupported source dtype %d", src_dtype);
+    if (n_blocks < 0 || block_size < 1) return fail(MXQ_ERR_INVALID, "mxq_quantize: bad n_blocks=%lld block_size=%d", (long long)n_blocks, block_size);
+    if (n_blocks == 0) return MXQ_OK;
+    if (!src || !codes || !scales) return fail(MXQ_ERR_INVALID, "mxq_quantize: null pointer");
+    if (elem == MXQ_ELEM_E2M1 && ((n_blocks * block_size) & 1))
+        return fail(MXQ_ERR_INVALID, "mxq_quantize: float4_e2m1 needs an even element count (got %lld)", (long long)(n_blocks * block_size));
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_quantize: selecting device");
+    const cudaError_t e = mxq::launch_quantize(src, src_dtype, n_blocks, block_size, elem, flags, codes, scales, sm_count_of(scope.cur),
+                                               quant_ept_override(), (cudaStream_t)stream);
+    return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_quantize: launch");
+}
+
+int mxq_dequantize(const void* codes, const uint8_t* scales, int64_t n_blocks, int block_size, int elem, int dst_dtype, void* dst, int device,
+                   void* stream) {
+    if (!valid_elem(elem)) return fail(MXQ_ERR_INVALID, "mxq_dequantize: unknown element type %d", elem);
+    if (dst_dtype != MXQ_HP_BF16 && dst_dtype != MXQ_HP_F32) return fail(MXQ_ERR_INVALID, "mxq_dequantize: unsupported target dtype %d", dst_dtype);
+    if (n_blocks < 0 || block_size < 1) return fail(MXQ_ERR_INVALID, "mxq_dequantize: bad n_blocks=%lld block_size=%d", (long long)n_blocks, block_size);
+    if (n_blocks == 0) return MXQ_OK;
+    if (!codes || !scales || !dst) return fail(MXQ_ERR_INVALID, "mxq_dequantize: null pointer");
+    if (elem == MXQ_ELEM_E2M1 && ((n_blocks * block_size) & 1)) return fail(MXQ_ERR_INVALID, "mxq_dequantize: float4_e2m1 needs an even element count");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_dequantize: selecting device");
+    const cudaError_t e = mxq::launch_dequantize(codes, scales, n_blocks, block_size, elem, dst_dtype, dst, sm_count_of(scope.cur), (cudaStream_t)stream);
+    return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_dequantize: launch");
+}
+
+int mxq_dequantize_strided(const void* codes, const uint8_t* scales, int ndim, const int64_t* sizes, const int64_t* code_strides,
+                           const int64_t* scale_strides, int block_dim, int block_size, int elem, int dst_dtype, void* dst, int device,
+                           void* stream) {
+    if (!valid_elem(elem)) return fail(MXQ_ERR_INVALID, "mxq_dequantize_strided: unknown element type %d", elem);
+    if (dst_dtype != MXQ_HP_BF16 && dst_dtype != MXQ_HP_F32) return fail(MXQ_ERR_INVALID, "mxq_dequantize_strided: unsupported target dtype %d", dst_dtype);
+    if (ndim < 1 || ndim > MXQ_MAX_DIMS) return fail(MXQ_ERR_INVALID, "mxq_dequantize_strided: ndim %d outside 1..%d", ndim, MXQ_MAX_DIMS);
+    if (block_dim < 0 || block_dim >= ndim || block_size < 1) return fail(MXQ_ERR_INVALID, "mxq_dequantize_strided: bad block_dim=%d block_size=%d", block_dim, block_size);
+    if (!sizes || !code_strides || !scale_strides) return fail(MXQ_ERR_INVALID, "mxq_dequantize_strided: null shape pointer");
+    int64_t total = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (sizes[d] < 0) return fail(MXQ_ERR_INVALID, "mxq_dequantize_strided: negative size");
+        total *= sizes[d];
+    }
+    if (sizes[block_dim] % block_size) return fail(MXQ_ERR_INVALID, "mxq_dequantize_strided: size %lld along the blocked dim is not a multiple of %d", (long long)sizes[block_dim], block_size);
+    if (elem == MXQ_ELEM_E2M1 && (sizes[block_dim] & 1)) return fail(MXQ_ERR_INVALID, "mxq_dequantize_strided: float4_e2m1 needs an even blocked dim");
+    if (total == 0) return MXQ_OK;
+    if (!codes || !scales || !dst) return fail(MXQ_ERR_INVALID, "mxq_dequantize_strided: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_dequantize_strided: selecting device");
+    const cudaError_t e = mxq::launch_dequantize_strided(codes, scales, ndim, sizes, code_strides, scale_strides, block_dim, block_size, elem, dst_dtype, dst, (cudaStream_t)stream);
+    return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_dequantize_strided: launch");
+}
+
+int mxq_transcode_to_e4m3(const void* codes, int elem, int64_t n_elements, void* out, int device, void* stream) {
+    if (elem < MXQ_ELEM_E4M3 || elem > MXQ_ELEM_E2M1) return fail(MXQ_ERR_INVALID, "mxq_transcode_to_e4m3: element type %d has no e4m3 container form", elem);
+    if (n_elements < 0) return fail(MXQ_ERR_INVALID, "mxq_transcode_to_e4m3: negative count");
+    if (n_elements == 0) return MXQ_OK;
+    if (!codes || !out) return fail(MXQ_ERR_INVALID, "mxq_transcode_to_e4m3: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_transcode_to_e4m3: selecting device");
+    const cudaError_t e = mxq::launch_transcode(codes, elem, n_elements, out, sm_count_of(scope.cur), (cudaStream_t)stream);
+    return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_transcode_to_e4m3: launch");
+}
+
+int mxq_gemm(const mxq_gemm_args_t* a, int device, void* stream) {
+    if (!a) return fail(MXQ_ERR_INVALID, "mxq_gemm: null args");
+    if (a->batch < 0 || a->M < 0 || a->N < 0 || a->K < 0) return fail(MXQ_ERR_INVALID, "mxq_gemm: negative extent");
+    if (a->batch == 0 || a->M == 0 || a->N == 0) return MXQ_OK;
+    if (!a->a_codes || !a->b_codes || !a->sfa || !a->sfb || !a->d) return fail(MXQ_ERR_INVALID, "mxq_gemm: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_gemm: selecting device");
+    char msg[400] = "";
+    const int rc = mxq::launch_gemm(a, sm_count_of(scope.cur), (cudaStream_t)stream, msg, sizeof(msg));
+    return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_gemm: %s", msg);
+}
+
+}  // extern "C"

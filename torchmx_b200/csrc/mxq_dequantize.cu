@@ -1,0 +1,270 @@
+// K2: fused MX dequantize (element codes + E8M0 scales -> bf16 / fp32), one pass over HBM.
+//
+// Replaces torchmx/mx_tensor.py:145-164 -> mx_quantization_utils.py:93-146 (decode), :415-432
+// (scale), utils.py:96-117 (fp4 unpack) and the repeat_interleave that materialises a full-size
+// scale tensor (13-37 aten launches on a GPU).
+//
+// out = RNE_target( decode(code) * 2^(s-127) ): decode is exact (F2FP to f16x2, or the integer
+// itself), the fp32 product is exact (<= 8 significant bits times a power of two, fp32
+// subnormals kept), so the single rounding happens in the final fp32 -> bf16 pack -- the same
+// value the reference's bf16 x bf16 -> bf16 product yields.
+//
+// Fast path (block 32, blocked axis innermost and contiguous): flat run of blocks, a thread owns
+// 16 codes (one 128-bit load; fp4: 16 bytes = one whole block) and writes 32/64 B (bf16) or
+// 64/128 B (fp32) with 256-bit stores.
+#include "mxq_common.cuh"
+
+namespace mxq {
+
+constexpr int kDequantThreads = 256;
+
+template <int ELEM>
+__device__ __forceinline__ void decode4(uint32_t word, float sc, float (&f)[4]) {
+    // four 1-byte codes in `word` (byte 0 = first element)
+    if constexpr (ELEM == MXQ_ELEM_INT8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = (float)(int)(int8_t)(word >> (8 * j)) * sc;
+    } else {
+        const uint32_t h0 = decode_pair_f16x2<ELEM>(word & 0xFFFF), h1 = decode_pair_f16x2<ELEM>(word >> 16);
+        f[0] = f16lo_to_f32(h0) * sc; f[1] = f16hi_to_f32(h0) * sc;
+        f[2] = f16lo_to_f32(h1) * sc; f[3] = f16hi_to_f32(h1) * sc;
+    }
+}
+
+// four packed fp4 bytes -> 8 elements; byte's HIGH nibble is the earlier element (utils.py:96-117)
+__device__ __forceinline__ void decode8_e2m1(uint32_t word, float sc, float (&f)[8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t h = decode_e2m1_byte_f16x2((word >> (8 * j)) & 0xFF);
+        f[2 * j] = f16hi_to_f32(h) * sc;
+        f[2 * j + 1] = f16lo_to_f32(h) * sc;
+    }
+}
+
+template <int N, bool F32>
+__device__ __forceinline__ void store_run(void* dst, int64_t first_elem, const float (&f)[N]) {
+    // N consecutive outputs starting at element `first_elem`; N*sizeof(T) is a multiple of 32 and aligned
+    if constexpr (F32) {
+        uint8_t* p = reinterpret_cast<uint8_t*>(dst) + first_elem * 4;
+#pragma unroll
+        for (int j = 0; j < N / 8; ++j) {
+            u32x8 o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = __float_as_uint(f[8 * j + k]);
+            stg256_stream(p + 32 * j, o);
+        }
+    } else {
+        uint8_t* p = reinterpret_cast<uint8_t*>(dst) + first_elem * 2;
+#pragma unroll
+        for (int j = 0; j < N / 16; ++j) {
+            u32x8 o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = pack_bf16x2(f[16 * j + 2 * k], f[16 * j + 2 * k + 1]);
+            stg256_stream(p + 32 * j, o);
+        }
+    }
+}
+
+template <int ELEM, bool F32>
+__global__ void __launch_bounds__(kDequantThreads) dequantize_b32_kernel(const uint8_t* __restrict__ codes, const uint8_t* __restrict__ scales,
+                                                                         void* __restrict__ dst, int64_t n_blocks) {
+    // chunk = 16 code bytes: half a block (1-byte codes) or a whole block (fp4)
+    constexpr int CPB = (ELEM == MXQ_ELEM_E2M1) ? 1 : 2;  // chunks per block
+    const int64_t n_chunks = n_blocks * CPB;
+    const int64_t stride = (int64_t)gridDim.x * kDequantThreads;
+    for (int64_t c = (int64_t)blockIdx.x * kDequantThreads + threadIdx.x; c < n_chunks; c += stride) {
+        const uint4 v = ldg128_stream(codes + c * 16);
+        const int s = __ldg(scales + c / CPB);
+        const float sc = scale_f32(s);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if constexpr (ELEM == MXQ_ELEM_E2M1) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float t[8];
+                decode8_e2m1(w[i], sc, t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[8 * i + k] = t[k];
+            }
+            store_run<32, F32>(dst, c * 32, f);
+        } else {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float t[4];
+                decode4<ELEM>(w[i], sc, t);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f[4 * i + k] = t[k];
+            }
+            store_run<16, F32>(dst, c * 16, f);
+        }
+    }
+}
+
+// ---- generic strided path ------------------------------------------------------------------------
+// One thread per output element; dst is C-contiguous in the logical shape, codes / scales are
+// arbitrary views (permuted, expanded, ...).  Covers every block size and every block_dim.
+struct StridedArgs {
+    int ndim, block_dim, block_size;
+    int64_t sizes[MXQ_MAX_DIMS], code_strides[MXQ_MAX_DIMS], scale_strides[MXQ_MAX_DIMS];
+    int64_t total;
+};
+
+template <int ELEM, bool F32>
+__global__ void dequantize_strided_kernel(const uint8_t* __restrict__ codes, const uint8_t* __restrict__ scales, void* __restrict__ dst,
+                                          StridedArgs a) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= a.total) return;
+    int64_t rem = o, coff = 0, soff = 0;
+    int nib = 0;
+#pragma unroll
+    for (int d = MXQ_MAX_DIMS - 1; d >= 0; --d) {
+        if (d < a.ndim) {
+            const int64_t idx = rem % a.sizes[d];
+            rem /= a.sizes[d];
+            if (d == a.block_dim) {
+                soff += (idx / a.block_size) * a.scale_strides[d];
+                if constexpr (ELEM == MXQ_ELEM_E2M1) { coff += (idx >> 1) * a.code_strides[d]; nib = (int)(idx & 1); }
+                else coff += idx * a.code_strides[d];
+            } else {
+                coff += idx * a.code_strides[d];
+                soff += idx * a.scale_strides[d];
+            }
+        }
+    }
+    uint32_t c = codes[coff];
+    if constexpr (ELEM == MXQ_ELEM_E2M1) c = nib ? (c & 0xF) : (c >> 4);
+    const float v = decode_one<ELEM>(c) * scale_f32(scales[soff]);
+    if constexpr (F32) reinterpret_cast<float*>(dst)[o] = v;
+    else reinterpret_cast<uint16_t*>(dst)[o] = (uint16_t)pack_bf16x2(v, 0.0f);
+}
+
+// ---- transposing path: blocked axis is second-to-last logically, but innermost physically --------
+// (what aten.t / transpose(-2,-1) of a quantized tensor produces: ops.py:122-158).  A 64x64 logical
+// tile is read along the physically contiguous (blocked) axis, decoded, transposed through shared
+// memory and written along the logically contiguous axis.
+template <int ELEM, bool F32>
+__global__ void __launch_bounds__(256) dequantize_transposed_kernel(const uint8_t* __restrict__ codes, const uint8_t* __restrict__ scales,
+                                                                    void* __restrict__ dst, int64_t batch, int64_t K, int64_t N,
+                                                                    int64_t code_batch_stride, int64_t code_row_stride,
+                                                                    int64_t scale_batch_stride, int64_t scale_row_stride, int block_size) {
+    // logical [batch, K, N] (K blocked); physical codes [batch][N rows][K contiguous]
+    __shared__ float tile[64][65];
+    const int64_t b = blockIdx.z;
+    const int64_t k0 = (int64_t)blockIdx.x * 64, n0 = (int64_t)blockIdx.y * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+    for (int r = ty; r < 64; r += 4) {
+        const int64_t n = n0 + r, k = k0 + tx;
+        float v = 0.0f;
+        if (n < N && k < K) {
+            uint32_t c;
+            if constexpr (ELEM == MXQ_ELEM_E2M1) {
+                c = codes[b * code_batch_stride + n * code_row_stride + (k >> 1)];
+                c = (k & 1) ? (c & 0xF) : (c >> 4);
+            } else {
+                c = codes[b * code_batch_stride + n * code_row_stride + k];
+            }
+            const int s = scales[b * scale_batch_stride + n * scale_row_stride + k / block_size];
+            v = decode_one<ELEM>(c) * scale_f32(s);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 64; r += 4) {
+        const int64_t k = k0 + r, n = n0 + tx;
+        if (k < K && n < N) {
+            const float v = tile[tx][r];
+            const int64_t o = (b * K + k) * N + n;
+            if constexpr (F32) reinterpret_cast<float*>(dst)[o] = v;
+            else reinterpret_cast<uint16_t*>(dst)[o] = (uint16_t)pack_bf16x2(v, 0.0f);
+        }
+    }
+}
+
+// ---- launchers -----------------------------------------------------------------------------------
+template <int ELEM, bool F32>
+static cudaError_t launch_flat(const void* codes, const uint8_t* scales, int64_t n_blocks, int block_size, void* dst, int sm_count,
+                               cudaStream_t stream) {
+    if (n_blocks == 0) return cudaSuccess;
+    if (block_size == 32 && ((uintptr_t)codes % 16) == 0 && ((uintptr_t)dst % 32) == 0) {
+        const int64_t n_chunks = n_blocks * ((ELEM == MXQ_ELEM_E2M1) ? 1 : 2);
+        const int64_t want = (n_chunks + kDequantThreads - 1) / kDequantThreads;
+        const int64_t cap = (int64_t)sm_count * 8 * 4;
+        const int grid = (int)(want < cap ? want : cap);
+        dequantize_b32_kernel<ELEM, F32><<<grid, kDequantThreads, 0, stream>>>((const uint8_t*)codes, scales, dst, n_blocks);
+        return cudaGetLastError();
+    }
+    // any other block size / alignment: the strided kernel on a 1-D view
+    StridedArgs a{};
+    a.ndim = 1; a.block_dim = 0; a.block_size = block_size;
+    a.sizes[0] = n_blocks * block_size; a.code_strides[0] = 1; a.scale_strides[0] = 1;
+    a.total = a.sizes[0];
+    const unsigned grid = (unsigned)((a.total + 255) / 256);
+    dequantize_strided_kernel<ELEM, F32><<<grid, 256, 0, stream>>>((const uint8_t*)codes, scales, dst, a);
+    return cudaGetLastError();
+}
+
+template <int ELEM, bool F32>
+static cudaError_t launch_strided(const void* codes, const uint8_t* scales, int ndim, const int64_t* sizes, const int64_t* cs,
+                                  const int64_t* ss, int block_dim, int block_size, void* dst, cudaStream_t stream) {
+    StridedArgs a{};
+    a.ndim = ndim; a.block_dim = block_dim; a.block_size = block_size;
+    a.total = 1;
+    for (int d = 0; d < ndim; ++d) { a.sizes[d] = sizes[d]; a.code_strides[d] = cs[d]; a.scale_strides[d] = ss[d]; a.total *= sizes[d]; }
+    if (a.total == 0) return cudaSuccess;
+    // transposing fast case: logical [..., K, N], blocked dim K = ndim-2 with unit code stride, rows (N) strided,
+    // leading dims collapsible into one batch index with uniform strides
+    if (ndim >= 2 && block_dim == ndim - 2 && cs[ndim - 2] == 1 && ss[ndim - 2] == 1) {
+        bool ok = true;
+        int64_t batch = 1, cbs = 0, sbs = 0;
+        // collapse leading dims right-to-left: stride[d] must equal stride[d+1]*size[d+1]
+        int64_t exp_c = 0, exp_s = 0;
+        bool first = true;
+        for (int d = ndim - 3; d >= 0; --d) {
+            if (sizes[d] == 1) continue;
+            if (first) { cbs = cs[d]; sbs = ss[d]; exp_c = cs[d] * sizes[d]; exp_s = ss[d] * sizes[d]; first = false; }
+            else { if (cs[d] != exp_c || ss[d] != exp_s) { ok = false; break; } exp_c *= sizes[d]; exp_s *= sizes[d]; }
+            batch *= sizes[d];
+        }
+        const int64_t K = sizes[ndim - 2], N = sizes[ndim - 1];
+        if (ok && batch <= 65535 && (N + 63) / 64 <= 65535) {
+            dim3 grid((unsigned)((K + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)batch);
+            dequantize_transposed_kernel<ELEM, F32><<<grid, 256, 0, stream>>>((const uint8_t*)codes, scales, dst, batch, K, N, cbs, cs[ndim - 1], sbs,
+                                                                              ss[ndim - 1], block_size);
+            return cudaGetLastError();
+        }
+    }
+    const unsigned grid = (unsigned)((a.total + 255) / 256);
+    dequantize_strided_kernel<ELEM, F32><<<grid, 256, 0, stream>>>((const uint8_t*)codes, scales, dst, a);
+    return cudaGetLastError();
+}
+
+#define MXQ_DISPATCH_ELEM_DT(elem, f32, CALL)                                                    \
+    switch (elem) {                                                                              \
+    case MXQ_ELEM_E4M3: return f32 ? CALL(MXQ_ELEM_E4M3, true) : CALL(MXQ_ELEM_E4M3, false);     \
+    case MXQ_ELEM_E3M2: return f32 ? CALL(MXQ_ELEM_E3M2, true) : CALL(MXQ_ELEM_E3M2, false);     \
+    case MXQ_ELEM_E2M3: return f32 ? CALL(MXQ_ELEM_E2M3, true) : CALL(MXQ_ELEM_E2M3, false);     \
+    case MXQ_ELEM_E2M1: return f32 ? CALL(MXQ_ELEM_E2M1, true) : CALL(MXQ_ELEM_E2M1, false);     \
+    case MXQ_ELEM_INT8: return f32 ? CALL(MXQ_ELEM_INT8, true) : CALL(MXQ_ELEM_INT8, false);     \
+    case MXQ_ELEM_E5M2: return f32 ? CALL(MXQ_ELEM_E5M2, true) : CALL(MXQ_ELEM_E5M2, false);     \
+    default: return cudaErrorInvalidValue;                                                       \
+    }
+
+cudaError_t launch_dequantize(const void* codes, const uint8_t* scales, int64_t n_blocks, int block_size, int elem, int dst_dtype, void* dst,
+                              int sm_count, cudaStream_t stream) {
+    const bool f32 = dst_dtype == MXQ_HP_F32;
+#define CALL(E, F) launch_flat<E, F>(codes, scales, n_blocks, block_size, dst, sm_count, stream)
+    MXQ_DISPATCH_ELEM_DT(elem, f32, CALL)
+#undef CALL
+}
+
+cudaError_t launch_dequantize_strided(const void* codes, const uint8_t* scales, int ndim, const int64_t* sizes, const int64_t* cs,
+                                      const int64_t* ss, int block_dim, int block_size, int elem, int dst_dtype, void* dst,
+                                      cudaStream_t stream) {
+    const bool f32 = dst_dtype == MXQ_HP_F32;
+#define CALL(E, F) launch_strided<E, F>(codes, scales, ndim, sizes, cs, ss, block_dim, block_size, dst, stream)
+    MXQ_DISPATCH_ELEM_DT(elem, f32, CALL)
+#undef CALL
+}
+
+}  // namespace mxq

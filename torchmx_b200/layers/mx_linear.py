@@ -1,0 +1,52 @@
+"""MXInferenceLinear: nn.Linear whose weight is pre-quantized to MX and whose activation is
+quantized on every forward (reference: /root/reference/torchmx/layers/mx_linear.py:8-95).
+
+forward = K1 (activation quantize) -> MX matmul (aten.linear / addmm override -> K3 tensor-core
+kernel, or the dequantize path when the operands do not qualify).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from ..config import QLinearConfig
+from ..mx_tensor import MXTensor
+
+
+class MXInferenceLinear(torch.nn.Linear):
+    def extra_repr(self) -> str:
+        return f"{super().extra_repr()}, qconfig={self.qconfig}"
+
+    @classmethod
+    @torch.no_grad()
+    def from_float(cls, mod: torch.nn.Linear, qconfig: QLinearConfig) -> "MXInferenceLinear":
+        """Swap-in constructor (reference: mx_linear.py:21-59): the module skeleton is built on the
+        meta device, the weight is quantized once unless it lives on `meta` itself (accelerate
+        offload), the bias object is shared with the source module."""
+        with torch.device("meta"):
+            new = cls(in_features=mod.in_features, out_features=mod.out_features, bias=False)
+        new.qconfig = qconfig
+        w = mod.weight.data
+        if w.device.type != "meta":
+            wc = qconfig.weights_config
+            new.weight = torch.nn.Parameter(MXTensor.to_mx(w, wc.elem_dtype, wc.block_size), requires_grad=False)
+        new.bias = mod.bias
+        return new
+
+    def _weight_mx(self) -> MXTensor:
+        w = self.weight.data
+        if isinstance(w, MXTensor):
+            return self.weight
+        # weights that were on `meta` at conversion time arrive high-precision (often fp32) at call time
+        # (reference: mx_linear.py:68-92): quantize on the fly, leave self.weight untouched
+        wc = self.qconfig.weights_config
+        return MXTensor.to_mx(w.to(torch.bfloat16), wc.elem_dtype, wc.block_size)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        ac = self.qconfig.activations_config
+        x_mx = MXTensor.to_mx(x, ac.elem_dtype, ac.block_size)
+        bias = self.bias
+        if not isinstance(self.weight.data, MXTensor) and bias is not None:
+            bias = bias.to(torch.bfloat16)
+        return F.linear(x_mx, self._weight_mx(), bias)

@@ -1,0 +1,60 @@
+"""Model surgery: swap nn.Linear for MXInferenceLinear in place
+(reference: /root/reference/torchmx/quant_api.py:161-215).
+
+`quantize_llm_` / the torchao tensor-subclass inserter of the reference depend on
+transformers==4.44 attention internals and on torchao; they are outside the hot-path scope
+ and are not provided.
+"""
+from __future__ import annotations
+
+from pprint import pformat
+from typing import Callable, Optional
+
+import torch
+
+from .config import QLinearConfig
+from .layers.mx_linear import MXInferenceLinear
+from .utils import get_logger
+
+logger = get_logger(__name__)
+
+
+def _swap_children(model: torch.nn.Module, replacement_fn: Callable, filter_fn: Callable, on_visit: Optional[Callable] = None,
+                   prefix: str = "") -> None:
+    """Depth-first walk; a matching child is replaced and NOT descended into
+    (reference: quant_api.py:161-185)."""
+    for name, child in list(model.named_children()):
+        fqn = f"{prefix}.{name}" if prefix else name
+        if on_visit:
+            on_visit(fqn)
+        if filter_fn(child, fqn):
+            setattr(model, name, replacement_fn(child))
+        else:
+            _swap_children(child, replacement_fn, filter_fn, on_visit, fqn)
+
+
+def quantize_linear_(model: torch.nn.Module, qconfig: QLinearConfig, layer_filter: Optional[Callable[[str], bool]] = None) -> None:
+    """Replace every module whose type is exactly `torch.nn.Linear` (lm_head included) with
+    `MXInferenceLinear.from_float(mod, qconfig)`, in place (reference: quant_api.py:188-215).
+
+    `layer_filter(fqn) -> bool` is a B200-side extension used by the layer-sharded multi-GPU
+    driver: only layers whose qualified name passes the filter are quantized by this rank.
+    """
+    logger.info("Quantizing the model by swapping nn.Linear with TorchMX's MXInferenceLinear")
+    logger.warning("This method only replaces/quantizes the linear layers. Use this as an approximation as we do not "
+                   "quantize QKV and other stuff. Use this only when a specific attention layer is not implemented.")
+    logger.info(f"Quantizing Linear layers with config:\n{pformat(qconfig)}\n")
+    try:
+        from tqdm import tqdm
+        bar = tqdm(desc="Quantizing linear layers in model...")
+        on_visit = lambda fqn: bar.update(1)  # noqa: E731
+    except Exception:  # tqdm is optional
+        bar, on_visit = None, None
+    _swap_children(
+        model,
+        replacement_fn=lambda mod: MXInferenceLinear.from_float(mod, qconfig),
+        filter_fn=lambda mod, fqn: type(mod) is torch.nn.Linear and (layer_filter is None or layer_filter(fqn)),
+        on_visit=on_visit,
+    )
+    if bar is not None:
+        bar.close()
