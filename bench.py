@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MX quantize / dequantize hot path on B200.
+
+Workload (BASELINE.json configs[1]): quantize/dequantize sweep over a 16384 x 16384 bf16 tensor
+for all element types (float8_e4m3, float6_e3m2, float6_e2m3, float4_e2m1, int8), block_size 32.
+One "step" = MXTensor.to_mx followed by MXTensor.to_dtype(bfloat16) for each of the five element
+types (10 kernel launches).  Metric: algorithmic GB/s = (2 + code + 1/32 bytes per element, once
+for quantize and once for dequantize) / device time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU): the tensors are independent, every rank runs the
+same sweep on its own GPU (weak scaling, no data-path collective); time = max over ranks.
+`--impl reference` times the CPU oracle (oracle/, the restatement of the reference's own CPU
+path -- the Python reference itself cannot travel to the GPU box) with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ELEMS = ["float8_e4m3", "float6_e3m2", "float6_e2m3", "float4_e2m1", "int8"]
+ROWS = COLS = 16384
+BLOCK = 32
+METRIC = "to_mx/to_dtype GB/s (algorithmic bytes: quantize + dequantize->bf16, 16384x16384 bf16, all elem dtypes, block 32)"
+
+
+def code_bytes(elem: str) -> float:
+    return 0.5 if elem == "float4_e2m1" else 1.0
+
+
+def algo_bytes(elem: str, n_elems: int) -> float:
+    """bytes one quantize (or one dequantize->bf16) of n_elems must move: 2 B hp + code + 1/32 B scale"""
+    return n_elems * (2.0 + code_bytes(elem) + 1.0 / BLOCK)
+
+
+def step_bytes(n_elems: int) -> float:
+    return sum(2.0 * algo_bytes(e, n_elems) for e in ELEMS)
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key: str):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+_CPU_BUFS = {}
+
+
+def cpu_port_throughput(rows: int, threads: int, repeats: int = 1):
+    """GB/s of the CPU oracle (the port of the reference's CPU path) on `rows` x 16384 of the workload."""
+    import numpy as np
+    from oracle import mx_oracle as mxo
+    mxo.lib()
+    if rows not in _CPU_BUFS:
+        rng = np.random.default_rng(0)
+        _CPU_BUFS[rows] = (mxo.f32_to_bf16_bits(rng.standard_normal((rows, COLS), dtype=np.float32)),
+                           np.zeros((rows, COLS), dtype=np.uint16), np.zeros((rows, COLS // BLOCK), dtype=np.uint8),
+                           np.zeros((rows, COLS), dtype=np.uint8), np.zeros((rows, COLS // 2), dtype=np.uint8))
+    x, out, scales, codes_full, codes_half = _CPU_BUFS[rows]
+    n = x.size
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for e in ELEMS:
+            codes = codes_half if e == "float4_e2m1" else codes_full
+            mxo.quantize_into(x, e, BLOCK, scales, codes, threads=threads)
+            mxo.dequantize_into(codes, scales, e, BLOCK, out, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return step_bytes(n) / best / 1e9, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port), all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = 1024  # 1/16 of the workload per step: ~16.8 M elements x 5 dtypes x (quantize + dequantize)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_throughput(rows, threads)
+    times = []
+    for _ in range(args.steps):
+        _, dt = cpu_port_throughput(rows, threads)
+        times.append(dt)
+    total = sum(times)
+    value = step_bytes(rows * COLS) * args.steps / total / 1e9
+    sample = f"{rows}x{COLS} bf16 rows of the 16384x16384 workload per step (1/16), all 5 elem dtypes, quantize+dequantize"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8 codes / f32 scaling arithmetic", "data": "synthetic",
+        "config": {"workload": "quantize/dequantize sweep 16384x16384 bf16, all elem dtypes, block 32 (BASELINE configs[1])",
+                   "sample": sample},
+        "cpu_baseline": {"value": round(value, 4), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torchmx_b200  # noqa: F401  registers the ops; raises if libmxq.so is missing
+    from torchmx_b200 import _C, dtypes
+    from torchmx_b200.mx_tensor import MXTensor
+    _C.lib()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_elems = ROWS * COLS
+    etypes = [dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[e] for e in ELEMS]
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # three rotating 512 MiB inputs (each > 126 MB L2), N(0,1) with a per-row power-of-two spread
+    xs = []
+    for _ in range(3):
+        x = torch.randn(ROWS, COLS, dtype=torch.bfloat16, device=dev, generator=g)
+        x *= torch.exp2(torch.randint(-20, 20, (ROWS, 1), device=dev, generator=g).float()).to(torch.bfloat16)
+        xs.append(x)
+
+    def step(i, ev=None):
+        x = xs[i % 3]
+        for j, et in enumerate(etypes):
+            if ev is not None:
+                ev[j][0].record()
+            m = MXTensor.to_mx(x, et, BLOCK)
+            if ev is not None:
+                ev[j][1].record()
+            y = m.to_dtype(torch.bfloat16)
+            if ev is not None:
+                ev[j][2].record()
+        return y
+
+    for i in range(args.warmup):
+        step(i)
+    # per-launch events (on the launching = current stream) for the roofline of the dominant kernel
+    evs = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in ELEMS] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t_start.record()
+    for i in range(args.steps):
+        step(i, evs[i])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * step_bytes(n_elems) * args.steps / (elapsed_ms * 1e-3) / 1e9
+
+    # ---- per-kernel durations -> roofline of the kernel with the largest share of the step
+    q_ms = {e: statistics.mean(evs[i][j][0].elapsed_time(evs[i][j][1]) for i in range(args.steps)) for j, e in enumerate(ELEMS)}
+    d_ms = {e: statistics.mean(evs[i][j][1].elapsed_time(evs[i][j][2]) for i in range(args.steps)) for j, e in enumerate(ELEMS)}
+    kernels = {}
+    for e in ELEMS:
+        kernels[f"quantize_b32_bf16_kernel<{e}>"] = {"ms": q_ms[e], "GB/s": algo_bytes(e, n_elems) / (q_ms[e] * 1e-3) / 1e9}
+        kernels[f"dequantize_b32_kernel<{e},bf16>"] = {"ms": d_ms[e], "GB/s": algo_bytes(e, n_elems) / (d_ms[e] * 1e-3) / 1e9}
+    families = {
+        "dequantize_b32_kernel (1-byte codes -> bf16)": [f"dequantize_b32_kernel<{e},bf16>" for e in ELEMS if e != "float4_e2m1"],
+        "quantize_b32_bf16_kernel (bf16 -> 1-byte codes)": [f"quantize_b32_bf16_kernel<{e}>" for e in ELEMS if e != "float4_e2m1"],
+    }
+    fam_ms = {k: sum(kernels[n]["ms"] for n in v) for k, v in families.items()}
+    dom = max(fam_ms, key=fam_ms.get)
+    dom_launch_ms = fam_ms[dom] / len(families[dom])
+    peak, peak_src = measured_peak_gbs()
+    achieved = algo_bytes("float8_e4m3", n_elems) / (dom_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "frac_of_8TBps": round(achieved / 8000.0, 4), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes("float8_e4m3", n_elems), "avg_launch_us": round(dom_launch_ms * 1e3, 2),
+                "traffic": ncu_traffic(dom), "share_of_step": round(fam_ms[dom] / (elapsed_ms / args.steps), 4)}
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e_steps = max(1, min(args.steps, 5))
+    xh = torch.empty(ROWS, COLS, dtype=torch.bfloat16).pin_memory()
+    xh.copy_(xs[0])
+    yh = torch.empty(ROWS, COLS, dtype=torch.bfloat16).pin_memory()
+    ch = {1.0: torch.empty(ROWS, COLS, dtype=torch.uint8).pin_memory(), 0.5: torch.empty(ROWS, COLS // 2, dtype=torch.uint8).pin_memory()}
+    sh = torch.empty(ROWS, COLS // BLOCK, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        h2d = d2h = 0
+        for et in etypes:
+            c_host = ch[code_bytes(et.name)]
+            xd = xh.to(dev, non_blocking=True)                      # H2D: the step's input
+            m = MXTensor.to_mx(xd, et, BLOCK)
+            c_host.view(m._data.dtype).copy_(m._data, non_blocking=True)   # D2H: the quantized result
+            sh.copy_(m._scale_e8m0, non_blocking=True)
+            cd = c_host.view(m._data.dtype).to(dev, non_blocking=True)     # H2D: codes + scales back in
+            sd = sh.to(dev, non_blocking=True)
+            m2 = MXTensor(sd, cd, et, BLOCK, torch.bfloat16)
+            yh.copy_(m2.to_dtype(torch.bfloat16), non_blocking=True)       # D2H: the dequantized result
+            h2d += xh.numel() * 2 + c_host.numel() + sh.numel()
+            d2h += c_host.numel() + sh.numel() + yh.numel() * 2
+        torch.cuda.current_stream().synchronize()
+        return h2d, d2h
+
+    h2d = d2h = 0
+    if args.skip_e2e:
+        e2e_steps = 0
+    else:
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h2d, d2h = e2e_step()
+    barrier()
+    e2e_s = max(time.perf_counter() - t0, 1e-9)
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * step_bytes(n_elems) * e2e_steps / e2e_s / 1e9 if e2e_steps else 0.0
+
+    if rank == 0:
+        cpu_threads = os.cpu_count() or 1
+        cpu_rows = 2048
+        cpu_value, cpu_dt = (None, None)
+        if not args.skip_cpu:
+            cpu_port_throughput(256, cpu_threads)  # warm the pages / thread pool
+            cpu_value, cpu_dt = cpu_port_throughput(cpu_rows, cpu_threads, repeats=2)
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 codes / f32 scaling arithmetic", "data": "synthetic",
+            "config": {"workload": "quantize/dequantize sweep 16384x16384 bf16, all elem dtypes (fp8 e4m3, fp6 e3m2/e2m3, fp4 e2m1, int8), "
+                                   "block 32 (BASELINE configs[1])",
+                       "step": "to_mx + to_dtype(bf16) per elem dtype = 10 launches", "l2": "inputs (512 MiB, 3 rotating) larger than L2",
+                       "parallelism": f"independent tensors per GPU x{world}, no collective"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": round(1e3 * e2e_s / max(e2e_steps, 1), 2), "note": "pinned host buffers, PCIe copies in the timed region"},
+            "gpu_launches": args.steps * 2 * len(ELEMS),
+            "roofline": roofline,
+            "cpu_baseline": None if cpu_value is None else {
+                "value": round(cpu_value, 3), "unit": "GB/s", "cores": cpu_threads, "kind": "port",
+                "sample": f"{cpu_rows}x{COLS} rows of the workload (1/8), all 5 elem dtypes, quantize+dequantize, best of 2, {cpu_dt:.2f} s"},
+            "kernels": {k: {"us": round(v["ms"] * 1e3, 2), "GB/s": round(v["GB/s"], 1)} for k, v in kernels.items()},
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

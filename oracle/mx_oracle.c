@@ -307,11 +307,9 @@ static inline float decode_elem(uint8_t c, int elem) {
  * (mx_tensor.py:157-162: both factors are cast to target_dtype first), which is the exact
  * product rounded once.  target_is_f32 == 1: fp32 product.
  */
-int mxo_dequantize(const uint8_t *codes, const uint8_t *scales, int64_t n_blocks, int block_size,
-                   int elem, int target_is_f32, void *dst) {
-    if (elem < 0 || elem >= MXO_NELEM || block_size < 1) return -2;
-    if (elem == MXO_E2M1 && (block_size & 1)) return -3;
-    for (int64_t b = 0; b < n_blocks; ++b) {
+static void dequantize_range(const uint8_t *codes, const uint8_t *scales, int64_t b0, int64_t b1, int block_size,
+                             int elem, int target_is_f32, void *dst) {
+    for (int64_t b = b0; b < b1; ++b) {
         const float sc = fp_scale(scales[b]);
         for (int i = 0; i < block_size; ++i) {
             const int64_t idx = b * block_size + i;
@@ -329,7 +327,42 @@ int mxo_dequantize(const uint8_t *codes, const uint8_t *scales, int64_t n_blocks
             else ((uint16_t *)dst)[idx] = f32_to_bf16_rne(v);
         }
     }
+}
+
+typedef struct {
+    const uint8_t *codes, *scales; int64_t b0, b1; int block_size, elem, target_is_f32; void *dst;
+} djob_t;
+
+static void *djob_main(void *p) {
+    djob_t *j = (djob_t *)p;
+    dequantize_range(j->codes, j->scales, j->b0, j->b1, j->block_size, j->elem, j->target_is_f32, j->dst);
+    return NULL;
+}
+
+int mxo_dequantize_mt(const uint8_t *codes, const uint8_t *scales, int64_t n_blocks, int block_size,
+                      int elem, int target_is_f32, void *dst, int n_threads) {
+    if (elem < 0 || elem >= MXO_NELEM || block_size < 1) return -2;
+    if (elem == MXO_E2M1 && (block_size & 1)) return -3;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads == 1 || n_blocks < 4 * n_threads) {
+        dequantize_range(codes, scales, 0, n_blocks, block_size, elem, target_is_f32, dst);
+        return 0;
+    }
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    djob_t *jobs = (djob_t *)malloc(sizeof(djob_t) * (size_t)n_threads);
+    for (int t = 0; t < n_threads; ++t) {
+        jobs[t] = (djob_t){codes, scales, n_blocks * t / n_threads, n_blocks * (t + 1) / n_threads,
+                           block_size, elem, target_is_f32, dst};
+        pthread_create(&th[t], NULL, djob_main, &jobs[t]);
+    }
+    for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    free(th); free(jobs);
     return 0;
+}
+
+int mxo_dequantize(const uint8_t *codes, const uint8_t *scales, int64_t n_blocks, int block_size,
+                   int elem, int target_is_f32, void *dst) {
+    return mxo_dequantize_mt(codes, scales, n_blocks, block_size, elem, target_is_f32, dst, 1);
 }
 
 /* pack/unpack helpers: torchmx/utils.py:96-145 (flattened tensor, even element -> high nibble) */

@@ -55,6 +55,8 @@ def lib() -> ctypes.CDLL:
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
             ctypes.c_int, ctypes.c_void_p,
         ]
+        L.mxo_dequantize_mt.restype = ctypes.c_int
+        L.mxo_dequantize_mt.argtypes = L.mxo_dequantize.argtypes + [ctypes.c_int]
         L.mxo_gemm_nt_bf16.restype = ctypes.c_int
         L.mxo_gemm_nt_bf16.argtypes = [
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
@@ -115,7 +117,7 @@ def quantize(x: np.ndarray, elem: str, block_size: int, hw_exact: bool = False,
 
 
 def dequantize(codes: np.ndarray, scales: np.ndarray, elem: str, block_size: int,
-               target: str = "bf16", block_dim: int = -1) -> np.ndarray:
+               target: str = "bf16", block_dim: int = -1, threads: int = 1) -> np.ndarray:
     """Inverse op.  `codes` may be any (possibly permuted) view whose blocked axis is
     `block_dim`; the result is C-contiguous in the logical shape, as FromMXConstrFunc returns it
     (mx_tensor.py:323).  target 'bf16' -> uint16 bit patterns, 'f32' -> float32."""
@@ -143,10 +145,28 @@ def dequantize(codes: np.ndarray, scales: np.ndarray, elem: str, block_size: int
             prod = (v * sc).astype(np.float32).reshape(out_shape)
         out = prod if target == "f32" else f32_to_bf16_bits(prod)
     else:
-        rc = lib().mxo_dequantize(_ptr(c), _ptr(s), n_blocks, block_size, ELEM_IDS[elem],
-                                  int(target == "f32"), _ptr(out))
+        rc = lib().mxo_dequantize_mt(_ptr(c), _ptr(s), n_blocks, block_size, ELEM_IDS[elem],
+                                     int(target == "f32"), _ptr(out), threads)
         assert rc == 0, rc
     return np.ascontiguousarray(np.moveaxis(out, -1, bd))
+
+
+def quantize_into(x: np.ndarray, elem: str, block_size: int, scales: np.ndarray, codes: np.ndarray,
+                  hw_exact: bool = False, threads: int = 1) -> None:
+    """allocation-free variant for timing (bench.py cpu_baseline): outputs are caller-provided."""
+    assert x.flags.c_contiguous and scales.flags.c_contiguous and codes.flags.c_contiguous
+    rc = lib().mxo_quantize(_ptr(x), int(x.dtype == np.float32), x.size // block_size, block_size, ELEM_IDS[elem],
+                            int(hw_exact), _ptr(scales), _ptr(codes), threads)
+    assert rc == 0, rc
+
+
+def dequantize_into(codes: np.ndarray, scales: np.ndarray, elem: str, block_size: int, out: np.ndarray,
+                    threads: int = 1) -> None:
+    """allocation-free variant for timing: blocked axis last, everything contiguous."""
+    assert codes.flags.c_contiguous and scales.flags.c_contiguous and out.flags.c_contiguous
+    rc = lib().mxo_dequantize_mt(_ptr(codes), _ptr(scales), scales.size, block_size, ELEM_IDS[elem],
+                                 int(out.dtype == np.float32), _ptr(out), threads)
+    assert rc == 0, rc
 
 
 def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:

@@ -8,8 +8,8 @@
 #include "mxq_common.cuh"
 
 namespace mxq {
-cudaError_t launch_quantize(const void*, int, int64_t, int, int, unsigned, void*, uint8_t*, int, int, cudaStream_t);
-cudaError_t launch_dequantize(const void*, const uint8_t*, int64_t, int, int, int, void*, int, cudaStream_t);
+cudaError_t launch_quantize(const void*, int, int64_t, int, int, unsigned, void*, uint8_t*, int, int, int, cudaStream_t);
+cudaError_t launch_dequantize(const void*, const uint8_t*, int64_t, int, int, int, void*, int, int, int, cudaStream_t);
 cudaError_t launch_dequantize_strided(const void*, const uint8_t*, int, const int64_t*, const int64_t*, const int64_t*, int, int, int, int,
                                       void*, cudaStream_t);
 cudaError_t launch_transcode(const void*, int, int64_t, void*, int, cudaStream_t);
@@ -58,16 +58,17 @@ int sm_count_of(int device) {
 
 bool valid_elem(int e) { return e >= MXQ_ELEM_E4M3 && e <= MXQ_ELEM_E5M2; }
 
-// developer knobs (not part of the reference-facing contract): MXQ_QUANT_EPT = 8 | 16 | 32
-int quant_ept_override() {
-    static int v = -1;
-    if (v < 0) {
-        const char* s = getenv("MXQ_QUANT_EPT");
-        v = s ? atoi(s) : 0;
-        if (v != 8 && v != 16 && v != 32) v = 0;
-    }
-    return v;
+// developer knobs (not part of the reference-facing contract), read once:
+//   MXQ_QUANT_EPT = 8 | 16 | 32   elements per thread of the quantize fast path
+//   MXQ_DEQ_CB    = 16 | 32       code bytes per thread of the dequantize fast path
+//   MXQ_WAVES     = n             grid cap = SMs * 8 * n CTAs (grid-stride beyond that)
+int env_int(const char* name) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : 0;
 }
+int quant_ept_override() { static int v = env_int("MXQ_QUANT_EPT"); return (v == 8 || v == 16 || v == 32) ? v : 0; }
+int deq_cb_override() { static int v = env_int("MXQ_DEQ_CB"); return (v == 16 || v == 32) ? v : 0; }
+int waves_override() { static int v = env_int("MXQ_WAVES"); return v > 0 ? v : 0; }
 
 }  // namespace
 
@@ -89,7 +90,7 @@ int mxq_quantize(const void* src, int src_dtype, int64_t n_blocks, int block_siz
     DeviceScope scope(device);
     if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_quantize: selecting device");
     const cudaError_t e = mxq::launch_quantize(src, src_dtype, n_blocks, block_size, elem, flags, codes, scales, sm_count_of(scope.cur),
-                                               quant_ept_override(), (cudaStream_t)stream);
+                                               quant_ept_override(), waves_override(), (cudaStream_t)stream);
     return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_quantize: launch");
 }
 
@@ -103,7 +104,8 @@ int mxq_dequantize(const void* codes, const uint8_t* scales, int64_t n_blocks, i
     if (elem == MXQ_ELEM_E2M1 && ((n_blocks * block_size) & 1)) return fail(MXQ_ERR_INVALID, "mxq_dequantize: float4_e2m1 needs an even element count");
     DeviceScope scope(device);
     if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_dequantize: selecting device");
-    const cudaError_t e = mxq::launch_dequantize(codes, scales, n_blocks, block_size, elem, dst_dtype, dst, sm_count_of(scope.cur), (cudaStream_t)stream);
+    const cudaError_t e = mxq::launch_dequantize(codes, scales, n_blocks, block_size, elem, dst_dtype, dst, sm_count_of(scope.cur), deq_cb_override(), waves_override(),
+                                                 (cudaStream_t)stream);
     return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_dequantize: launch");
 }
 

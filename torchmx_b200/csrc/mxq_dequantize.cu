@@ -65,38 +65,53 @@ __device__ __forceinline__ void store_run(void* dst, int64_t first_elem, const f
     }
 }
 
-template <int ELEM, bool F32>
+template <int ELEM, bool F32, int CB>
 __global__ void __launch_bounds__(kDequantThreads) dequantize_b32_kernel(const uint8_t* __restrict__ codes, const uint8_t* __restrict__ scales,
-                                                                         void* __restrict__ dst, int64_t n_blocks) {
-    // chunk = 16 code bytes: half a block (1-byte codes) or a whole block (fp4)
-    constexpr int CPB = (ELEM == MXQ_ELEM_E2M1) ? 1 : 2;  // chunks per block
-    const int64_t n_chunks = n_blocks * CPB;
+                                                                         void* __restrict__ dst, int64_t n_code_bytes) {
+    // a thread owns CB = 16 or 32 consecutive code bytes; each 16-byte half is half a block (1-byte
+    // codes) or a whole block (fp4) and carries its own scale byte
+    constexpr int PER = (ELEM == MXQ_ELEM_E2M1) ? 2 : 1;  // elements per code byte
+    constexpr int NH = CB / 16;
+    const int64_t n_chunks = n_code_bytes / CB;
     const int64_t stride = (int64_t)gridDim.x * kDequantThreads;
     for (int64_t c = (int64_t)blockIdx.x * kDequantThreads + threadIdx.x; c < n_chunks; c += stride) {
-        const uint4 v = ldg128_stream(codes + c * 16);
-        const int s = __ldg(scales + c / CPB);
-        const float sc = scale_f32(s);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        if constexpr (ELEM == MXQ_ELEM_E2M1) {
-            float f[32];
+        uint32_t w[CB / 4];
+        if constexpr (CB == 32) {
+            const u32x8 v = ldg256_stream(codes + c * 32);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float t[8];
-                decode8_e2m1(w[i], sc, t);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) f[8 * i + k] = t[k];
-            }
-            store_run<32, F32>(dst, c * 32, f);
+            for (int k = 0; k < 8; ++k) w[k] = v.v[k];
         } else {
-            float f[16];
+            const uint4 v = ldg128_stream(codes + c * 16);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        }
+        int s[NH];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float t[4];
-                decode4<ELEM>(w[i], sc, t);
+        for (int h = 0; h < NH; ++h) s[h] = __ldg(scales + ((c * CB + 16 * h) * PER) / 32);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) f[4 * i + k] = t[k];
+        for (int h = 0; h < NH; ++h) {
+            const float sc = scale_f32(s[h]);
+            const int64_t e0 = (c * CB + 16 * h) * PER;
+            if constexpr (ELEM == MXQ_ELEM_E2M1) {
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float t[8];
+                    decode8_e2m1(w[4 * h + i], sc, t);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[8 * i + k] = t[k];
+                }
+                store_run<32, F32>(dst, e0, f);
+            } else {
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float t[4];
+                    decode4<ELEM>(w[4 * h + i], sc, t);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) f[4 * i + k] = t[k];
+                }
+                store_run<16, F32>(dst, e0, f);
             }
-            store_run<16, F32>(dst, c * 16, f);
         }
     }
 }
@@ -183,15 +198,21 @@ __global__ void __launch_bounds__(256) dequantize_transposed_kernel(const uint8_
 
 // ---- launchers -----------------------------------------------------------------------------------
 template <int ELEM, bool F32>
-static cudaError_t launch_flat(const void* codes, const uint8_t* scales, int64_t n_blocks, int block_size, void* dst, int sm_count,
-                               cudaStream_t stream) {
+static cudaError_t launch_flat(const void* codes, const uint8_t* scales, int64_t n_blocks, int block_size, void* dst, int sm_count, int cb,
+                               int waves, cudaStream_t stream) {
     if (n_blocks == 0) return cudaSuccess;
-    if (block_size == 32 && ((uintptr_t)codes % 16) == 0 && ((uintptr_t)dst % 32) == 0) {
-        const int64_t n_chunks = n_blocks * ((ELEM == MXQ_ELEM_E2M1) ? 1 : 2);
+    if (block_size == 32 && ((uintptr_t)codes % 32) == 0 && ((uintptr_t)dst % 32) == 0) {
+        const int64_t n_code_bytes = n_blocks * ((ELEM == MXQ_ELEM_E2M1) ? 16 : 32);
+        // measured on B200 (tools/quick_bench.py sweep): 32 code bytes per thread is best for 1-byte codes -> bf16
+        // (6.6 TB/s), 16 for fp4 and for every fp32 target (more store bytes per thread already)
+        if (cb != 16 && cb != 32) cb = (!F32 && ELEM != MXQ_ELEM_E2M1) ? 32 : 16;
+        if (n_code_bytes % cb) cb = 16;
+        const int64_t n_chunks = n_code_bytes / cb;
         const int64_t want = (n_chunks + kDequantThreads - 1) / kDequantThreads;
-        const int64_t cap = (int64_t)sm_count * 8 * 4;
+        const int64_t cap = waves > 0 ? (int64_t)sm_count * 8 * waves : (int64_t)0x7FFFFFFF;
         const int grid = (int)(want < cap ? want : cap);
-        dequantize_b32_kernel<ELEM, F32><<<grid, kDequantThreads, 0, stream>>>((const uint8_t*)codes, scales, dst, n_blocks);
+        if (cb == 32) dequantize_b32_kernel<ELEM, F32, 32><<<grid, kDequantThreads, 0, stream>>>((const uint8_t*)codes, scales, dst, n_code_bytes);
+        else dequantize_b32_kernel<ELEM, F32, 16><<<grid, kDequantThreads, 0, stream>>>((const uint8_t*)codes, scales, dst, n_code_bytes);
         return cudaGetLastError();
     }
     // any other block size / alignment: the strided kernel on a 1-D view
@@ -251,9 +272,9 @@ static cudaError_t launch_strided(const void* codes, const uint8_t* scales, int 
     }
 
 cudaError_t launch_dequantize(const void* codes, const uint8_t* scales, int64_t n_blocks, int block_size, int elem, int dst_dtype, void* dst,
-                              int sm_count, cudaStream_t stream) {
+                              int sm_count, int cb, int waves, cudaStream_t stream) {
     const bool f32 = dst_dtype == MXQ_HP_F32;
-#define CALL(E, F) launch_flat<E, F>(codes, scales, n_blocks, block_size, dst, sm_count, stream)
+#define CALL(E, F) launch_flat<E, F>(codes, scales, n_blocks, block_size, dst, sm_count, cb, waves, stream)
     MXQ_DISPATCH_ELEM_DT(elem, f32, CALL)
 #undef CALL
 }

@@ -188,15 +188,16 @@ __global__ void codes_generic_kernel(const T* __restrict__ src, const uint8_t* _
 // ---- launchers ---------------------------------------------------------------------------------
 template <int ELEM>
 static cudaError_t launch_quantize_elem(const void* src, int src_dtype, int64_t n_blocks, int block_size, unsigned flags, void* codes,
-                                        uint8_t* scales, int sm_count, int ept_override, cudaStream_t stream) {
+                                        uint8_t* scales, int sm_count, int ept_override, int waves, cudaStream_t stream) {
     if (n_blocks == 0) return cudaSuccess;
     const uintptr_t a_src = (uintptr_t)src, a_codes = (uintptr_t)codes;
     if (block_size == 32 && src_dtype == MXQ_HP_BF16 && (a_src % 32) == 0 && (a_codes % 32) == 0) {
-        int ept = ept_override ? ept_override : 16;
+        int ept = ept_override ? ept_override : 32;
         const int lpb = 32 / ept;
         const int64_t n_chunks = n_blocks * lpb;
         const int64_t want = (n_chunks + kQuantThreads - 1) / kQuantThreads;
-        const int64_t cap = (int64_t)sm_count * 8 * 4;  // grid-stride: a few waves of 8 resident CTAs per SM
+        // one chunk per thread measured fastest on B200 (6.7 TB/s vs 6.6 with a 4-wave grid-stride cap); MXQ_WAVES caps the grid
+        const int64_t cap = waves > 0 ? (int64_t)sm_count * 8 * waves : (int64_t)0x7FFFFFFF;
         const int grid = (int)(want < cap ? want : cap);
         const uint16_t* s16 = (const uint16_t*)src;
         uint8_t* c8 = (uint8_t*)codes;
@@ -220,14 +221,14 @@ static cudaError_t launch_quantize_elem(const void* src, int src_dtype, int64_t 
 }
 
 cudaError_t launch_quantize(const void* src, int src_dtype, int64_t n_blocks, int block_size, int elem, unsigned flags, void* codes,
-                            uint8_t* scales, int sm_count, int ept_override, cudaStream_t stream) {
+                            uint8_t* scales, int sm_count, int ept_override, int waves, cudaStream_t stream) {
     switch (elem) {
-    case MXQ_ELEM_E4M3: return launch_quantize_elem<MXQ_ELEM_E4M3>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, stream);
-    case MXQ_ELEM_E3M2: return launch_quantize_elem<MXQ_ELEM_E3M2>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, stream);
-    case MXQ_ELEM_E2M3: return launch_quantize_elem<MXQ_ELEM_E2M3>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, stream);
-    case MXQ_ELEM_E2M1: return launch_quantize_elem<MXQ_ELEM_E2M1>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, stream);
-    case MXQ_ELEM_INT8: return launch_quantize_elem<MXQ_ELEM_INT8>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, stream);
-    case MXQ_ELEM_E5M2: return launch_quantize_elem<MXQ_ELEM_E5M2>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, stream);
+    case MXQ_ELEM_E4M3: return launch_quantize_elem<MXQ_ELEM_E4M3>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, waves, stream);
+    case MXQ_ELEM_E3M2: return launch_quantize_elem<MXQ_ELEM_E3M2>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, waves, stream);
+    case MXQ_ELEM_E2M3: return launch_quantize_elem<MXQ_ELEM_E2M3>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, waves, stream);
+    case MXQ_ELEM_E2M1: return launch_quantize_elem<MXQ_ELEM_E2M1>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, waves, stream);
+    case MXQ_ELEM_INT8: return launch_quantize_elem<MXQ_ELEM_INT8>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, waves, stream);
+    case MXQ_ELEM_E5M2: return launch_quantize_elem<MXQ_ELEM_E5M2>(src, src_dtype, n_blocks, block_size, flags, codes, scales, sm_count, ept_override, waves, stream);
     default: return cudaErrorInvalidValue;
     }
 }
