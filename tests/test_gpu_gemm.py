@@ -1,0 +1,179 @@
+"""GPU tier: MX matmul (aten.mm / bmm / addmm / linear overrides).
+
+Parity definition (DESIGN.md "matmul parity"): the reference computes dequantize(A) @ dequantize(B)^T
+with a bf16 GEMM that accumulates in fp32 and rounds the result to bf16 once (torchmx/ops.py:18-19,
+29-41).  The dequantized operands are exact, so the only freedom is the fp32 accumulation order.
+Tolerance, written out: |out - ref| <= 2^-8 |ref| + 2^-18 * sum_k |a_k b_k|, with `ref` the same
+contraction evaluated in fp64 (one bf16 ulp of the result + fp32 accumulation slack).  The fallback
+path (operands that cannot use the tensor cores) must equal dequantize-then-aten-op EXACTLY, as the
+reference's own test_bmm demands (tests/test_mx_tensor.py:266-289).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import bf16_tensor, bits_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def mx():
+    import torchmx
+    from torchmx_b200 import _C
+    _C.lib()
+    return torchmx
+
+
+def _tol_check(out, A, B, bias=None, what=""):
+    ad, bd = A.to_dtype(torch.float32).double(), B.to_dtype(torch.float32).double()
+    ref = ad @ bd.transpose(-1, -2)
+    S = ad.abs() @ bd.abs().transpose(-1, -2)
+    if bias is not None:
+        ref = ref + bias.double()
+        S = S + bias.double().abs()
+    err = (out.double() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 2.0 ** -18 * S + 1e-30
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{what}: {bad}/{err.numel()} outside tolerance, worst err/S {(err / (S + 1e-30)).max().item():.3e}"
+    assert not torch.isnan(out).any()
+
+
+CASES = [
+    # M, N, K, elem A, elem B, bias, batch, per-block exponent spread
+    (128, 128, 128, "float8_e4m3", "float8_e4m3", False, 0, 0),
+    (128, 256, 256, "float8_e4m3", "float6_e3m2", False, 0, 0),
+    (256, 512, 512, "float8_e4m3", "float6_e3m2", False, 0, 8),
+    (100, 200, 384, "float8_e4m3", "float4_e2m1", True, 0, 0),
+    (1, 4096, 1024, "float8_e4m3", "float6_e3m2", False, 0, 0),
+    (33, 130, 1024, "float6_e2m3", "float6_e3m2", True, 0, 20),
+    (300, 77, 640, "float6_e3m2", "float6_e2m3", False, 0, 30),
+    (512, 512, 128, "float8_e4m3", "float6_e3m2", False, 4, 0),
+    (77, 300, 256, "float4_e2m1", "float4_e2m1", False, 3, 0),
+    (1024, 2048, 2048, "float8_e4m3", "float6_e3m2", False, 0, 4),
+]
+
+
+@pytest.mark.parametrize("M,N,K,ea,eb,bias,batch,spread", CASES)
+def test_tensor_core_matmul(mx, M, N, K, ea, eb, bias, batch, spread):
+    from torchmx import dtypes
+    from torchmx.mx_tensor import MXTensor
+    from torchmx_b200 import mx_gemm
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
+    sa, sb = ((batch, M, K), (batch, N, K)) if batch else ((M, K), (N, K))
+    a = torch.randn(*sa, device=DEV, dtype=torch.bfloat16, generator=g)
+    b = torch.randn(*sb, device=DEV, dtype=torch.bfloat16, generator=g)
+    if spread:
+        for t in (a, b):
+            e = torch.randint(-spread, spread, (*t.shape[:-1], K // 32), device=DEV, generator=g).float()
+            t *= torch.exp2(e).repeat_interleave(32, -1).to(torch.bfloat16)
+    A = MXTensor.to_mx(a, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[ea], 32)
+    B = MXTensor.to_mx(b, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[eb], 32)
+    bias_t = torch.randn(N, device=DEV, dtype=torch.bfloat16, generator=g) if bias else None
+    before = dict(mx_gemm.stats)
+    if batch:
+        out = torch.bmm(A, B.transpose(1, 2))
+    else:
+        out = torch.nn.functional.linear(A, B, bias_t)
+    assert mx_gemm.stats["tensor_core"] == before["tensor_core"] + 1, "expected the tcgen05 path"
+    assert out.dtype == torch.bfloat16 and out.shape == ((batch, M, N) if batch else (M, N))
+    _tol_check(out, A, B, bias_t, f"{M}x{N}x{K} {ea}x{eb}")
+
+
+def test_matmul_entry_points_agree(mx):
+    """mm, addmm, linear (2-D and 3-D input, inference_mode and no_grad) and 4-D matmul all reach the
+    same kernel and must agree bit-for-bit with each other."""
+    from torchmx import dtypes
+    from torchmx.mx_tensor import MXTensor
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(4, 48, 256, device=DEV, dtype=torch.bfloat16, generator=g)
+    w = torch.randn(320, 256, device=DEV, dtype=torch.bfloat16, generator=g)
+    bias = torch.randn(320, device=DEV, dtype=torch.bfloat16, generator=g)
+    X = MXTensor.to_mx(x, dtypes.float8_e4m3, 32)
+    X2 = MXTensor.to_mx(x.reshape(-1, 256), dtypes.float8_e4m3, 32)
+    W = MXTensor.to_mx(w, dtypes.float6_e3m2, 32)
+    with torch.no_grad():
+        y_lin3 = torch.nn.functional.linear(X, W, bias)
+        y_lin2 = torch.nn.functional.linear(X2, W, bias)
+        y_mm = torch.mm(X2, W.t())
+        y_addmm = torch.addmm(bias, X2, W.t())
+        y_nobias = torch.nn.functional.linear(X2, W)
+    with torch.inference_mode():
+        y_inf = torch.nn.functional.linear(X, W, bias)
+    assert torch.equal(y_lin3.reshape(-1, 320), y_lin2)
+    assert torch.equal(y_inf, y_lin3)
+    assert torch.equal(y_addmm, y_lin2)
+    assert torch.equal(y_mm, y_nobias)
+    _tol_check(y_lin2, X2, W, bias, "linear")
+    # attention-shaped 4-D matmuls (layers/mx_llama_attention.py:215-217, 243)
+    q = torch.randn(2, 4, 64, 128, device=DEV, dtype=torch.bfloat16, generator=g)
+    k = torch.randn(2, 4, 96, 128, device=DEV, dtype=torch.bfloat16, generator=g)
+    Q, K = MXTensor.to_mx(q, dtypes.float8_e4m3, 32), MXTensor.to_mx(k, dtypes.float6_e3m2, 32)
+    s = torch.matmul(Q, K.transpose(2, 3))
+    assert s.shape == (2, 4, 64, 96)
+    _tol_check(s, Q, K, None, "q @ k^T")
+    # P @ V with V quantized along the sequence (block dim second to last after the transpose)
+    pm = torch.rand(2, 4, 64, 128, device=DEV, dtype=torch.bfloat16, generator=g)
+    v = torch.randn(2, 4, 128, 64, device=DEV, dtype=torch.bfloat16, generator=g)
+    P = MXTensor.to_mx(pm, dtypes.float8_e4m3, 32)
+    Vt = MXTensor.to_mx(v.transpose(2, 3).contiguous(), dtypes.float6_e3m2, 32)  # [.., 64, 128] blocked along seq
+    o = torch.matmul(P, Vt.transpose(2, 3))
+    _tol_check(o, P, Vt, None, "p @ v")
+
+
+@pytest.mark.parametrize("ea,ew", [("float8_e4m3", "float6_e3m2"), ("float8_e4m3", "float4_e2m1"), ("float6_e2m3", "float6_e3m2"),
+                                   ("float4_e2m1", "float4_e2m1"), ("int8", "int8"), ("float8_e4m3", "float8_e4m3")])
+def test_fallback_matches_reference_fixture(mx, fixtures, ea, ew):
+    """K = 96 / 64 cannot use the tensor-core path (K % 128 != 0): dequantize-then-aten, compared with
+    the reference's CPU outputs.  Operands are bit-identical; the bf16 GEMM itself is cuBLAS here and
+    MKL there, so equality is up to accumulation order (same tolerance as above)."""
+    from torchmx import dtypes
+    from torchmx.mx_tensor import MXTensor
+    a, w = bf16_tensor(fixtures["mm/a"], DEV), bf16_tensor(fixtures["mm/w"], DEV)
+    bias = bf16_tensor(fixtures["mm/bias"], DEV)
+    q, k = bf16_tensor(fixtures["mm/q"], DEV), bf16_tensor(fixtures["mm/k"], DEV)
+    A, W = MXTensor.to_mx(a, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[ea], 32), MXTensor.to_mx(w, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[ew], 32)
+    Q, K = MXTensor.to_mx(q, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[ea], 32), MXTensor.to_mx(k, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[ew], 32)
+    tag = f"mm/{ea}x{ew}"
+    with torch.no_grad():
+        outs = {"linear": torch.nn.functional.linear(A, W), "linear_bias": torch.nn.functional.linear(A, W, bias),
+                "mm": torch.matmul(A, W.t()), "qk": torch.matmul(Q, K.transpose(2, 3))}
+    for name, out in outs.items():
+        ref = bf16_tensor(fixtures[f"{tag}/{name}"], DEV).float()
+        # one bf16 ulp of the result plus fp32-accumulation slack on ~100 products of O(10) magnitude
+        torch.testing.assert_close(out.float(), ref, rtol=2 ** -7, atol=2e-2 if "int8" not in ea else 0.5)
+    # and exactly equal to dequantize-then-matmul on this device (reference: tests/test_mx_tensor.py:289)
+    assert torch.equal(outs["mm"], torch.matmul(A.to_dtype(torch.bfloat16), W.to_dtype(torch.bfloat16).t()))
+    assert torch.equal(outs["qk"], torch.matmul(Q.to_dtype(torch.bfloat16), K.to_dtype(torch.bfloat16).transpose(2, 3)))
+
+
+def test_mx_inference_linear_and_quantize_linear(mx):
+    """quantize_linear_ swaps every nn.Linear; MXInferenceLinear.forward = activation quantize + MX matmul
+    (reference: quant_api.py:188-215, layers/mx_linear.py:61-95)."""
+    from torchmx.config import MXConfig, QLinearConfig
+    from torchmx.layers.mx_linear import MXInferenceLinear
+    from torchmx.mx_tensor import MXTensor
+    from torchmx.quant_api import quantize_linear_
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(256, 512, bias=True), torch.nn.GELU(), torch.nn.Linear(512, 128, bias=False)).to(DEV, torch.bfloat16)
+    ref = [m for m in model if isinstance(m, torch.nn.Linear)]
+    w0, b0, w1 = ref[0].weight.data.clone(), ref[0].bias.data.clone(), ref[1].weight.data.clone()
+    qc = QLinearConfig(weights_config=MXConfig("float6_e3m2", 32), activations_config=MXConfig("float8_e4m3", 32))
+    quantize_linear_(model, qc)
+    assert type(model[0]) is MXInferenceLinear and type(model[2]) is MXInferenceLinear
+    assert isinstance(model[0].weight.data, MXTensor) and model[0].weight.shape == (512, 256)
+    x = torch.randn(3, 40, 256, device=DEV, dtype=torch.bfloat16)
+    y = model(x)
+    assert y.shape == (3, 40, 128) and y.dtype == torch.bfloat16
+    # same computation spelled out with dequantized operands
+    from torchmx import dtypes
+    xq = MXTensor.to_mx(x, dtypes.float8_e4m3, 32).to_dtype(torch.float32)
+    h = torch.nn.functional.gelu((xq @ MXTensor.to_mx(w0, dtypes.float6_e3m2, 32).to_dtype(torch.float32).t() + b0.float()).to(torch.bfloat16))
+    hq = MXTensor.to_mx(h, dtypes.float8_e4m3, 32).to_dtype(torch.float32)
+    want = (hq @ MXTensor.to_mx(w1, dtypes.float6_e3m2, 32).to_dtype(torch.float32).t())
+    sqnr = 20 * torch.log10(want.norm() / (want - y.float()).norm())
+    assert sqnr > 35, sqnr
+    # state_dict round trip keeps the MXTensor storage (reference: mx_tensor.py:526-528)
+    sd = model.state_dict()
+    assert isinstance(sd["0.weight"], MXTensor)

@@ -1,16 +1,447 @@
-// K3: block-scaled MX GEMM on tcgen05 (kind::mxf8f6f4, E8M0 scale factors in TMEM).  Placeholder
-// until the tensor-core kernel lands: reports "unsupported shape" so the host takes the
-// dequantize path (which is what the reference itself does, torchmx/ops.py:29-41).
+// K3: block-scaled MX GEMM on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+//   D[b][m][n] = sum_k ( A[b][m][k] * 2^(sfa[b][m][k/32]-127) ) * ( B[b][n][k] * 2^(sfb[b][n][k/32]-127) ) (+ bias[n])
+//
+// replaces the reference's dequantize -> bf16 aten op recipe (torchmx/ops.py:29-41, 60-68, 99-119):
+// the element codes stay 1 byte (E4M3 container), the E8M0 scales are applied by the MMA itself
+// (tcgen05.mma.kind::mxf8f6f4.block_scale, scale factors in TMEM), accumulation is fp32 in TMEM.
+//
+// Kernel anatomy (one CTA per SM, persistent over 128 x BLOCK_N output tiles, 8 warps):
+//   warp 0      TMA producer: A [128 x 128 B] and B [BLOCK_N x 128 B] K-major tiles, 128B swizzle,
+//               STAGES-deep mbarrier ring
+//   warp 1      MMA issuer (one elected lane): per 128-wide K block, tcgen05.cp the scale factors
+//               smem -> TMEM, then four K=32 MMAs; tcgen05.commit releases the stage / publishes
+//               the accumulator
+//   warp 2      scale-factor loader: reads the reference-layout scales ([rows, K/32] uint8, row-major)
+//               straight from global and writes them into the 32x16B layout tcgen05.cp expects
+//               (row r of a 128-row group -> 16-byte chunk r%32, word r/32), two K blocks ahead
+//   warp 3      TMEM allocator
+//   warps 4..7  epilogue: tcgen05.ld the fp32 accumulator (lane = row), + bias, -> bf16, 64-byte row
+//               segments to global
+#include <cuda.h>
+
 #include <cstdio>
 
 #include "mxq_common.cuh"
 
 namespace mxq {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 128;  // bytes == elements (1-byte codes): one 128B swizzle row, 4 MX blocks
+constexpr int UMMA_K = 32;
+constexpr int kThreads = 256;
+constexpr int kEpilogueThreads = 128;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|p, 0xFFFFFFFF;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+
+// smem -> TMEM, 32 rows x 128 bit, replicated to the four 32-lane quadrants (scale factors)
+__device__ __forceinline__ void tc_copy_sf(uint32_t tmem_addr, uint64_t smem_desc) {
+    asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_addr), "l"(smem_desc) : "memory");
+}
+__device__ __forceinline__ void tc_mma_mx(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t tmem_sfa, uint32_t tmem_sfb) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors ------------------------------------------------------------------------------------
+// shared-memory matrix descriptor (sm_100 format: version 1 in bits [46,48))
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
+}
+constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2;
+
+// instruction descriptor for kind::mxf8f6f4.block_scale: E4M3 x E4M3 (K-major both), UE8M0 scales, dense K=32
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t idesc_with_sf(uint32_t idesc, uint32_t sfa_id, uint32_t sfb_id) {
+    return idesc | (sfb_id << 4) | (sfa_id << 29);
+}
+
+struct Params {
+    const uint8_t* sfa; const uint8_t* sfb; const uint16_t* bias; uint16_t* d;
+    int64_t ld_sfa, ld_sfb, sfa_batch, sfb_batch, ldd, d_batch;
+    int M, N, K, batch, m_blocks, n_blocks;
+};
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+    static constexpr int A_STAGE = BLOCK_M * BLOCK_K;           // 16 KB
+    static constexpr int B_STAGE = BLOCK_N * BLOCK_K;           // 16 / 32 KB
+    static constexpr int SFA_STAGE = 512;                       // 128 rows x 4 bytes
+    static constexpr int SFB_STAGE = (BLOCK_N / 128) * 512;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
+    static constexpr int OFF_SFA = OFF_B + STAGES * B_STAGE;
+    static constexpr int OFF_SFB = OFF_SFA + STAGES * SFA_STAGE;
+    static constexpr int OFF_BAR = OFF_SFB + STAGES * SFB_STAGE;
+    static constexpr int NUM_BARS = 3 * STAGES + 2;
+    static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+    static constexpr int TOTAL = OFF_TMEM_PTR + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for the manual 1024-byte alignment
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                              const Params p) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    constexpr int SF_COLS_A = 4, SF_COLS_B = BLOCK_N / 32;
+    constexpr int TMEM_COLS = (BLOCK_N + SF_COLS_A + SF_COLS_B) <= 256 ? 256 : 512;
+    constexpr uint32_t TM_SFA = BLOCK_N, TM_SFB = BLOCK_N + SF_COLS_A;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* full = bars;                    // TMA bytes landed          (count 1 + tx)
+    uint64_t* sf_full = bars + STAGES;        // scale factors in smem     (count 32)
+    uint64_t* empty = bars + 2 * STAGES;      // MMAs of the stage retired (count 1, tcgen05.commit)
+    uint64_t* tmem_full = bars + 3 * STAGES;  // accumulator complete      (count 1, tcgen05.commit)
+    uint64_t* tmem_empty = tmem_full + 1;     // accumulator drained       (count 128)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k_blocks = p.K / BLOCK_K;
+    const int tiles_per_batch = p.m_blocks * p.n_blocks;
+    const int num_tiles = tiles_per_batch * p.batch;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&sf_full[i], 32);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, kEpilogueThreads);
+        fence_barrier_init();
+    }
+    if (warp == 3) tmem_alloc<TMEM_COLS>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto tile_coords = [&](int tile, int& b, int& mb, int& nb) {
+        b = tile / tiles_per_batch;
+        const int t = tile - b * tiles_per_batch;
+        nb = t / p.m_blocks;  // m fastest: concurrently running CTAs share one B panel
+        mb = t - nb * p.m_blocks;
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int b, mb, nb;
+                tile_coords(tile, b, mb, nb);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], L::A_STAGE + L::B_STAGE);
+                    tma_load_3d(&map_a, &full[stage], smem + L::OFF_A + stage * L::A_STAGE, kb * BLOCK_K, mb * BLOCK_M, b);
+                    tma_load_3d(&map_b, &full[stage], smem + L::OFF_B + stage * L::B_STAGE, kb * BLOCK_K, nb * BLOCK_N, b);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+        uint32_t stage = 0, phase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(tmem_empty, acc_phase ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                mbar_wait(&full[stage], phase);
+                mbar_wait(&sf_full[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(smem + L::OFF_A + stage * L::A_STAGE);
+                    const uint32_t b_addr = smem_u32(smem + L::OFF_B + stage * L::B_STAGE);
+                    const uint32_t sfa_addr = smem_u32(smem + L::OFF_SFA + stage * L::SFA_STAGE);
+                    const uint32_t sfb_addr = smem_u32(smem + L::OFF_SFB + stage * L::SFB_STAGE);
+                    tc_copy_sf(tmem_base + TM_SFA, smem_desc(sfa_addr, 128, kLayoutNone));
+#pragma unroll
+                    for (int i = 0; i < BLOCK_N / 128; ++i) tc_copy_sf(tmem_base + TM_SFB + 4 * i, smem_desc(sfb_addr + 512 * i, 128, kLayoutNone));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // K-major SW128 tile: 8-row groups are 1024 B apart; advancing K inside the swizzle row = +32 B
+                        const uint64_t da = smem_desc(a_addr + k * UMMA_K, 1024, kLayoutSw128);
+                        const uint64_t db = smem_desc(b_addr + k * UMMA_K, 1024, kLayoutSw128);
+                        tc_mma_mx(tmem_base, da, db, idesc_with_sf(idesc, k, k), (kb | k) != 0, tmem_base + TM_SFA, tmem_base + TM_SFB);
+                    }
+                    tc_commit(&empty[stage]);
+                    if (kb == k_blocks - 1) tc_commit(tmem_full);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            acc_phase ^= 1;
+        }
+    } else if (warp == 2) {
+        // ================= scale-factor loader =================
+        // per K block: A needs word (row r, kb) for r in the 128-row tile, B for BLOCK_N rows.
+        // lane i owns rows i, i+32, i+64, i+96 of each 128-row group -> one 16-byte chunk.
+        constexpr int GROUPS = 1 + BLOCK_N / 128;  // 128-row groups: A, then B
+        constexpr int AHEAD = 2;                   // K blocks kept in flight in registers
+        uint32_t stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int b, mb, nb;
+            tile_coords(tile, b, mb, nb);
+            const uint8_t* rows[GROUPS][4];
+            bool ok[GROUPS][4];
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (g == 0) {
+                        const int r = mb * BLOCK_M + q * 32 + lane;
+                        ok[g][q] = r < p.M;
+                        rows[g][q] = p.sfa + (int64_t)b * p.sfa_batch + (int64_t)(ok[g][q] ? r : 0) * p.ld_sfa;
+                    } else {
+                        const int r = nb * BLOCK_N + (g - 1) * 128 + q * 32 + lane;
+                        ok[g][q] = r < p.N;
+                        rows[g][q] = p.sfb + (int64_t)b * p.sfb_batch + (int64_t)(ok[g][q] ? r : 0) * p.ld_sfb;
+                    }
+                }
+            uint32_t buf[AHEAD + 1][GROUPS][4];
+            auto issue = [&](int kb, uint32_t (&dst)[GROUPS][4]) {
+#pragma unroll
+                for (int g = 0; g < GROUPS; ++g)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        dst[g][q] = (kb < k_blocks && ok[g][q]) ? *reinterpret_cast<const uint32_t*>(rows[g][q] + 4 * kb) : 0u;
+            };
+#pragma unroll
+            for (int i = 0; i < AHEAD; ++i) issue(i, buf[i]);
+            for (int kb0 = 0; kb0 < k_blocks; kb0 += AHEAD + 1) {
+#pragma unroll
+                for (int j = 0; j <= AHEAD; ++j) {
+                    const int kb = kb0 + j;
+                    if (kb < k_blocks) {
+                        issue(kb + AHEAD, buf[(j + AHEAD) % (AHEAD + 1)]);
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + L::OFF_SFA + stage * L::SFA_STAGE;
+                        uint8_t* sb = smem + L::OFF_SFB + stage * L::SFB_STAGE;
+                        *reinterpret_cast<uint4*>(sa + 16 * lane) = make_uint4(buf[j][0][0], buf[j][0][1], buf[j][0][2], buf[j][0][3]);
+#pragma unroll
+                        for (int g = 1; g < GROUPS; ++g)
+                            *reinterpret_cast<uint4*>(sb + 512 * (g - 1) + 16 * lane) = make_uint4(buf[j][g][0], buf[j][g][1], buf[j][g][2], buf[j][g][3]);
+                        fence_proxy_async_smem();
+                        mbar_arrive(&sf_full[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int b, mb, nb;
+            tile_coords(tile, b, mb, nb);
+            mbar_wait(tmem_full, acc_phase);
+            tc_fence_after();
+            const int row = mb * BLOCK_M + quad * 32 + lane;
+            uint16_t* drow = p.d + (int64_t)b * p.d_batch + (int64_t)row * p.ldd;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+                tmem_ld_wait();
+                const int col0 = nb * BLOCK_N + c * 32;
+                if (row < p.M && col0 < p.N) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.N) f[i] += __uint_as_float((uint32_t)p.bias[col0 + i] << 16);
+                    }
+                    if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(drow + col0) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 o;
+                            o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+                            o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+                            o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+                            o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+                            *reinterpret_cast<uint4*>(drow + col0 + 8 * i) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.N) drow[col0 + i] = (uint16_t)pack_bf16x2(f[i], 0.0f);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty);
+            acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// [batch][rows][K bytes] uint8, K contiguous, box = 128 bytes x box_rows, 128B swizzle, OOB rows read as zero
+static bool make_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows, int64_t batch, int64_t ld, int64_t batch_stride,
+                             int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)(batch > 1 ? batch_stride : ld * rows)};
+    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t stream, char* msg,
+                      size_t msg_len) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    {   // per device / context attribute: set on every launch (a few hundred ns)
+        const cudaError_t e = cudaFuncSetAttribute(mx_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+        if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    }
+    Params p;
+    p.sfa = a->sfa; p.sfb = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
+    p.ld_sfa = a->ld_sfa; p.ld_sfb = a->ld_sfb; p.sfa_batch = a->sfa_batch_stride; p.sfb_batch = a->sfb_batch_stride;
+    p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
+    p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
+    p.m_blocks = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
+    p.n_blocks = (int)((a->N + BLOCK_N - 1) / BLOCK_N);
+    const int64_t tiles = (int64_t)p.m_blocks * p.n_blocks * p.batch;
+    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    mx_gemm_kernel<BLOCK_N, STAGES><<<grid, kThreads, L::DYN_BYTES, stream>>>(ma, mb, p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "launch: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    return MXQ_OK;
+}
+
+}  // namespace gemm
 
 int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, char* msg, size_t msg_len) {
-    (void)a; (void)sm_count; (void)stream;
-    snprintf(msg, msg_len, "tensor-core path not built yet");
-    return MXQ_ERR_UNSUPPORTED_SHAPE;
+    using namespace gemm;
+    if (a->K <= 0 || a->K % BLOCK_K) { snprintf(msg, msg_len, "K=%lld is not a positive multiple of %d", (long long)a->K, BLOCK_K); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+    if ((a->lda % 16) || (a->ldb % 16) || ((uintptr_t)a->a_codes % 16) || ((uintptr_t)a->b_codes % 16) || (a->a_batch_stride % 16) || (a->b_batch_stride % 16)) {
+        snprintf(msg, msg_len, "operand pointers / strides must be 16-byte aligned for TMA");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    if ((a->ld_sfa % 4) || (a->ld_sfb % 4) || ((uintptr_t)a->sfa % 4) || ((uintptr_t)a->sfb % 4) || (a->sfa_batch_stride % 4) || (a->sfb_batch_stride % 4)) {
+        snprintf(msg, msg_len, "scale pointers / strides must be 4-byte aligned");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    if (a->M > 0x7FFFFFFF || a->N > 0x7FFFFFFF || a->K > 0x7FFFFFFF || a->batch > 0x7FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+    const bool wide = a->N > 128;
+    CUtensorMap ma, mb;
+    if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M) ||
+        !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128)) {
+        snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    return wide ? launch_cfg<256, 4>(a, ma, mb, sm_count, stream, msg, msg_len) : launch_cfg<128, 6>(a, ma, mb, sm_count, stream, msg, msg_len);
 }
 
 }  // namespace mxq

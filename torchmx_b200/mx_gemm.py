@@ -2,22 +2,156 @@
 on the tcgen05 block-scaled kernel, prepares the E4M3-container operand views and calls mxq_gemm.
 Returns None when the pair does not qualify; ops.py then takes the dequantize path the reference
 itself uses (torchmx/ops.py:29-41).
+
+Qualifying pair (what every layer of the reference produces, torchmx/layers/mx_linear.py:61-95,
+mx_llama_attention.py:195-243): both operands FP element types, block size 32 along the contraction
+dim, no padding, K a multiple of 128, codes K-contiguous in memory.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Optional
 
 import torch
 
 from . import _C, dtypes
-from .mx_tensor import MXTensor
+from .mx_tensor import MXTensor, _stream_ptr
 
 aten = torch.ops.aten
 
 # developer switch: MXQ_DISABLE_TC=1 forces the dequantize path (used by parity tests)
 _DISABLED = os.environ.get("MXQ_DISABLE_TC", "0") == "1"
+_SHADOW_ATTR = "_mxq_e4m3_shadow"
+
+stats = {"tensor_core": 0, "fallback": 0}
+
+
+def set_enabled(flag: bool) -> None:
+    global _DISABLED
+    _DISABLED = not flag
+
+
+def _e4m3_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """codes: [..., rows, Kb] with unit stride along Kb -> uint8 [..., rows, K] E4M3-container bytes.
+    float8_e4m3 passes through untouched (a view); fp6 / fp4 are transcoded exactly by the CUDA
+    transcoder, and the result is cached on `cache_on` (the weight's storage tensor) when given."""
+    if elem == dtypes.float8_e4m3:
+        return codes
+    if cache_on is not None:
+        hit = cache_on.__dict__.get(_SHADOW_ATTR)
+        if hit is not None and hit[0] == (codes.data_ptr(), tuple(codes.shape), tuple(codes.stride()), cache_on._version):
+            return hit[1]
+    src = codes.contiguous()
+    per = 2 if elem == dtypes.float4_e2m1 else 1
+    out = torch.empty(tuple(src.shape[:-1]) + (src.shape[-1] * per,), dtype=torch.uint8, device=src.device)
+    rc = _C.lib().mxq_transcode_to_e4m3(src.data_ptr(), dtypes.ELEM_ID[elem.name], out.numel(), out.data_ptr(), src.device.index,
+                                        _stream_ptr(src))
+    _C.check(rc, "mxq_transcode_to_e4m3")
+    if cache_on is not None:
+        cache_on.__dict__[_SHADOW_ATTR] = ((codes.data_ptr(), tuple(codes.shape), tuple(codes.stride()), cache_on._version), out)
+    return out
+
+
+def _rows_k(t: MXTensor, k_dim_from_end: int):
+    """(codes, scales) viewed as [..., rows, K-ish] with K innermost, or None if K is not unit-stride."""
+    d, s = t._data, t._scale_e8m0
+    if k_dim_from_end == 2:  # operand given as [..., K, rows]
+        d, s = d.transpose(-1, -2), s.transpose(-1, -2)
+    if d.stride(-1) != 1 or s.stride(-1) != 1:
+        return None
+    return d, s
+
+
+def _qualifies(t: MXTensor) -> bool:
+    return (isinstance(t, MXTensor) and t._elem_dtype in dtypes.SUPPORTED_FP_ELEM_DTYPES and t._block_size == 32 and t._padding == 0
+            and t._data.is_cuda and t._orig_dtype == torch.bfloat16)
+
+
+def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs, sfb_bs, out) -> bool:
+    g = _C.GemmArgs()
+    g.a_codes, g.sfa, g.lda, g.ld_sfa = a_codes.data_ptr(), sfa.data_ptr(), a_codes.stride(-2), sfa.stride(-2)
+    g.a_batch_stride, g.sfa_batch_stride = a_bs, sfa_bs
+    g.b_codes, g.sfb, g.ldb, g.ld_sfb = b_codes.data_ptr(), sfb.data_ptr(), b_codes.stride(-2), sfb.stride(-2)
+    g.b_batch_stride, g.sfb_batch_stride = b_bs, sfb_bs
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.d, g.ldd, g.d_batch_stride = out.data_ptr(), N, M * N
+    g.batch, g.M, g.N, g.K = batch, M, N, K
+    rc = _C.lib().mxq_gemm(ctypes.byref(g), out.device.index, _stream_ptr(out))
+    if rc == _C.ERR_UNSUPPORTED_SHAPE:
+        return False
+    _C.check(rc, "mxq_gemm")
+    return True
 
 
 def try_tensor_core(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back) -> Optional[torch.Tensor]:
-    return None
+    out = None
+    if not _DISABLED and _qualifies(a) and _qualifies(b):
+        out = _dispatch(aten_op, a, b, extra_front, extra_back)
+    stats["tensor_core" if out is not None else "fallback"] += 1
+    return out
+
+
+def _dispatch(aten_op, a, b, extra_front, extra_back):
+    bias = None
+    if aten_op is aten.linear.default:
+        bias = extra_back[0] if extra_back else None
+        b_k_from_end = 1  # weight is [N, K]
+    elif aten_op is aten.addmm.default:
+        bias = extra_front[0]
+        b_k_from_end = 2  # mat2 is [K, N]
+    elif aten_op in (aten.mm.default, aten.bmm.default):
+        b_k_from_end = 2
+    else:
+        return None
+    nd_a = a._data.dim()
+    if a._block_dim != nd_a - 1:
+        return None
+    if b._block_dim != b._data.dim() - b_k_from_end:
+        return None
+    ak = _rows_k(a, 1)
+    bk = _rows_k(b, b_k_from_end)
+    if ak is None or bk is None:
+        return None
+    (a_codes, sfa), (b_codes, sfb) = ak, bk
+    K = a.shape[-1]
+    if K % 128 != 0 or K != (b.shape[-1] if b_k_from_end == 1 else b.shape[-2]):
+        return None
+    N = b.shape[-2] if b_k_from_end == 1 else b.shape[-1]
+    if bias is not None:
+        if isinstance(bias, MXTensor) or bias.dtype != torch.bfloat16 or bias.dim() != 1 or bias.shape[0] != N or not bias.is_contiguous():
+            return None
+
+    batched = aten_op is aten.bmm.default
+    if batched:
+        if a._data.dim() != 3 or b._data.dim() != 3:
+            return None
+        batch, M = a.shape[0], a.shape[1]
+        lead_shape = (batch, M)
+    else:
+        if b._data.dim() != 2:
+            return None
+        if nd_a > 2:  # aten.linear on [..., K]: rows must collapse into one strided dim
+            if not (a._data.is_contiguous() and a._scale_e8m0.is_contiguous()):
+                return None
+            a_codes, sfa = a_codes.reshape(-1, a_codes.shape[-1]), sfa.reshape(-1, sfa.shape[-1])
+        batch, M = 1, a_codes.shape[0]
+        lead_shape = tuple(a.shape[:-1])
+
+    # E4M3-container operands (exact transcode of fp6 / fp4 codes; weights cache theirs on the storage tensor)
+    b_base = b._data._base if b._data._base is not None else b._data
+    a_e = _e4m3_rows(a_codes, a._elem_dtype, None)
+    b_e = _e4m3_rows(b_codes, b._elem_dtype, b_base if not batched else None)
+    if a_e.stride(-1) != 1 or b_e.stride(-1) != 1:
+        return None
+    out = torch.empty(lead_shape + (N,), dtype=torch.bfloat16, device=a._data.device)
+    if out.numel() == 0:
+        return out
+    if batched:
+        strides = (a_e.stride(0), sfa.stride(0), b_e.stride(0), sfb.stride(0))
+        if any(s <= 0 for s in strides):
+            return None  # expanded (stride 0) batch: not expressible as a TMA stride
+    else:
+        strides = (0, 0, 0, 0)
+    ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out)
+    return out if ok else None
