@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "mxq_common.cuh"
 
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* full = bars;                    // TMA bytes landed          (count 1 + tx)
-    uint64_t* sf_full = bars + STAGES;        // scale factors in smem     (count 32)
+    uint64_t* sf_full = bars + STAGES;        // scale factors in smem     (count 64: both loader warps)
     uint64_t* empty = bars + 2 * STAGES;      // MMAs of the stage retired (count 1, tcgen05.commit)
     uint64_t* tmem_full = bars + 3 * STAGES;  // accumulator complete      (count 1, tcgen05.commit)
     uint64_t* tmem_empty = tmem_full + 1;     // accumulator drained       (count 128)
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&sf_full[i], 32);
+            mbar_init(&sf_full[i], 64);
             mbar_init(&empty[i], 1);
         }
         mbar_init(tmem_full, 1);
@@ -259,58 +260,79 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
             }
             acc_phase ^= 1;
         }
-    } else if (warp == 2) {
-        // ================= scale-factor loader =================
-        // per K block: A needs word (row r, kb) for r in the 128-row tile, B for BLOCK_N rows.
-        // lane i owns rows i, i+32, i+64, i+96 of each 128-row group -> one 16-byte chunk.
-        constexpr int GROUPS = 1 + BLOCK_N / 128;  // 128-row groups: A, then B
-        constexpr int AHEAD = 2;                   // K blocks kept in flight in registers
+    } else if (warp == 2 || warp == 3) {
+        // ================= scale-factor loaders (warp 2: A rows, warp 3: B rows) =================
+        // The reference keeps scales as [rows, K/32] bytes, i.e. one 32-bit word per (row, 128-wide K block).
+        // tcgen05.cp wants, per 128-row group and K block, 32 chunks of 16 B: chunk i = words of rows
+        // i, i+32, i+64, i+96.  Lane i therefore owns those four rows; it fetches 16 B per row (four K
+        // blocks) per load, two load groups (8 K blocks) ahead of use, and emits one 16-byte store per K block.
+        constexpr int GROUPS = (BLOCK_N / 128);  // 128-row groups handled by the B warp (the A warp has 1)
+        constexpr int KB_PER_LOAD = 4;
+        const bool is_a = warp == 2;
+        const int ngroups = is_a ? 1 : GROUPS;
         uint32_t stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int b, mb, nb;
             tile_coords(tile, b, mb, nb);
             const uint8_t* rows[GROUPS][4];
-            bool ok[GROUPS][4];
 #pragma unroll
             for (int g = 0; g < GROUPS; ++g)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (g == 0) {
-                        const int r = mb * BLOCK_M + q * 32 + lane;
-                        ok[g][q] = r < p.M;
-                        rows[g][q] = p.sfa + (int64_t)b * p.sfa_batch + (int64_t)(ok[g][q] ? r : 0) * p.ld_sfa;
-                    } else {
-                        const int r = nb * BLOCK_N + (g - 1) * 128 + q * 32 + lane;
-                        ok[g][q] = r < p.N;
-                        rows[g][q] = p.sfb + (int64_t)b * p.sfb_batch + (int64_t)(ok[g][q] ? r : 0) * p.ld_sfb;
+                    const int r = (is_a ? mb * BLOCK_M : nb * BLOCK_N + g * 128) + q * 32 + lane;
+                    const int lim = is_a ? p.M : p.N;
+                    const int rc = r < lim ? r : lim - 1;  // clamp: rows past the edge only feed masked outputs
+                    rows[g][q] = is_a ? p.sfa + (int64_t)b * p.sfa_batch + (int64_t)rc * p.ld_sfa
+                                      : p.sfb + (int64_t)b * p.sfb_batch + (int64_t)rc * p.ld_sfb;
+                }
+            const int n_loads = (k_blocks + KB_PER_LOAD - 1) / KB_PER_LOAD;
+            const bool vec_ok = ((is_a ? p.ld_sfa : p.ld_sfb) % 16 == 0) && ((reinterpret_cast<uintptr_t>(rows[0][0]) & 15) == 0) &&
+                                (k_blocks % KB_PER_LOAD == 0);
+            uint4 buf[3][GROUPS][4];
+            auto issue = [&](int l, uint4 (&dst)[GROUPS][4]) {
+                if (l >= n_loads) return;
+#pragma unroll
+                for (int g = 0; g < GROUPS; ++g) {
+                    if (g < ngroups) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint8_t* src = rows[g][q] + 16 * l;
+                            if (vec_ok) {
+                                dst[g][q] = *reinterpret_cast<const uint4*>(src);
+                            } else {
+                                uint32_t w[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) w[j] = (l * KB_PER_LOAD + j < k_blocks) ? *reinterpret_cast<const uint32_t*>(src + 4 * j) : 0u;
+                                dst[g][q] = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
+                        }
                     }
                 }
-            uint32_t buf[AHEAD + 1][GROUPS][4];
-            auto issue = [&](int kb, uint32_t (&dst)[GROUPS][4]) {
-#pragma unroll
-                for (int g = 0; g < GROUPS; ++g)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        dst[g][q] = (kb < k_blocks && ok[g][q]) ? *reinterpret_cast<const uint32_t*>(rows[g][q] + 4 * kb) : 0u;
             };
+            auto word = [](const uint4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); };
+            issue(0, buf[0]);
+            issue(1, buf[1]);
+            for (int l0 = 0; l0 < n_loads; l0 += 3) {
 #pragma unroll
-            for (int i = 0; i < AHEAD; ++i) issue(i, buf[i]);
-            for (int kb0 = 0; kb0 < k_blocks; kb0 += AHEAD + 1) {
+                for (int u = 0; u < 3; ++u) {
+                    const int l = l0 + u;
+                    if (l < n_loads) {
+                        issue(l + 2, buf[(u + 2) % 3]);
 #pragma unroll
-                for (int j = 0; j <= AHEAD; ++j) {
-                    const int kb = kb0 + j;
-                    if (kb < k_blocks) {
-                        issue(kb + AHEAD, buf[(j + AHEAD) % (AHEAD + 1)]);
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* sa = smem + L::OFF_SFA + stage * L::SFA_STAGE;
-                        uint8_t* sb = smem + L::OFF_SFB + stage * L::SFB_STAGE;
-                        *reinterpret_cast<uint4*>(sa + 16 * lane) = make_uint4(buf[j][0][0], buf[j][0][1], buf[j][0][2], buf[j][0][3]);
+                        for (int j = 0; j < KB_PER_LOAD; ++j) {
+                            if (l * KB_PER_LOAD + j < k_blocks) {
+                                mbar_wait(&empty[stage], phase ^ 1);
+                                uint8_t* dst = smem + (is_a ? L::OFF_SFA + stage * L::SFA_STAGE : L::OFF_SFB + stage * L::SFB_STAGE);
 #pragma unroll
-                        for (int g = 1; g < GROUPS; ++g)
-                            *reinterpret_cast<uint4*>(sb + 512 * (g - 1) + 16 * lane) = make_uint4(buf[j][g][0], buf[j][g][1], buf[j][g][2], buf[j][g][3]);
-                        fence_proxy_async_smem();
-                        mbar_arrive(&sf_full[stage]);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                for (int g = 0; g < GROUPS; ++g)
+                                    if (g < ngroups)
+                                        *reinterpret_cast<uint4*>(dst + 512 * g + 16 * lane) =
+                                            make_uint4(word(buf[u][g][0], j), word(buf[u][g][1], j), word(buf[u][g][2], j), word(buf[u][g][3], j));
+                                fence_proxy_async_smem();
+                                mbar_arrive(&sf_full[stage]);
+                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            }
+                        }
                     }
                 }
             }
@@ -434,14 +456,23 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
     if (a->M > 0x7FFFFFFF || a->N > 0x7FFFFFFF || a->K > 0x7FFFFFFF || a->batch > 0x7FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
-    const bool wide = a->N > 128;
+    static const int force_narrow = getenv("MXQ_GEMM_NARROW") ? atoi(getenv("MXQ_GEMM_NARROW")) : 0;
+    const bool wide = a->N > 128 && !force_narrow;
     CUtensorMap ma, mb;
     if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M) ||
         !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128)) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
-    return wide ? launch_cfg<256, 4>(a, ma, mb, sm_count, stream, msg, msg_len) : launch_cfg<128, 6>(a, ma, mb, sm_count, stream, msg, msg_len);
+    static const int cfg = getenv("MXQ_GEMM_CFG") ? atoi(getenv("MXQ_GEMM_CFG")) : 0;  // developer knob: <BLOCK_N><STAGES>
+    if (wide) {
+        if (cfg == 2563) return launch_cfg<256, 3>(a, ma, mb, sm_count, stream, msg, msg_len);
+        if (cfg == 2562) return launch_cfg<256, 2>(a, ma, mb, sm_count, stream, msg, msg_len);
+        return launch_cfg<256, 4>(a, ma, mb, sm_count, stream, msg, msg_len);
+    }
+    if (cfg == 1284) return launch_cfg<128, 4>(a, ma, mb, sm_count, stream, msg, msg_len);
+    if (cfg == 1283) return launch_cfg<128, 3>(a, ma, mb, sm_count, stream, msg, msg_len);
+    return launch_cfg<128, 6>(a, ma, mb, sm_count, stream, msg, msg_len);
 }
 
 }  // namespace mxq
