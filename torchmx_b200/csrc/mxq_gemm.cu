@@ -122,6 +122,73 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- cluster / cta_group::2 flavours ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// address of the same shared-memory object in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id): a cluster-scope release costs a
+    // full membar that also waits for the loader warps' in-flight global prefetches
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are posted on an mbarrier of either CTA of the pair (cluster address)
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tc_copy_sf_pair(uint32_t tmem_addr, uint64_t smem_desc) {
+    asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_addr), "l"(smem_desc) : "memory");
+}
+__device__ __forceinline__ void tc_mma_mx_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                               uint32_t tmem_sfa, uint32_t tmem_sfb) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in both CTAs of the pair once all prior MMAs retire
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------------------
 // shared-memory matrix descriptor (sm_100 format: version 1 in bits [46,48))
 __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -142,6 +209,74 @@ struct Params {
     int64_t ld_sfa, ld_sfb, sfa_batch, sfb_batch, ldd, d_batch;
     int M, N, K, batch, m_blocks, n_blocks;
 };
+
+
+// ---- scale-factor loader (one warp, one output tile) ---------------------------------------------------
+// The reference keeps scales as [rows, K/32] bytes, i.e. one 32-bit word per (row, 128-wide K block).
+// tcgen05.cp.32x128b.warpx4 wants, per 128-row group and K block, 32 chunks of 16 B: chunk i = the words of
+// rows i, i+32, i+64, i+96.  Lane i therefore owns those four rows of each of the GROUPS 128-row groups; it
+// fetches 16 B per row (four K blocks) per load, two load groups (8 K blocks) ahead of use, and emits one
+// 16-byte shared-memory store per group and K block.  `arrive(stage)` publishes the stage (fence + mbarrier).
+template <int GROUPS, int STAGES, typename Arrive>
+__device__ __forceinline__ void sf_load_tile(const uint8_t* base, int64_t ld, int row0, int row_lim, int k_blocks, uint8_t* sf_smem,
+                                             int sf_stage_bytes, uint64_t* empty, uint32_t& stage, uint32_t& phase, int lane, Arrive&& arrive) {
+    constexpr int KB_PER_LOAD = 4;
+    const uint8_t* rows[GROUPS][4];
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = row0 + g * 128 + q * 32 + lane;
+            const int rc = r < row_lim ? r : row_lim - 1;  // clamp: rows past the edge only feed masked outputs
+            rows[g][q] = base + (int64_t)rc * ld;
+        }
+    const int n_loads = (k_blocks + KB_PER_LOAD - 1) / KB_PER_LOAD;
+    const bool vec_ok = (ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (k_blocks % KB_PER_LOAD == 0);
+    uint4 buf[3][GROUPS][4];
+    auto issue = [&](int l, uint4 (&dst)[GROUPS][4]) {
+        if (l >= n_loads) return;
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint8_t* src = rows[g][q] + 16 * l;
+                if (vec_ok) {
+                    dst[g][q] = *reinterpret_cast<const uint4*>(src);
+                } else {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w[j] = (l * KB_PER_LOAD + j < k_blocks) ? *reinterpret_cast<const uint32_t*>(src + 4 * j) : 0u;
+                    dst[g][q] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    };
+    auto word = [](const uint4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); };
+    issue(0, buf[0]);
+    issue(1, buf[1]);
+    for (int l0 = 0; l0 < n_loads; l0 += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int l = l0 + u;
+            if (l < n_loads) {
+                issue(l + 2, buf[(u + 2) % 3]);
+#pragma unroll
+                for (int j = 0; j < KB_PER_LOAD; ++j) {
+                    if (l * KB_PER_LOAD + j < k_blocks) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* dst = sf_smem + stage * sf_stage_bytes;
+#pragma unroll
+                        for (int g = 0; g < GROUPS; ++g)
+                            *reinterpret_cast<uint4*>(dst + 512 * g + 16 * lane) =
+                                make_uint4(word(buf[u][g][0], j), word(buf[u][g][1], j), word(buf[u][g][2], j), word(buf[u][g][3], j));
+                        arrive(stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    }
+}
 
 template <int BLOCK_N, int STAGES>
 struct SmemLayout {
@@ -262,80 +397,21 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
         }
     } else if (warp == 2 || warp == 3) {
         // ================= scale-factor loaders (warp 2: A rows, warp 3: B rows) =================
-        // The reference keeps scales as [rows, K/32] bytes, i.e. one 32-bit word per (row, 128-wide K block).
-        // tcgen05.cp wants, per 128-row group and K block, 32 chunks of 16 B: chunk i = words of rows
-        // i, i+32, i+64, i+96.  Lane i therefore owns those four rows; it fetches 16 B per row (four K
-        // blocks) per load, two load groups (8 K blocks) ahead of use, and emits one 16-byte store per K block.
-        constexpr int GROUPS = (BLOCK_N / 128);  // 128-row groups handled by the B warp (the A warp has 1)
-        constexpr int KB_PER_LOAD = 4;
         const bool is_a = warp == 2;
-        const int ngroups = is_a ? 1 : GROUPS;
         uint32_t stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int b, mb, nb;
             tile_coords(tile, b, mb, nb);
-            const uint8_t* rows[GROUPS][4];
-#pragma unroll
-            for (int g = 0; g < GROUPS; ++g)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int r = (is_a ? mb * BLOCK_M : nb * BLOCK_N + g * 128) + q * 32 + lane;
-                    const int lim = is_a ? p.M : p.N;
-                    const int rc = r < lim ? r : lim - 1;  // clamp: rows past the edge only feed masked outputs
-                    rows[g][q] = is_a ? p.sfa + (int64_t)b * p.sfa_batch + (int64_t)rc * p.ld_sfa
-                                      : p.sfb + (int64_t)b * p.sfb_batch + (int64_t)rc * p.ld_sfb;
-                }
-            const int n_loads = (k_blocks + KB_PER_LOAD - 1) / KB_PER_LOAD;
-            const bool vec_ok = ((is_a ? p.ld_sfa : p.ld_sfb) % 16 == 0) && ((reinterpret_cast<uintptr_t>(rows[0][0]) & 15) == 0) &&
-                                (k_blocks % KB_PER_LOAD == 0);
-            uint4 buf[3][GROUPS][4];
-            auto issue = [&](int l, uint4 (&dst)[GROUPS][4]) {
-                if (l >= n_loads) return;
-#pragma unroll
-                for (int g = 0; g < GROUPS; ++g) {
-                    if (g < ngroups) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint8_t* src = rows[g][q] + 16 * l;
-                            if (vec_ok) {
-                                dst[g][q] = *reinterpret_cast<const uint4*>(src);
-                            } else {
-                                uint32_t w[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) w[j] = (l * KB_PER_LOAD + j < k_blocks) ? *reinterpret_cast<const uint32_t*>(src + 4 * j) : 0u;
-                                dst[g][q] = make_uint4(w[0], w[1], w[2], w[3]);
-                            }
-                        }
-                    }
-                }
+            auto arrive = [&](uint32_t st) {
+                fence_proxy_async_smem();
+                mbar_arrive(&sf_full[st]);
             };
-            auto word = [](const uint4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); };
-            issue(0, buf[0]);
-            issue(1, buf[1]);
-            for (int l0 = 0; l0 < n_loads; l0 += 3) {
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int l = l0 + u;
-                    if (l < n_loads) {
-                        issue(l + 2, buf[(u + 2) % 3]);
-#pragma unroll
-                        for (int j = 0; j < KB_PER_LOAD; ++j) {
-                            if (l * KB_PER_LOAD + j < k_blocks) {
-                                mbar_wait(&empty[stage], phase ^ 1);
-                                uint8_t* dst = smem + (is_a ? L::OFF_SFA + stage * L::SFA_STAGE : L::OFF_SFB + stage * L::SFB_STAGE);
-#pragma unroll
-                                for (int g = 0; g < GROUPS; ++g)
-                                    if (g < ngroups)
-                                        *reinterpret_cast<uint4*>(dst + 512 * g + 16 * lane) =
-                                            make_uint4(word(buf[u][g][0], j), word(buf[u][g][1], j), word(buf[u][g][2], j), word(buf[u][g][3], j));
-                                fence_proxy_async_smem();
-                                mbar_arrive(&sf_full[stage]);
-                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                            }
-                        }
-                    }
-                }
-            }
+            if (is_a)
+                sf_load_tile<1, STAGES>(p.sfa + (int64_t)b * p.sfa_batch, p.ld_sfa, mb * BLOCK_M, p.M, k_blocks, smem + L::OFF_SFA, L::SFA_STAGE, empty,
+                                        stage, phase, lane, arrive);
+            else
+                sf_load_tile<BLOCK_N / 128, STAGES>(p.sfb + (int64_t)b * p.sfb_batch, p.ld_sfb, nb * BLOCK_N, p.N, k_blocks, smem + L::OFF_SFB,
+                                                    L::SFB_STAGE, empty, stage, phase, lane, arrive);
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
@@ -391,6 +467,243 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
     if (warp == 3) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+
+// ---- K3b: CTA-pair variant (cta_group::2) -------------------------------------------------------------------
+// Two CTAs of a cluster (same TPC) compute one 256 x 256 output tile: each CTA stages its own 128 rows of A
+// and 128 of the 256 B rows, the leader's single thread issues M=256 MMAs that read both CTAs' shared memory,
+// and each CTA ends up with its 128 x 256 half of the accumulator in its own TMEM.  Per CTA and MMA this
+// halves the B bytes written by TMA and read by the tensor core (24 KB -> 16 KB of shared-memory traffic per
+// 128-cycle MMA), which is what bounds the single-CTA kernel with 1-byte operands.
+//
+// TMEM (512 columns): two accumulator slots at columns 0 and 192 that overlap in [192,256).  The epilogue drains
+// the overlapping 64 columns first and then hands the slot back, so the MMAs of the next tile (other slot) run
+// under the rest of the epilogue.  Scale factors: two 12-column buffers (SFA 4 + SFB 8) from column 448.
+//
+// Barriers: full / sf_full / tmem_empty live in the leader CTA (TMA complete_tx and the loader / epilogue warps of
+// both CTAs arrive there); empty / tmem_full exist in both CTAs and are signalled by multicast tcgen05.commit.
+namespace pair {
+constexpr int TILE_M = 256, TILE_N = 256;
+constexpr int kThreads = 256;
+constexpr uint32_t ACC_SLOT1 = 192;
+constexpr uint32_t TM_SF = 448, SF_BUF_COLS = 12;
+constexpr int kEpilogueWarps = 4;
+
+template <int STAGES>
+struct Smem {
+    static constexpr int A_STAGE = 128 * BLOCK_K;  // 16 KB
+    static constexpr int B_STAGE = 128 * BLOCK_K;  // 16 KB: this CTA's half of the 256 B rows
+    static constexpr int SFA_STAGE = 512;          // own 128 A rows
+    static constexpr int SFB_STAGE = 1024;         // all 256 B rows (each CTA's tensor core scales every column)
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
+    static constexpr int OFF_SFA = OFF_B + STAGES * B_STAGE;
+    static constexpr int OFF_SFB = OFF_SFA + STAGES * SFA_STAGE;
+    static constexpr int OFF_BAR = OFF_SFB + STAGES * SFB_STAGE;
+    static constexpr int NUM_BARS = 3 * STAGES + 2;
+    static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+    static constexpr int TOTAL = OFF_TMEM_PTR + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    mx_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+    using L = Smem<STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    // the dynamic shared window starts at the same offset in both CTAs, so the aligned carve-up matches too
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* full = bars;                    // leader: both CTAs' TMA bytes landed   (count 1 + tx)
+    uint64_t* sf_full = bars + STAGES;        // leader: scale factors in both smems   (count 4: two loader warps x two CTAs)
+    uint64_t* empty = bars + 2 * STAGES;      // both:   MMAs of the stage retired     (count 1, multicast commit)
+    uint64_t* tmem_full = bars + 3 * STAGES;  // both:   accumulator complete          (count 1, multicast commit)
+    uint64_t* tmem_empty = tmem_full + 1;     // leader: accumulator slot reusable     (count 8: epilogue warps of both CTAs)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int k_blocks = p.K / BLOCK_K;
+    const int tiles_per_batch = p.m_blocks * p.n_blocks;
+    const int num_tiles = tiles_per_batch * p.batch;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&sf_full[i], 4);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 2 * kEpilogueWarps);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (warp == 3) tmem_alloc_pair<512>(tmem_ptr);
+    tc_fence_before();
+    cluster_sync_all();  // the peer's barriers must be initialised before anything is posted on them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto tile_coords = [&](int tile, int& b, int& mb, int& nb) {
+        b = tile / tiles_per_batch;
+        const int t = tile - b * tiles_per_batch;
+        nb = t / p.m_blocks;  // m fastest: concurrently running pairs share one B panel
+        mb = t - nb * p.m_blocks;
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs; completion bytes are posted on the leader's barrier) =================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                int b, mb, nb;
+                tile_coords(tile, b, mb, nb);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (L::A_STAGE + L::B_STAGE));
+                    const uint32_t full_leader = mapa_shared(smem_u32(&full[stage]), 0);
+                    tma_load_3d_pair(&map_a, full_leader, smem + L::OFF_A + stage * L::A_STAGE, kb * BLOCK_K, mb * TILE_M + (int)rank * 128, b);
+                    tma_load_3d_pair(&map_b, full_leader, smem + L::OFF_B + stage * L::B_STAGE, kb * BLOCK_K, nb * TILE_N + (int)rank * 128, b);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc(TILE_M, TILE_N);
+            uint32_t stage = 0, phase = 0, acc_phase = 0, slot = 0, sf_sel = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                mbar_wait_cluster(tmem_empty, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (slot ? ACC_SLOT1 : 0u);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    mbar_wait_cluster(&sf_full[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_addr = smem_u32(smem + L::OFF_A + stage * L::A_STAGE);
+                        const uint32_t b_addr = smem_u32(smem + L::OFF_B + stage * L::B_STAGE);
+                        const uint32_t sfa_addr = smem_u32(smem + L::OFF_SFA + stage * L::SFA_STAGE);
+                        const uint32_t sfb_addr = smem_u32(smem + L::OFF_SFB + stage * L::SFB_STAGE);
+                        const uint32_t tm_sfa = tmem_base + TM_SF + sf_sel * SF_BUF_COLS, tm_sfb = tm_sfa + 4;
+                        tc_copy_sf_pair(tm_sfa, smem_desc(sfa_addr, 128, kLayoutNone));
+                        tc_copy_sf_pair(tm_sfb, smem_desc(sfb_addr, 128, kLayoutNone));
+                        tc_copy_sf_pair(tm_sfb + 4, smem_desc(sfb_addr + 512, 128, kLayoutNone));
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t da = smem_desc(a_addr + k * UMMA_K, 1024, kLayoutSw128);
+                            const uint64_t db = smem_desc(b_addr + k * UMMA_K, 1024, kLayoutSw128);
+                            tc_mma_mx_pair(tmem_d, da, db, idesc_with_sf(idesc, k, k), (kb | k) != 0, tm_sfa, tm_sfb);
+                        }
+                        tc_commit_pair(&empty[stage]);
+                        if (kb == k_blocks - 1) tc_commit_pair(tmem_full);
+                    }
+                    __syncwarp();
+                    sf_sel ^= 1;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc_phase ^= 1;
+                slot ^= 1;
+            }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ================= scale-factor loaders (both CTAs; warp 2: own 128 A rows, warp 3: all 256 B rows) =================
+        const bool is_a = warp == 2;
+        uint32_t stage = 0, phase = 0;
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+            int b, mb, nb;
+            tile_coords(tile, b, mb, nb);
+            auto arrive = [&](uint32_t st) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&sf_full[st]), 0));
+            };
+            if (is_a)
+                sf_load_tile<1, STAGES>(p.sfa + (int64_t)b * p.sfa_batch, p.ld_sfa, mb * TILE_M + (int)rank * 128, p.M, k_blocks, smem + L::OFF_SFA,
+                                        L::SFA_STAGE, empty, stage, phase, lane, arrive);
+            else
+                sf_load_tile<2, STAGES>(p.sfb + (int64_t)b * p.sfb_batch, p.ld_sfb, nb * TILE_N, p.N, k_blocks, smem + L::OFF_SFB, L::SFB_STAGE, empty,
+                                        stage, phase, lane, arrive);
+        }
+    } else {
+        // ================= epilogue (both CTAs, own 128 x 256 accumulator half) =================
+        const int quad = warp & 3;
+        const uint32_t tmem_empty_leader = mapa_shared(smem_u32(tmem_empty), 0);
+        uint32_t acc_phase = 0, slot = 0;
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+            int b, mb, nb;
+            tile_coords(tile, b, mb, nb);
+            mbar_wait(tmem_full, acc_phase);
+            tc_fence_after();
+            const int row = mb * TILE_M + (int)rank * 128 + quad * 32 + lane;
+            uint16_t* drow = p.d + (int64_t)b * p.d_batch + (int64_t)row * p.ldd;
+            const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (slot ? ACC_SLOT1 : 0u);
+            const int first = slot ? 0 : 6;  // the two 32-column chunks inside [192,256) of TMEM come first
+            auto store_chunk = [&](const uint32_t (&v)[32], int c) {
+                const int col0 = nb * TILE_N + c * 32;
+                if (row < p.M && col0 < p.N) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.N) f[i] += __uint_as_float((uint32_t)p.bias[col0 + i] << 16);
+                    }
+                    if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(drow + col0) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 o;
+                            o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+                            o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+                            o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+                            o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+                            *reinterpret_cast<uint4*>(drow + col0 + 8 * i) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.N) drow[col0 + i] = (uint16_t)pack_bf16x2(f[i], 0.0f);
+                    }
+                }
+            };
+            {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32b_x32(tmem_acc + first * 32, v0);
+                tmem_ld_32x32b_x32(tmem_acc + (first + 1) * 32, v1);
+                tmem_ld_wait();
+                // the columns shared with the other slot are in registers: the next tile's MMAs may start
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+                store_chunk(v0, first);
+                store_chunk(v1, first + 1);
+            }
+#pragma unroll 1
+            for (int ci = 2; ci < 8; ++ci) {
+                const int c = (first + ci) & 7;
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_acc + c * 32, v);
+                tmem_ld_wait();
+                store_chunk(v, c);
+            }
+            acc_phase ^= 1;
+            slot ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still post on its barriers / read its smem
+    if (warp == 3) tmem_dealloc_pair<512>(tmem_base);
+}
+}  // namespace pair
+
 // ---- host side ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -442,6 +755,31 @@ static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUt
     return MXQ_OK;
 }
 
+
+template <int STAGES>
+static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t stream, char* msg,
+                       size_t msg_len) {
+    using L = pair::Smem<STAGES>;
+    {
+        const cudaError_t e = cudaFuncSetAttribute(pair::mx_gemm_pair_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+        if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    }
+    Params p;
+    p.sfa = a->sfa; p.sfb = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
+    p.ld_sfa = a->ld_sfa; p.ld_sfb = a->ld_sfb; p.sfa_batch = a->sfa_batch_stride; p.sfb_batch = a->sfb_batch_stride;
+    p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
+    p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
+    p.m_blocks = (int)((a->M + pair::TILE_M - 1) / pair::TILE_M);
+    p.n_blocks = (int)((a->N + pair::TILE_N - 1) / pair::TILE_N);
+    const int64_t tiles = (int64_t)p.m_blocks * p.n_blocks * p.batch;
+    const int max_pairs = sm_count / 2;
+    const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
+    pair::mx_gemm_pair_kernel<STAGES><<<2 * pairs, pair::kThreads, L::DYN_BYTES, stream>>>(ma, mb, p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (pair): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    return MXQ_OK;
+}
+
 }  // namespace gemm
 
 int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, char* msg, size_t msg_len) {
@@ -457,14 +795,25 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
     }
     if (a->M > 0x7FFFFFFF || a->N > 0x7FFFFFFF || a->K > 0x7FFFFFFF || a->batch > 0x7FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
     static const int force_narrow = getenv("MXQ_GEMM_NARROW") ? atoi(getenv("MXQ_GEMM_NARROW")) : 0;
+    static const int cfg = getenv("MXQ_GEMM_CFG") ? atoi(getenv("MXQ_GEMM_CFG")) : 0;  // developer knob: <BLOCK_N><STAGES>, 2<STAGES> = CTA pair
     const bool wide = a->N > 128 && !force_narrow;
     CUtensorMap ma, mb;
+    const bool use_pair = wide && a->M > 128 && sm_count >= 2 && (cfg == 0 || cfg / 10 == 2);
+    if (use_pair) {
+        if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, 128) ||
+            !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, 128)) {
+            snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
+            return MXQ_ERR_UNSUPPORTED_SHAPE;
+        }
+        if (cfg == 24) return launch_pair<4>(a, ma, mb, sm_count, stream, msg, msg_len);
+        if (cfg == 25) return launch_pair<5>(a, ma, mb, sm_count, stream, msg, msg_len);
+        return launch_pair<6>(a, ma, mb, sm_count, stream, msg, msg_len);
+    }
     if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M) ||
         !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128)) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
-    static const int cfg = getenv("MXQ_GEMM_CFG") ? atoi(getenv("MXQ_GEMM_CFG")) : 0;  // developer knob: <BLOCK_N><STAGES>
     if (wide) {
         if (cfg == 2563) return launch_cfg<256, 3>(a, ma, mb, sm_count, stream, msg, msg_len);
         if (cfg == 2562) return launch_cfg<256, 2>(a, ma, mb, sm_count, stream, msg, msg_len);
