@@ -1,25 +1,48 @@
-import os, sys, torch
+"""Kernel-level timing of the MX GEMM through the public op (F.linear on MXTensors), replayed from a CUDA
+graph so host dispatch is not in the number.  GT_SHAPES=MxNxK,..  GT_CFGS=comma list of MXQ_GEMM_CFG[:GM] values
+(0 = default dispatch), interleaved over GT_ROUNDS rounds; prints min / median per config."""
+import os, sys, statistics, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torchmx_b200  # noqa
 from torchmx_b200 import dtypes
 from torchmx_b200.mx_tensor import MXTensor
 shapes = [tuple(int(v) for v in s.split("x")) for s in os.environ.get("GT_SHAPES", "8192x8192x8192").split(",")]
+cfgs = os.environ.get("GT_CFGS", "0").split(",")
+rounds = int(os.environ.get("GT_ROUNDS", "3"))
+n = int(os.environ.get("GT_ITERS", "10"))
+wdt = getattr(dtypes, os.environ.get("GT_W", "float6_e3m2"))
 for (M, N, K) in shapes:
     a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
     b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
     A = MXTensor.to_mx(a, dtypes.float8_e4m3, 32)
-    B = MXTensor.to_mx(b, dtypes.float6_e3m2, 32)
-    for _ in range(3):
-        y = torch.nn.functional.linear(A, B)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 20
-    e0.record()
-    for _ in range(n):
-        y = torch.nn.functional.linear(A, B)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
+    B = MXTensor.to_mx(b, wdt, 32)
     ref = A.to_dtype(torch.float32)[:64] @ B.to_dtype(torch.float32).t()
-    err = (y[:64].float() - ref).abs().max().item() / ref.abs().max().item()
-    print(f"cfg={os.environ.get('MXQ_GEMM_CFG','-')} narrow={os.environ.get('MXQ_GEMM_NARROW','0')} {M}x{N}x{K}: {ms*1e3:.1f} us {2*M*N*K/ms/1e9:.0f} TFLOP/s relerr {err:.2e}", flush=True)
+    graphs = {}
+    for c in cfgs:
+        cfg, _, gm = c.partition(":")
+        os.environ["MXQ_GEMM_CFG"] = cfg
+        os.environ["MXQ_GEMM_GM"] = gm or "0"
+        y = torch.nn.functional.linear(A, B)
+        torch.cuda.synchronize()
+        err = (y[:64].float() - ref).abs().max().item() / ref.abs().max().item()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(n):
+                    y = torch.nn.functional.linear(A, B)
+        graphs[c] = (g, err)
+    times = {c: [] for c in cfgs}
+    for r in range(rounds + 1):
+        for c in cfgs:
+            g, _ = graphs[c]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            if r > 0:
+                times[c].append(e0.elapsed_time(e1) / n * 1e3)
+    for c in cfgs:
+        t = times[c]
+        print(f"{M}x{N}x{K} cfg={c}: min {min(t):.1f} us ({2*M*N*K/min(t)/1e6:.0f} TFLOP/s) median {statistics.median(t):.1f} us relerr {graphs[c][1]:.2e}", flush=True)

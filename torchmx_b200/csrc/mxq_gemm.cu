@@ -479,45 +479,110 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
 // the overlapping 64 columns first and then hands the slot back, so the MMAs of the next tile (other slot) run
 // under the rest of the epilogue.  Scale factors: two 12-column buffers (SFA 4 + SFB 8) from column 448.
 //
+// Two rings: operand stages (one 128-wide K block each, TMA) and scale-factor stages (FOUR K blocks each -- the
+// loader warps read 16 B = four K blocks per row anyway), so the issuing thread and the loaders synchronise on
+// scale factors once per 2048 MMA cycles instead of once per 512.
+//
 // Barriers: full / sf_full / tmem_empty live in the leader CTA (TMA complete_tx and the loader / epilogue warps of
-// both CTAs arrive there); empty / tmem_full exist in both CTAs and are signalled by multicast tcgen05.commit.
+// both CTAs arrive there); empty / sf_empty / tmem_full exist in both CTAs and are signalled by multicast
+// tcgen05.commit.
 namespace pair {
 constexpr int TILE_M = 256, TILE_N = 256;
 constexpr int kThreads = 256;
 constexpr uint32_t ACC_SLOT1 = 192;
 constexpr uint32_t TM_SF = 448, SF_BUF_COLS = 12;
 constexpr int kEpilogueWarps = 4;
+constexpr int SF_STAGES = 4, SF_KB = 4;  // scale-factor ring: stages x K blocks per stage
 
 template <int STAGES>
 struct Smem {
     static constexpr int A_STAGE = 128 * BLOCK_K;  // 16 KB
     static constexpr int B_STAGE = 128 * BLOCK_K;  // 16 KB: this CTA's half of the 256 B rows
-    static constexpr int SFA_STAGE = 512;          // own 128 A rows
-    static constexpr int SFB_STAGE = 1024;         // all 256 B rows (each CTA's tensor core scales every column)
+    static constexpr int SFA_KB = 512, SFB_KB = 1024;  // per K block: own 128 A rows / all 256 B rows
+    static constexpr int SFA_STAGE = SF_KB * SFA_KB, SFB_STAGE = SF_KB * SFB_KB;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
     static constexpr int OFF_SFA = OFF_B + STAGES * B_STAGE;
-    static constexpr int OFF_SFB = OFF_SFA + STAGES * SFA_STAGE;
-    static constexpr int OFF_BAR = OFF_SFB + STAGES * SFB_STAGE;
-    static constexpr int NUM_BARS = 3 * STAGES + 2;
+    static constexpr int OFF_SFB = OFF_SFA + SF_STAGES * SFA_STAGE;
+    static constexpr int OFF_BAR = OFF_SFB + SF_STAGES * SFB_STAGE;
+    static constexpr int NUM_BARS = 2 * STAGES + 2 * SF_STAGES + 2;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM_PTR + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
+// one warp, one tile: rows row0 + g*128 + q*32 + lane; SF ring stage = 4 K blocks (one 16-byte load per row)
+template <int GROUPS, typename Arrive>
+__device__ __forceinline__ void sf_load_tile4(const uint8_t* base, int64_t ld, int row0, int row_lim, int k_blocks, uint8_t* sf_smem, int sf_kb_bytes,
+                                              uint64_t* sf_empty, uint32_t& sfs, uint32_t& sf_phase, int lane, Arrive&& arrive) {
+    const uint8_t* rows[GROUPS][4];
+#pragma unroll
+    for (int g = 0; g < GROUPS; ++g)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = row0 + g * 128 + q * 32 + lane;
+            const int rc = r < row_lim ? r : row_lim - 1;  // clamp: rows past the edge only feed masked outputs
+            rows[g][q] = base + (int64_t)rc * ld;
+        }
+    const int n_loads = (k_blocks + SF_KB - 1) / SF_KB;
+    const bool vec_ok = (ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (k_blocks % SF_KB == 0);
+    uint4 buf[3][GROUPS][4];
+    auto issue = [&](int l, uint4 (&dst)[GROUPS][4]) {
+        if (l >= n_loads) return;
+#pragma unroll
+        for (int g = 0; g < GROUPS; ++g) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint8_t* src = rows[g][q] + 16 * l;
+                if (vec_ok) {
+                    dst[g][q] = *reinterpret_cast<const uint4*>(src);
+                } else {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w[j] = (l * SF_KB + j < k_blocks) ? *reinterpret_cast<const uint32_t*>(src + 4 * j) : 0u;
+                    dst[g][q] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    };
+    auto word = [](const uint4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); };
+    issue(0, buf[0]);
+    issue(1, buf[1]);
+    for (int l0 = 0; l0 < n_loads; l0 += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int l = l0 + u;
+            if (l < n_loads) {
+                issue(l + 2, buf[(u + 2) % 3]);
+                mbar_wait(&sf_empty[sfs], sf_phase ^ 1);
+                uint8_t* dst = sf_smem + sfs * (SF_KB * sf_kb_bytes);
+#pragma unroll
+                for (int j = 0; j < SF_KB; ++j)
+#pragma unroll
+                    for (int g = 0; g < GROUPS; ++g)
+                        *reinterpret_cast<uint4*>(dst + j * sf_kb_bytes + 512 * g + 16 * lane) =
+                            make_uint4(word(buf[u][g][0], j), word(buf[u][g][1], j), word(buf[u][g][2], j), word(buf[u][g][3], j));
+                arrive(sfs);
+                if (++sfs == SF_STAGES) { sfs = 0; sf_phase ^= 1; }
+            }
+        }
+    }
+}
+
 template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-    mx_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+    mx_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p, const int group_m) {
     using L = Smem<STAGES>;
     extern __shared__ uint8_t smem_raw[];
     // the dynamic shared window starts at the same offset in both CTAs, so the aligned carve-up matches too
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-    uint64_t* full = bars;                    // leader: both CTAs' TMA bytes landed   (count 1 + tx)
-    uint64_t* sf_full = bars + STAGES;        // leader: scale factors in both smems   (count 4: two loader warps x two CTAs)
-    uint64_t* empty = bars + 2 * STAGES;      // both:   MMAs of the stage retired     (count 1, multicast commit)
-    uint64_t* tmem_full = bars + 3 * STAGES;  // both:   accumulator complete          (count 1, multicast commit)
-    uint64_t* tmem_empty = tmem_full + 1;     // leader: accumulator slot reusable     (count 8: epilogue warps of both CTAs)
+    uint64_t* full = bars;                              // leader: both CTAs' TMA bytes landed  (count 1 + tx)
+    uint64_t* empty = bars + STAGES;                    // both:   MMAs of the stage retired    (count 1, multicast commit)
+    uint64_t* sf_full = bars + 2 * STAGES;              // leader: scale factors in both smems  (count 4: two loader warps x two CTAs)
+    uint64_t* sf_empty = sf_full + SF_STAGES;           // both:   MMAs using the SF stage retired (count 1, multicast commit)
+    uint64_t* tmem_full = sf_empty + SF_STAGES;         // both:   accumulator complete         (count 1, multicast commit)
+    uint64_t* tmem_empty = tmem_full + 1;               // leader: accumulator slot reusable    (count 8: epilogue warps of both CTAs)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -535,8 +600,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&sf_full[i], 4);
             mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < SF_STAGES; ++i) {
+            mbar_init(&sf_full[i], 4);
+            mbar_init(&sf_empty[i], 1);
         }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 2 * kEpilogueWarps);
@@ -549,11 +617,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // grouped rasterisation: group_m row-blocks x all column-blocks at a time, row-block fastest, so one wave of
+    // pairs touches ~group_m A panels and ~num_pairs/group_m B panels (both stay in L2) instead of every A panel
     auto tile_coords = [&](int tile, int& b, int& mb, int& nb) {
         b = tile / tiles_per_batch;
         const int t = tile - b * tiles_per_batch;
-        nb = t / p.m_blocks;  // m fastest: concurrently running pairs share one B panel
-        mb = t - nb * p.m_blocks;
+        const int per_group = group_m * p.n_blocks;
+        const int g = t / per_group;
+        const int first_m = g * group_m;
+        const int gm = min(group_m, p.m_blocks - first_m);
+        const int r = t - g * per_group;
+        nb = r / gm;
+        mb = first_m + (r - nb * gm);
     };
 
     if (warp == 0) {
@@ -574,37 +649,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (leader CTA only) =================
+        // ================= MMA issuer (leader CTA; the whole warp runs the loop so that every operand stays in
+        // uniform registers -- a single-lane loop makes ptxas wrap each tcgen05 instruction in a lane-serialising
+        // R2UR loop -- and one elected lane issues) =================
         if (leader) {
             constexpr uint32_t idesc = make_idesc(TILE_M, TILE_N);
-            uint32_t stage = 0, phase = 0, acc_phase = 0, slot = 0, sf_sel = 0;
+            // descriptor words: the high halves are constants, the low halves are (shared address >> 4) + offsets
+            constexpr uint64_t HI_OPERAND = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutSw128 << 61);
+            constexpr uint64_t HI_SF = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutNone << 61);
+            const uint32_t a_lo0 = smem_u32(smem + L::OFF_A) >> 4, b_lo0 = smem_u32(smem + L::OFF_B) >> 4;
+            const uint32_t sfa_lo0 = smem_u32(smem + L::OFF_SFA) >> 4, sfb_lo0 = smem_u32(smem + L::OFF_SFB) >> 4;
+            uint32_t stage = 0, phase = 0, sfs = 0, sf_phase = 0, sf_j = 0, acc_phase = 0, slot = 0, sf_sel = 0;
             for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-                mbar_wait_cluster(tmem_empty, acc_phase ^ 1);
+                mbar_wait(tmem_empty, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (slot ? ACC_SLOT1 : 0u);
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    if (sf_j == 0) mbar_wait(&sf_full[sfs], sf_phase);
                     mbar_wait(&full[stage], phase);
-                    mbar_wait_cluster(&sf_full[stage], phase);
                     tc_fence_after();
+                    const bool last = kb == k_blocks - 1;
+                    const bool sf_done = sf_j == SF_KB - 1 || last;
                     if (elect_one()) {
-                        const uint32_t a_addr = smem_u32(smem + L::OFF_A + stage * L::A_STAGE);
-                        const uint32_t b_addr = smem_u32(smem + L::OFF_B + stage * L::B_STAGE);
-                        const uint32_t sfa_addr = smem_u32(smem + L::OFF_SFA + stage * L::SFA_STAGE);
-                        const uint32_t sfb_addr = smem_u32(smem + L::OFF_SFB + stage * L::SFB_STAGE);
+                        const uint32_t a_lo = a_lo0 + stage * (L::A_STAGE >> 4), b_lo = b_lo0 + stage * (L::B_STAGE >> 4);
+                        const uint32_t sfa_lo = sfa_lo0 + sfs * (L::SFA_STAGE >> 4) + sf_j * (L::SFA_KB >> 4);
+                        const uint32_t sfb_lo = sfb_lo0 + sfs * (L::SFB_STAGE >> 4) + sf_j * (L::SFB_KB >> 4);
                         const uint32_t tm_sfa = tmem_base + TM_SF + sf_sel * SF_BUF_COLS, tm_sfb = tm_sfa + 4;
-                        tc_copy_sf_pair(tm_sfa, smem_desc(sfa_addr, 128, kLayoutNone));
-                        tc_copy_sf_pair(tm_sfb, smem_desc(sfb_addr, 128, kLayoutNone));
-                        tc_copy_sf_pair(tm_sfb + 4, smem_desc(sfb_addr + 512, 128, kLayoutNone));
+                        tc_copy_sf_pair(tm_sfa, HI_SF | sfa_lo);
+                        tc_copy_sf_pair(tm_sfb, HI_SF | sfb_lo);
+                        tc_copy_sf_pair(tm_sfb + 4, HI_SF | (sfb_lo + (512 >> 4)));
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t da = smem_desc(a_addr + k * UMMA_K, 1024, kLayoutSw128);
-                            const uint64_t db = smem_desc(b_addr + k * UMMA_K, 1024, kLayoutSw128);
-                            tc_mma_mx_pair(tmem_d, da, db, idesc_with_sf(idesc, k, k), (kb | k) != 0, tm_sfa, tm_sfb);
-                        }
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)  // advancing K inside the 128B swizzle row = +32 B
+                            tc_mma_mx_pair(tmem_d, HI_OPERAND | (a_lo + k * (UMMA_K >> 4)), HI_OPERAND | (b_lo + k * (UMMA_K >> 4)),
+                                           idesc_with_sf(idesc, k, k), (kb | k) != 0, tm_sfa, tm_sfb);
                         tc_commit_pair(&empty[stage]);
-                        if (kb == k_blocks - 1) tc_commit_pair(tmem_full);
+                        if (sf_done) tc_commit_pair(&sf_empty[sfs]);
+                        if (last) tc_commit_pair(tmem_full);
                     }
                     __syncwarp();
+                    if (sf_done) {
+                        sf_j = 0;
+                        if (++sfs == SF_STAGES) { sfs = 0; sf_phase ^= 1; }
+                    } else {
+                        ++sf_j;
+                    }
                     sf_sel ^= 1;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -615,7 +703,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     } else if (warp == 2 || warp == 3) {
         // ================= scale-factor loaders (both CTAs; warp 2: own 128 A rows, warp 3: all 256 B rows) =================
         const bool is_a = warp == 2;
-        uint32_t stage = 0, phase = 0;
+        uint32_t sfs = 0, sf_phase = 0;
         for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
             int b, mb, nb;
             tile_coords(tile, b, mb, nb);
@@ -625,11 +713,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&sf_full[st]), 0));
             };
             if (is_a)
-                sf_load_tile<1, STAGES>(p.sfa + (int64_t)b * p.sfa_batch, p.ld_sfa, mb * TILE_M + (int)rank * 128, p.M, k_blocks, smem + L::OFF_SFA,
-                                        L::SFA_STAGE, empty, stage, phase, lane, arrive);
+                sf_load_tile4<1>(p.sfa + (int64_t)b * p.sfa_batch, p.ld_sfa, mb * TILE_M + (int)rank * 128, p.M, k_blocks, smem + L::OFF_SFA, L::SFA_KB,
+                                 sf_empty, sfs, sf_phase, lane, arrive);
             else
-                sf_load_tile<2, STAGES>(p.sfb + (int64_t)b * p.sfb_batch, p.ld_sfb, nb * TILE_N, p.N, k_blocks, smem + L::OFF_SFB, L::SFB_STAGE, empty,
-                                        stage, phase, lane, arrive);
+                sf_load_tile4<2>(p.sfb + (int64_t)b * p.sfb_batch, p.ld_sfb, nb * TILE_N, p.N, k_blocks, smem + L::OFF_SFB, L::SFB_KB, sf_empty, sfs,
+                                 sf_phase, lane, arrive);
         }
     } else {
         // ================= epilogue (both CTAs, own 128 x 256 accumulator half) =================
@@ -698,6 +786,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
     }
 
+    __syncwarp();  // single-lane roles (producer, MMA issuer) rejoin their warp before the aligned cluster barrier
     tc_fence_before();
     cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still post on its barriers / read its smem
     if (warp == 3) tmem_dealloc_pair<512>(tmem_base);
@@ -774,7 +863,9 @@ static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CU
     const int64_t tiles = (int64_t)p.m_blocks * p.n_blocks * p.batch;
     const int max_pairs = sm_count / 2;
     const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
-    pair::mx_gemm_pair_kernel<STAGES><<<2 * pairs, pair::kThreads, L::DYN_BYTES, stream>>>(ma, mb, p);
+    const int group_m_env = getenv("MXQ_GEMM_GM") ? atoi(getenv("MXQ_GEMM_GM")) : 0;
+    const int group_m = group_m_env > 0 ? group_m_env : 8;
+    pair::mx_gemm_pair_kernel<STAGES><<<2 * pairs, pair::kThreads, L::DYN_BYTES, stream>>>(ma, mb, p, group_m);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (pair): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;
@@ -794,8 +885,8 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
     if (a->M > 0x7FFFFFFF || a->N > 0x7FFFFFFF || a->K > 0x7FFFFFFF || a->batch > 0x7FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
-    static const int force_narrow = getenv("MXQ_GEMM_NARROW") ? atoi(getenv("MXQ_GEMM_NARROW")) : 0;
-    static const int cfg = getenv("MXQ_GEMM_CFG") ? atoi(getenv("MXQ_GEMM_CFG")) : 0;  // developer knob: <BLOCK_N><STAGES>, 2<STAGES> = CTA pair
+    const int force_narrow = getenv("MXQ_GEMM_NARROW") ? atoi(getenv("MXQ_GEMM_NARROW")) : 0;  // developer knobs, re-read per call
+    const int cfg = getenv("MXQ_GEMM_CFG") ? atoi(getenv("MXQ_GEMM_CFG")) : 0;  // developer knob: <BLOCK_N><STAGES>, 2<STAGES> = CTA pair
     const bool wide = a->N > 128 && !force_narrow;
     CUtensorMap ma, mb;
     const bool use_pair = wide && a->M > 128 && sm_count >= 2 && (cfg == 0 || cfg / 10 == 2);
