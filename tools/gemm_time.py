@@ -18,7 +18,21 @@ for (M, N, K) in shapes:
     B = MXTensor.to_mx(b, wdt, 32)
     ref = A.to_dtype(torch.float32)[:64] @ B.to_dtype(torch.float32).t()
     graphs = {}
+    a8, b8 = a.to(torch.float8_e4m3fn), b.to(torch.float8_e4m3fn)
+    rup = lambda x, m: (x + m - 1) // m * m
+    sa = torch.full((rup(M, 128) * rup(K // 32, 4),), 127, dtype=torch.uint8, device="cuda").view(torch.float8_e8m0fnu)
+    sb = torch.full((rup(N, 128) * rup(K // 32, 4),), 127, dtype=torch.uint8, device="cuda").view(torch.float8_e8m0fnu)
     for c in cfgs:
+        if c == "cublas":  # library ceiling (cuBLASLt MXFP8), context only
+            f = lambda: torch._scaled_mm(a8, b8.t(), scale_a=sa, scale_b=sb, out_dtype=torch.bfloat16)
+            f(); torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph(); st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                with torch.cuda.graph(g, stream=st):
+                    for _ in range(n):
+                        y = f()
+            graphs[c] = (g, float("nan"))
+            continue
         cfg, _, gm = c.partition(":")
         os.environ["MXQ_GEMM_CFG"] = cfg
         os.environ["MXQ_GEMM_GM"] = gm or "0"

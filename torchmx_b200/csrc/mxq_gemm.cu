@@ -78,6 +78,17 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// shared -> global tile store (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1),
+                 "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -208,6 +219,8 @@ struct Params {
     const uint8_t* sfa; const uint8_t* sfb; const uint16_t* bias; uint16_t* d;
     int64_t ld_sfa, ld_sfb, sfa_batch, sfb_batch, ldd, d_batch;
     int M, N, K, batch, m_blocks, n_blocks;
+    int dbg;           // developer hook (MXQ_GEMM_DBG): bit0 = epilogue skips the global stores
+    long long* trace;  // developer hook (MXQ_GEMM_TRACE=<device pointer>): clock64 stamps of pair 0's leader, 8 slots per tile
 };
 
 
@@ -504,7 +517,9 @@ struct Smem {
     static constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
     static constexpr int OFF_SFA = OFF_B + STAGES * B_STAGE;
     static constexpr int OFF_SFB = OFF_SFA + SF_STAGES * SFA_STAGE;
-    static constexpr int OFF_BAR = OFF_SFB + SF_STAGES * SFB_STAGE;
+    static constexpr int EPI_WARP = 2 * 4096;  // per epilogue warp: two buffers of 32 rows x 64 bf16 columns (128B-swizzled rows)
+    static constexpr int OFF_EPI = OFF_SFB + SF_STAGES * SFB_STAGE;
+    static constexpr int OFF_BAR = OFF_EPI + kEpilogueWarps * EPI_WARP;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * SF_STAGES + 2;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM_PTR + 16;
@@ -571,7 +586,8 @@ __device__ __forceinline__ void sf_load_tile4(const uint8_t* base, int64_t ld, i
 
 template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-    mx_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p, const int group_m) {
+    mx_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_d,
+                        const Params p, const int group_m, const int tma_store) {
     using L = Smem<STAGES>;
     extern __shared__ uint8_t smem_raw[];
     // the dynamic shared window starts at the same offset in both CTAs, so the aligned carve-up matches too
@@ -596,6 +612,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if (tma_store) tma_prefetch_desc(&map_d);
     }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < STAGES; ++i) {
@@ -616,6 +633,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     cluster_sync_all();  // the peer's barriers must be initialised before anything is posted on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (p.trace != nullptr && leader && threadIdx.x == 128) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[640 + pair_id] = (long long)t;
+    }
 
     // grouped rasterisation: group_m row-blocks x all column-blocks at a time, row-block fastest, so one wave of
     // pairs touches ~group_m A panels and ~num_pairs/group_m B panels (both stay in L2) instead of every A panel
@@ -660,14 +682,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             const uint32_t a_lo0 = smem_u32(smem + L::OFF_A) >> 4, b_lo0 = smem_u32(smem + L::OFF_B) >> 4;
             const uint32_t sfa_lo0 = smem_u32(smem + L::OFF_SFA) >> 4, sfb_lo0 = smem_u32(smem + L::OFF_SFB) >> 4;
             uint32_t stage = 0, phase = 0, sfs = 0, sf_phase = 0, sf_j = 0, acc_phase = 0, slot = 0, sf_sel = 0;
-            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+            const bool tracing = p.trace != nullptr && pair_id == 0 && lane == 0;
+            int tile_iter = 0;
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tile_iter) {
+                if (tracing) p.trace[tile_iter * 8 + 0] = clock64();
                 mbar_wait(tmem_empty, acc_phase ^ 1);
                 tc_fence_after();
+                if (tracing) p.trace[tile_iter * 8 + 1] = clock64();
                 const uint32_t tmem_d = tmem_base + (slot ? ACC_SLOT1 : 0u);
                 for (int kb = 0; kb < k_blocks; ++kb) {
+                    if (tracing && tile_iter == 2 && kb < 64) p.trace[256 + kb * 4 + 0] = clock64();
                     if (sf_j == 0) mbar_wait(&sf_full[sfs], sf_phase);
+                    if (tracing && tile_iter == 2 && kb < 64) p.trace[256 + kb * 4 + 1] = clock64();
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+                    if (tracing && tile_iter == 2 && kb < 64) p.trace[256 + kb * 4 + 2] = clock64();
+                    if (tracing && kb == 0) p.trace[tile_iter * 8 + 2] = clock64();
                     const bool last = kb == k_blocks - 1;
                     const bool sf_done = sf_j == SF_KB - 1 || last;
                     if (elect_one()) {
@@ -696,6 +726,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     sf_sel ^= 1;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (tracing) p.trace[tile_iter * 8 + 3] = clock64();
                 acc_phase ^= 1;
                 slot ^= 1;
             }
@@ -724,18 +755,76 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const int quad = warp & 3;
         const uint32_t tmem_empty_leader = mapa_shared(smem_u32(tmem_empty), 0);
         uint32_t acc_phase = 0, slot = 0;
-        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const bool tracing = p.trace != nullptr && pair_id == 0 && leader && warp == 4 && lane == 0;
+        int tile_iter = 0;
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tile_iter) {
             int b, mb, nb;
             tile_coords(tile, b, mb, nb);
             mbar_wait(tmem_full, acc_phase);
             tc_fence_after();
+            if (tracing) p.trace[tile_iter * 8 + 4] = clock64();
             const int row = mb * TILE_M + (int)rank * 128 + quad * 32 + lane;
             uint16_t* drow = p.d + (int64_t)b * p.d_batch + (int64_t)row * p.ldd;
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (slot ? ACC_SLOT1 : 0u);
+            if (tma_store) {
+                // Coalesced path: 64-column groups go registers -> 128B-swizzled shared rows -> one TMA store per warp and
+                // group (32 rows x 128 B; rows / columns past the matrix edge are clipped by the tensor map).  Direct
+                // 16-byte st.global from one row per lane costs 32 partial-sector L2 writes per instruction and was
+                // measured to stall the TMA loads of the next tile.
+                uint8_t* ebuf = smem + L::OFF_EPI + quad * L::EPI_WARP;
+                const int first_g = slot ? 0 : 3;  // the 64-column group inside [192,256) of TMEM comes first
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {
+                    const int g = (first_g + h) & 3;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32b_x32(tmem_acc + g * 64, v0);
+                    tmem_ld_32x32b_x32(tmem_acc + g * 64 + 32, v1);
+                    tmem_ld_wait();
+                    if (h == 0) {  // the columns shared with the other slot are in registers: the next tile's MMAs may start
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+                        if (tracing) p.trace[tile_iter * 8 + 5] = clock64();
+                    }
+                    const int col0 = nb * TILE_N + g * 64;
+                    uint8_t* buf = ebuf + (h & 1) * 4096;
+                    if (lane == 0) tma_store_wait_read<1>();  // the store that last read this buffer (two groups ago) is done with it
+                    __syncwarp();
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float f0 = __uint_as_float(v0[2 * i]), f1 = __uint_as_float(v0[2 * i + 1]);
+                        float f2 = __uint_as_float(v1[2 * i]), f3 = __uint_as_float(v1[2 * i + 1]);
+                        if (p.bias != nullptr) {
+                            const int c = col0 + 2 * i;
+                            if (c < p.N) f0 += __uint_as_float((uint32_t)p.bias[c] << 16);
+                            if (c + 1 < p.N) f1 += __uint_as_float((uint32_t)p.bias[c + 1] << 16);
+                            if (c + 32 < p.N) f2 += __uint_as_float((uint32_t)p.bias[c + 32] << 16);
+                            if (c + 33 < p.N) f3 += __uint_as_float((uint32_t)p.bias[c + 33] << 16);
+                        }
+                        pk[i] = pack_bf16x2(f0, f1);
+                        pk[16 + i] = pack_bf16x2(f2, f3);
+                    }
+                    // lane = row of the 32-row box; 16-byte chunk c of the row lives at chunk (c ^ (row & 7)) (SWIZZLE_128B)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&map_d, buf, col0, mb * TILE_M + (int)rank * 128 + quad * 32, b);
+                        tma_store_commit();
+                    }
+                }
+                if (tracing) p.trace[tile_iter * 8 + 6] = clock64();
+                acc_phase ^= 1;
+                slot ^= 1;
+                continue;
+            }
             const int first = slot ? 0 : 6;  // the two 32-column chunks inside [192,256) of TMEM come first
             auto store_chunk = [&](const uint32_t (&v)[32], int c) {
                 const int col0 = nb * TILE_N + c * 32;
-                if (row < p.M && col0 < p.N) {
+                if (row < p.M && col0 < p.N && !(p.dbg & 1)) {
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -770,6 +859,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+                if (tracing) p.trace[tile_iter * 8 + 5] = clock64();
                 store_chunk(v0, first);
                 store_chunk(v1, first + 1);
             }
@@ -781,11 +871,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 tmem_ld_wait();
                 store_chunk(v, c);
             }
+            if (tracing) p.trace[tile_iter * 8 + 6] = clock64();
             acc_phase ^= 1;
             slot ^= 1;
         }
     }
 
+    if (p.trace != nullptr && leader && threadIdx.x == 128) {  // epilogue warp 4 of every leader: when did this pair finish (ns)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[512 + pair_id] = (long long)t;
+    }
+    if (tma_store && warp >= 4 && lane == 0) tma_store_wait<0>();  // this thread's bulk stores have left shared memory and are performed
     __syncwarp();  // single-lane roles (producer, MMA issuer) rejoin their warp before the aligned cluster barrier
     tc_fence_before();
     cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still post on its barriers / read its smem
@@ -834,6 +931,8 @@ static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUt
     p.ld_sfa = a->ld_sfa; p.ld_sfb = a->ld_sfb; p.sfa_batch = a->sfa_batch_stride; p.sfb_batch = a->sfb_batch_stride;
     p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
+    p.trace = nullptr;
+    p.dbg = 0;
     p.m_blocks = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
     p.n_blocks = (int)((a->N + BLOCK_N - 1) / BLOCK_N);
     const int64_t tiles = (int64_t)p.m_blocks * p.n_blocks * p.batch;
@@ -844,6 +943,18 @@ static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUt
     return MXQ_OK;
 }
 
+
+// D: [batch][M][N] bf16, box = 64 columns x 32 rows, 128B swizzle (one epilogue warp's staging buffer)
+static bool make_d_map(CUtensorMap* map, void* base, int64_t N, int64_t M, int64_t batch, int64_t ldd, int64_t batch_stride) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ldd * 2, (cuuint64_t)(batch > 1 ? batch_stride : ldd * M) * 2};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 template <int STAGES>
 static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t stream, char* msg,
@@ -858,6 +969,8 @@ static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CU
     p.ld_sfa = a->ld_sfa; p.ld_sfb = a->ld_sfb; p.sfa_batch = a->sfa_batch_stride; p.sfb_batch = a->sfb_batch_stride;
     p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
+    p.dbg = getenv("MXQ_GEMM_DBG") ? atoi(getenv("MXQ_GEMM_DBG")) : 0;
+    p.trace = getenv("MXQ_GEMM_TRACE") ? reinterpret_cast<long long*>(strtoull(getenv("MXQ_GEMM_TRACE"), nullptr, 0)) : nullptr;
     p.m_blocks = (int)((a->M + pair::TILE_M - 1) / pair::TILE_M);
     p.n_blocks = (int)((a->N + pair::TILE_N - 1) / pair::TILE_N);
     const int64_t tiles = (int64_t)p.m_blocks * p.n_blocks * p.batch;
@@ -865,7 +978,12 @@ static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CU
     const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
     const int group_m_env = getenv("MXQ_GEMM_GM") ? atoi(getenv("MXQ_GEMM_GM")) : 0;
     const int group_m = group_m_env > 0 ? group_m_env : 8;
-    pair::mx_gemm_pair_kernel<STAGES><<<2 * pairs, pair::kThreads, L::DYN_BYTES, stream>>>(ma, mb, p, group_m);
+    // coalesced TMA-store epilogue needs a 16-byte aligned D with a 16-byte multiple row pitch; otherwise direct stores
+    CUtensorMap md;
+    int tma_store = ((uintptr_t)a->d % 16 == 0) && (a->ldd % 8 == 0) && (a->d_batch_stride % 8 == 0) && !(p.dbg & 2);
+    if (tma_store && !make_d_map(&md, a->d, a->N, a->M, a->batch, a->ldd, a->d_batch_stride)) tma_store = 0;
+    if (!tma_store) md = ma;  // unused placeholder
+    pair::mx_gemm_pair_kernel<STAGES><<<2 * pairs, pair::kThreads, L::DYN_BYTES, stream>>>(ma, mb, md, p, group_m, tma_store);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (pair): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;
@@ -897,8 +1015,7 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
             return MXQ_ERR_UNSUPPORTED_SHAPE;
         }
         if (cfg == 24) return launch_pair<4>(a, ma, mb, sm_count, stream, msg, msg_len);
-        if (cfg == 25) return launch_pair<5>(a, ma, mb, sm_count, stream, msg, msg_len);
-        return launch_pair<6>(a, ma, mb, sm_count, stream, msg, msg_len);
+        return launch_pair<5>(a, ma, mb, sm_count, stream, msg, msg_len);
     }
     if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M) ||
         !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128)) {
