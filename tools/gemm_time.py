@@ -59,4 +59,5 @@ for (M, N, K) in shapes:
                 times[c].append(e0.elapsed_time(e1) / n * 1e3)
     for c in cfgs:
         t = times[c]
-        print(f"{M}x{N}x{K} cfg={c}: min {min(t):.1f} us ({2*M*N*K/min(t)/1e6:.0f} TFLOP/s) median {statistics.median(t):.1f} us relerr {graphs[c][1]:.2e}", flush=True)
+        wbytes = N * K * (1 + 1 / 32) + M * K * (1 + 1 / 32) + M * N * 2
+        print(f"{M}x{N}x{K} cfg={c}: min {min(t):.1f} us ({2*M*N*K/min(t)/1e6:.0f} TFLOP/s, {wbytes/min(t)/1e3:.0f} GB/s operand+output bytes) median {statistics.median(t):.1f} us relerr {graphs[c][1]:.2e}", flush=True)

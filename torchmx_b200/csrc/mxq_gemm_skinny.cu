@@ -1,0 +1,322 @@
+// K3c: skinny MX GEMM for decode-sized activations (M <= 128 rows), HBM-bound weight streaming.
+//
+//   D[t][n] = sum_k ( X[t][k] * 2^(sfx[t][k/32]-127) ) * ( W[n][k] * 2^(sfw[n][k/32]-127) ) (+ bias[n])
+//
+// Same contraction as K3 (torchmx/ops.py:29-41 with a [tokens, K] activation and an [N, K] weight), but the roles of
+// the MMA operands are swapped: the WEIGHT rows are the MMA M dimension (128 per CTA) and the tokens are the MMA N
+// dimension (32 / 64 / 128 columns), so a CTA streams a 128-row slab of W exactly once and the tensor core never
+// idles on padding rows.  What bounds the kernel is reading W once from HBM: the grid is n_tiles x S CTAs where the
+// S CTAs of a cluster split K, so that ~one CTA per SM is streaming even when N / 128 is far below the SM count
+// (q/k/v/o projections).  The S partial accumulators are reduced through distributed shared memory in a fixed
+// order (deterministic), each CTA finishing 1/S of the tokens.
+//
+// Per CTA: warp 0 TMA producer (W 128 x 128 B + X N_TOK x 128 B per K block, STAGES-deep ring), warp 1 MMA issuer
+// (tcgen05.mma cta_group::1 kind::mxf8f6f4.block_scale, M=128, N=N_TOK), warps 2/3 scale-factor loaders (W rows /
+// token rows, four K blocks per ring stage), warps 4..7 epilogue.
+#include "mxq_tc.cuh"
+
+namespace mxq {
+namespace gemm {
+namespace skinny {
+
+constexpr int TILE_W = 128;  // weight rows per CTA
+constexpr int kThreads = 256;
+constexpr int SF_KB_BYTES = 512;  // one K block of scale factors for (up to) 128 rows
+
+struct Params {
+    const uint8_t* sfx; const uint8_t* sfw; const uint16_t* bias; uint16_t* d;
+    int64_t ld_sfx, ld_sfw, ldd;
+    int M, N, K, splits;
+    int w_tiled;  // W codes are the tile-major shadow ([N/128][K/128][128][128 B])
+    int pf_dist;  // L2 prefetch distance of the W stream, in K blocks
+    int sf_tma;   // scales are 16-byte aligned with a 16-byte multiple row pitch: fetch them with TMA (deep prefetch)
+};
+
+constexpr int RAW_X = 2;  // raw scale ring of the (L2-resident) token scales
+
+template <int N_TOK, int STAGES, int RAW_W>
+struct Smem {
+    static constexpr int W_STAGE = TILE_W * BLOCK_K;  // 16 KB
+    static constexpr int X_STAGE = N_TOK * BLOCK_K;   // 4 / 8 / 16 KB
+    static constexpr int SF_STAGE = SF_KB * SF_KB_BYTES;
+    static constexpr int OFF_W = 0;
+    static constexpr int OFF_X = OFF_W + STAGES * W_STAGE;
+    static constexpr int OFF_SFW = OFF_X + STAGES * X_STAGE;
+    static constexpr int OFF_SFX = OFF_SFW + SF_STAGES * SF_STAGE;
+    static constexpr int OFF_RAW_W = OFF_SFX + SF_STAGES * SF_STAGE;  // TMA landing buffers of the scales: [128 rows][16 B] each
+    static constexpr int OFF_RAW_X = OFF_RAW_W + RAW_W * 2048;
+    static constexpr int OFF_BAR = OFF_RAW_X + RAW_X * 2048;
+    static constexpr int NUM_BARS = 2 * STAGES + 2 * SF_STAGES + 1 + RAW_W + RAW_X;
+    static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+    static constexpr int TOTAL = OFF_TMEM_PTR + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;
+    // split-K partials (fp32 [N_TOK][128], token-major so that a warp writes / reads 128 contiguous bytes) reuse the
+    // W ring once every MMA has retired
+    static_assert(STAGES * W_STAGE >= N_TOK * TILE_W * 4, "partial-sum buffer does not fit the W ring");
+    static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
+
+template <int N_TOK, int STAGES, int RAW_W>
+__global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                                                                  const __grid_constant__ CUtensorMap map_sfw,
+                                                                  const __grid_constant__ CUtensorMap map_sfx, const Params p) {
+    using L = Smem<N_TOK, STAGES, RAW_W>;
+    constexpr int TMEM_COLS = N_TOK + 16 <= 64 ? 64 : (N_TOK + 16 <= 128 ? 128 : 256);
+    constexpr uint32_t TM_SF = N_TOK, SF_BUF_COLS = 8;  // two buffers of (4 W + 4 X) scale-factor columns
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* full = bars;                       // TMA bytes landed              (count 1 + tx)
+    uint64_t* empty = bars + STAGES;             // MMAs of the stage retired     (count 1, tcgen05.commit)
+    uint64_t* sf_full = bars + 2 * STAGES;       // scale factors in smem         (count 2: both loader warps)
+    uint64_t* sf_empty = sf_full + SF_STAGES;    // MMAs using the SF stage retired (count 1, tcgen05.commit)
+    uint64_t* tmem_full = sf_empty + SF_STAGES;  // accumulator complete          (count 1, tcgen05.commit)
+    uint64_t* raw_w = tmem_full + 1;             // raw W-scale boxes landed      (count 1 + tx)
+    uint64_t* raw_x = raw_w + RAW_W;             // raw token-scale boxes landed  (count 1 + tx)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_PTR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.splits;
+    const int tile = blockIdx.x / S;
+    const int split = (int)cluster_ctarank();  // == blockIdx.x % S: the cluster spans the K splits of one tile
+    const int k_blocks_total = p.K / BLOCK_K;
+    const int kb0 = (int)((int64_t)k_blocks_total * split / S), kb1 = (int)((int64_t)k_blocks_total * (split + 1) / S);
+    const int k_blocks = kb1 - kb0;
+    const int n0 = tile * TILE_W;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_x);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < SF_STAGES; ++i) {
+            mbar_init(&sf_full[i], 2);
+            mbar_init(&sf_empty[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        for (int i = 0; i < RAW_W; ++i) mbar_init(&raw_w[i], 1);
+        for (int i = 0; i < RAW_X; ++i) mbar_init(&raw_x[i], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (warp == 3) tmem_alloc<TMEM_COLS>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            // The TMA unit keeps only a few tens of KB of loads in flight per SM, which at DRAM latency is ~1/3 of the HBM
+            // rate; L2 prefetches are fire-and-forget, so W is pulled DRAM -> L2 `pf_dist` K blocks ahead of the ring and
+            // the ring's own loads become L2 hits.
+            const int pf_dist = p.pf_dist;
+            for (int kb = kb0; kb < kb1 && kb < kb0 + pf_dist; ++kb) tma_prefetch_l2_3d(&map_w, kb * BLOCK_K, n0, 0);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if (kb + pf_dist < kb1) tma_prefetch_l2_3d(&map_w, (kb + pf_dist) * BLOCK_K, n0, 0);
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full[stage], L::W_STAGE + L::X_STAGE);
+                if (p.w_tiled)
+                    tma_load_4d(&map_w, &full[stage], smem + L::OFF_W + stage * L::W_STAGE, 0, 0, kb, tile);
+                else
+                    tma_load_3d(&map_w, &full[stage], smem + L::OFF_W + stage * L::W_STAGE, kb * BLOCK_K, n0, 0);
+                tma_load_3d(&map_x, &full[stage], smem + L::OFF_X + stage * L::X_STAGE, kb * BLOCK_K, 0, 0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+        constexpr uint32_t idesc = make_idesc(TILE_W, N_TOK);
+        constexpr uint64_t HI_OPERAND = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutSw128 << 61);
+        constexpr uint64_t HI_SF = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutNone << 61);
+        const uint32_t w_lo0 = smem_u32(smem + L::OFF_W) >> 4, x_lo0 = smem_u32(smem + L::OFF_X) >> 4;
+        const uint32_t sfw_lo0 = smem_u32(smem + L::OFF_SFW) >> 4, sfx_lo0 = smem_u32(smem + L::OFF_SFX) >> 4;
+        uint32_t stage = 0, phase = 0, sfs = 0, sf_phase = 0, sf_j = 0, sf_sel = 0;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+            if (sf_j == 0) mbar_wait(&sf_full[sfs], sf_phase);
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const bool last = kb == k_blocks - 1;
+            const bool sf_done = sf_j == SF_KB - 1 || last;
+            if (elect_one()) {
+                const uint32_t w_lo = w_lo0 + stage * (L::W_STAGE >> 4), x_lo = x_lo0 + stage * (L::X_STAGE >> 4);
+                const uint32_t sf_off = sfs * (L::SF_STAGE >> 4) + sf_j * (SF_KB_BYTES >> 4);
+                const uint32_t tm_sfw = tmem_base + TM_SF + sf_sel * SF_BUF_COLS, tm_sfx = tm_sfw + 4;
+                tc_copy_sf(tm_sfw, HI_SF | (sfw_lo0 + sf_off));
+                tc_copy_sf(tm_sfx, HI_SF | (sfx_lo0 + sf_off));
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                    tc_mma_mx(tmem_base, HI_OPERAND | (w_lo + k * (UMMA_K >> 4)), HI_OPERAND | (x_lo + k * (UMMA_K >> 4)), idesc_with_sf(idesc, k, k),
+                              (kb | k) != 0, tm_sfw, tm_sfx);
+                tc_commit(&empty[stage]);
+                if (sf_done) tc_commit(&sf_empty[sfs]);
+                if (last) tc_commit(tmem_full);
+            }
+            __syncwarp();
+            if (sf_done) {
+                sf_j = 0;
+                if (++sfs == SF_STAGES) { sfs = 0; sf_phase ^= 1; }
+            } else {
+                ++sf_j;
+            }
+            sf_sel ^= 1;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ================= scale-factor loaders (warp 2: the 128 W rows, warp 3: the token rows) =================
+        uint32_t sfs = 0, sf_phase = 0;
+        auto arrive = [&](uint32_t st) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sf_full[st]);
+        };
+        if (p.sf_tma) {
+            if (warp == 2)
+                sf_tma_tile4<RAW_W>(&map_sfw, kb0 * 4, n0, k_blocks, smem + L::OFF_RAW_W, raw_w, smem + L::OFF_SFW, sf_empty, sfs, sf_phase, lane, arrive);
+            else
+                sf_tma_tile4<RAW_X>(&map_sfx, kb0 * 4, 0, k_blocks, smem + L::OFF_RAW_X, raw_x, smem + L::OFF_SFX, sf_empty, sfs, sf_phase, lane, arrive);
+        } else if (warp == 2) {
+            sf_load_tile4<1>(p.sfw + (int64_t)kb0 * 4, p.ld_sfw, n0, p.N, k_blocks, smem + L::OFF_SFW, SF_KB_BYTES, sf_empty, sfs, sf_phase, lane, arrive);
+        } else {
+            sf_load_tile4<1>(p.sfx + (int64_t)kb0 * 4, p.ld_sfx, 0, p.M, k_blocks, smem + L::OFF_SFX, SF_KB_BYTES, sf_empty, sfs, sf_phase, lane, arrive);
+        }
+    } else {
+        // ================= epilogue, part 1: accumulator -> global (S == 1) or -> partial-sum buffer (S > 1) =================
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;  // accumulator lane == weight row within the tile
+        const int n = n0 + r;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        float* part = reinterpret_cast<float*>(smem + L::OFF_W);
+        const float bias = (S == 1 && p.bias != nullptr && n < p.N) ? __uint_as_float((uint32_t)p.bias[n] << 16) : 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < N_TOK / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+            tmem_ld_wait();
+            if (S == 1) {
+                if (n < p.N) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int t = c * 32 + i;
+                        if (t < p.M) p.d[(int64_t)t * p.ldd + n] = (uint16_t)pack_bf16x2(__uint_as_float(v[i]) + bias, 0.0f);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) part[(c * 32 + i) * TILE_W + r] = __uint_as_float(v[i]);
+            }
+        }
+        tc_fence_before();
+    }
+
+    if (S > 1) {
+        // ================= epilogue, part 2: fixed-order reduction of the S partials through DSMEM =================
+        __syncwarp();
+        cluster_sync_all();  // every CTA's partials are written (and every MMA has retired, so the W ring was free to reuse)
+        if (warp >= 4) {
+            const int r = (warp & 3) * 32 + lane;
+            const int n = n0 + r;
+            const uint32_t part_addr = smem_u32(smem + L::OFF_W);
+            const float bias = (p.bias != nullptr && n < p.N) ? __uint_as_float((uint32_t)p.bias[n] << 16) : 0.0f;
+            for (int t = split; t < p.M; t += S) {  // this CTA finishes tokens split, split + S, ...
+                float acc = 0.0f;
+                for (int s = 0; s < S; ++s) acc += ld_dsmem_f32(mapa_shared(part_addr + (uint32_t)(t * TILE_W + r) * 4u, (uint32_t)s));
+                if (n < p.N) p.d[(int64_t)t * p.ldd + n] = (uint16_t)pack_bf16x2(acc + bias, 0.0f);
+            }
+        }
+        __syncwarp();
+        cluster_sync_all();  // nobody exits while a peer may still read its partials
+    } else {
+        __syncwarp();
+        __syncthreads();
+    }
+    if (warp == 3) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int N_TOK, int STAGES, int RAW_W>
+static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, char* msg, size_t msg_len) {
+    using L = Smem<N_TOK, STAGES, RAW_W>;
+    CUtensorMap mw, mx;
+    const int fake_tiled = getenv("MXQ_SKINNY_FAKE_TILED") ? atoi(getenv("MXQ_SKINNY_FAKE_TILED")) : 0;  // timing experiment only (wrong results)
+    const bool w_ok = fake_tiled ? make_tiled_operand_map(&mw, a->b_codes, a->K, a->N / 128 * 128, 1) : make_operand_map(&mw, a->b_codes, a->K, a->N, 1, a->ldb, 0, TILE_W);
+    if (!w_ok || !make_operand_map(&mx, a->a_codes, a->K, a->M, 1, a->lda, 0, N_TOK)) {
+        snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    // scales by TMA when their layout allows it (every split then starts on a 16-byte boundary: splits are 4-K-block aligned)
+    CUtensorMap msw = mw, msx = mx;
+    const int k_blocks_total = (int)(a->K / BLOCK_K);
+    int sf_tma = ((uintptr_t)a->sfa % 16 == 0) && ((uintptr_t)a->sfb % 16 == 0) && (a->ld_sfa % 16 == 0) && (a->ld_sfb % 16 == 0) &&
+                 (k_blocks_total % (splits * SF_KB) == 0) && !getenv("MXQ_SKINNY_NO_SFTMA");
+    if (sf_tma && (!make_scale_map(&msw, a->sfb, a->K / 32, a->N, a->ld_sfb) || !make_scale_map(&msx, a->sfa, a->K / 32, a->M, a->ld_sfa))) sf_tma = 0;
+    auto kernel = mx_gemm_skinny_kernel<N_TOK, STAGES, RAW_W>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    Params p;
+    p.sfx = a->sfa; p.sfw = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
+    p.ld_sfx = a->ld_sfa; p.ld_sfw = a->ld_sfb; p.ldd = a->ldd;
+    p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.splits = splits;
+    p.w_tiled = fake_tiled;
+    p.sf_tma = sf_tma;
+    p.pf_dist = getenv("MXQ_SKINNY_PF") ? atoi(getenv("MXQ_SKINNY_PF")) : 0;  // measured: no gain on B200 (0 = off)
+    const int n_tiles = (int)((a->N + TILE_W - 1) / TILE_W);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_tiles * splits), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = L::DYN_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)splits;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, mw, mx, msw, msx, p);
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (skinny): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    return MXQ_OK;
+}
+
+}  // namespace skinny
+
+// M <= 128, batch == 1.  Returns MXQ_ERR_UNSUPPORTED_SHAPE when the caller should use the general kernels.
+int launch_gemm_skinny(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, char* msg, size_t msg_len) {
+    using namespace skinny;
+    if (a->batch != 1 || a->M > 128 || a->K % BLOCK_K) return MXQ_ERR_UNSUPPORTED_SHAPE;
+    const int k_blocks = (int)(a->K / BLOCK_K);
+    const int n_tiles = (int)((a->N + TILE_W - 1) / TILE_W);
+    // split K across a cluster until about one CTA per SM is streaming; keep >= 4 K blocks per CTA and 4-K-block aligned
+    // split points (the scale-factor loaders read 16 bytes = 4 K blocks per row)
+    int splits = 1;
+    const int forced = getenv("MXQ_SKINNY_SPLITS") ? atoi(getenv("MXQ_SKINNY_SPLITS")) : 0;
+    if (forced > 0) {
+        splits = forced;
+    } else {
+        while (splits < 8 && n_tiles * splits * 2 <= sm_count && k_blocks % (splits * 2 * 4) == 0 && k_blocks / (splits * 2) >= 4) splits *= 2;
+    }
+    if (splits > k_blocks) splits = k_blocks;
+    const bool deep = (int64_t)n_tiles * splits <= sm_count;  // one CTA per SM: spend the shared memory on a deeper ring
+    if (a->M <= 32) return deep ? launch<32, 8, 8>(a, splits, stream, msg, msg_len) : launch<32, 4, 4>(a, splits, stream, msg, msg_len);
+    if (a->M <= 64) return deep ? launch<64, 7, 8>(a, splits, stream, msg, msg_len) : launch<64, 4, 4>(a, splits, stream, msg, msg_len);
+    return deep ? launch<128, 6, 4>(a, splits, stream, msg, msg_len) : launch<128, 4, 4>(a, splits, stream, msg, msg_len);
+}
+
+}  // namespace gemm
+}  // namespace mxq

@@ -24,7 +24,7 @@ aten = torch.ops.aten
 _DISABLED = os.environ.get("MXQ_DISABLE_TC", "0") == "1"
 _SHADOW_ATTR = "_mxq_e4m3_shadow"
 
-stats = {"tensor_core": 0, "fallback": 0}
+stats = {"tensor_core": 0, "fallback": 0, "transcode": 0}
 
 
 def set_enabled(flag: bool) -> None:
@@ -32,16 +32,21 @@ def set_enabled(flag: bool) -> None:
     _DISABLED = not flag
 
 
-def _e4m3_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+def _e4m3_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[MXTensor]) -> Optional[torch.Tensor]:
     """codes: [..., rows, Kb] with unit stride along Kb -> uint8 [..., rows, K] E4M3-container bytes.
     float8_e4m3 passes through untouched (a view); fp6 / fp4 are transcoded exactly by the CUDA
-    transcoder, and the result is cached on `cache_on` (the weight's storage tensor) when given."""
+    transcoder.  When `cache_on` is given (the long-lived MXTensor the operand is a view of, i.e. a layer's
+    weight) the result is cached on that Python object, keyed by the view geometry and the version counter
+    of the codes, so a weight is transcoded once, not once per forward."""
     if elem == dtypes.float8_e4m3:
         return codes
+    key = None
     if cache_on is not None:
+        key = (codes.data_ptr(), tuple(codes.shape), tuple(codes.stride()), cache_on._data._version)
         hit = cache_on.__dict__.get(_SHADOW_ATTR)
-        if hit is not None and hit[0] == (codes.data_ptr(), tuple(codes.shape), tuple(codes.stride()), cache_on._version):
+        if hit is not None and hit[0] == key:
             return hit[1]
+    stats["transcode"] += 1
     src = codes.contiguous()
     per = 2 if elem == dtypes.float4_e2m1 else 1
     out = torch.empty(tuple(src.shape[:-1]) + (src.shape[-1] * per,), dtype=torch.uint8, device=src.device)
@@ -49,7 +54,7 @@ def _e4m3_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[torch
                                         _stream_ptr(src))
     _C.check(rc, "mxq_transcode_to_e4m3")
     if cache_on is not None:
-        cache_on.__dict__[_SHADOW_ATTR] = ((codes.data_ptr(), tuple(codes.shape), tuple(codes.stride()), cache_on._version), out)
+        cache_on.__dict__[_SHADOW_ATTR] = (key, out)
     return out
 
 
@@ -139,9 +144,9 @@ def _dispatch(aten_op, a, b, extra_front, extra_back):
         lead_shape = tuple(a.shape[:-1])
 
     # E4M3-container operands (exact transcode of fp6 / fp4 codes; weights cache theirs on the storage tensor)
-    b_base = b._data._base if b._data._base is not None else b._data
+    b_origin = getattr(b, "_mxq_origin", b)
     a_e = _e4m3_rows(a_codes, a._elem_dtype, None)
-    b_e = _e4m3_rows(b_codes, b._elem_dtype, b_base if not batched else None)
+    b_e = _e4m3_rows(b_codes, b._elem_dtype, b_origin if not batched else None)
     if a_e.stride(-1) != 1 or b_e.stride(-1) != 1:
         return None
     out = torch.empty(lead_shape + (N,), dtype=torch.bfloat16, device=a._data.device)
