@@ -168,6 +168,79 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def measured_tensor_peaks():
+    """(nominal block-scaled fp8/fp6 dense peak, 2 x measured cuBLAS bf16 burst) in TFLOP/s"""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return 4500.0, 2.0 * float(json.load(f)["bf16_tflops"]), "2 x MEASURED_PEAKS.json bf16_tflops (cuBLAS burst, measured)"
+    except Exception:
+        return 4500.0, 2.0 * 1590.0, "2 x fallback 1.59 PFLOP/s (B200_PROFILING.md)"
+
+
+def mx_matmul_extras(dev):
+    """Secondary numbers of the metric ("MX matmul TFLOP/s", BASELINE configs[2]): the 8192^3 fp8_e4m3 x fp6_e3m2 MX linear,
+    the 4-D attention Q@K^T MX bmm and one decode-sized linear, each through the public op (F.linear / torch.matmul on
+    MXTensors), replayed from a CUDA graph (10 launches) so host dispatch is not in the number; min / median of 5 replays."""
+    import torch
+    from torchmx_b200 import dtypes, mx_gemm
+    from torchmx_b200.mx_tensor import MXTensor
+
+    def timed(fn, n=10, rounds=5):
+        fn()
+        torch.cuda.synchronize()
+        g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(n):
+                    fn()
+        ts = []
+        for r in range(rounds + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            if r:
+                ts.append(e0.elapsed_time(e1) / n * 1e3)
+        return min(ts), statistics.median(ts)
+
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(7)
+    before = dict(mx_gemm.stats)
+    # (1) 8192^3 linear
+    M = N = K = 8192
+    A = MXTensor.to_mx(torch.randn(M, K, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.float8_e4m3, BLOCK)
+    W = MXTensor.to_mx(torch.randn(N, K, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.float6_e3m2, BLOCK)
+    us_min, us_med = timed(lambda: torch.nn.functional.linear(A, W))
+    nominal, meas2, src = measured_tensor_peaks()
+    flops = 2.0 * M * N * K
+    out["linear_8192x8192x8192_e4m3xe3m2"] = {
+        "us": round(us_med, 1), "us_best": round(us_min, 1), "TFLOP/s": round(flops / us_med / 1e6, 1),
+        "roofline": {"bound": "tensor", "kernel": "mx_gemm_pair_kernel (tcgen05 cta_group::2 kind::mxf8f6f4.block_scale)",
+                     "achieved": round(flops / us_med / 1e6, 1), "peak": nominal, "unit": "TFLOP/s", "frac": round(flops / us_med / 1e6 / nominal, 4),
+                     "peak_source": "nominal dense block-scaled fp8/fp6 (4.5 PFLOP/s)", "frac_of_2x_measured_bf16": round(flops / us_med / 1e6 / meas2, 4),
+                     "peak_2x_measured_bf16": meas2, "peak_2x_source": src, "flop_per_launch": flops}}
+    del A, W
+    # (2) attention-shaped batched MX bmm: Q @ K^T, [1, 32, 2048, 128] x [1, 32, 2048, 128]^T -> bf16 [1, 32, 2048, 2048] (output-bound)
+    Q = MXTensor.to_mx(torch.randn(1, 32, 2048, 128, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.float8_e4m3, BLOCK)
+    Kt = MXTensor.to_mx(torch.randn(1, 32, 2048, 128, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.float6_e3m2, BLOCK)
+    us_min, us_med = timed(lambda: torch.matmul(Q, Kt.transpose(2, 3)))
+    qk_bytes = 32 * 2048 * 2048 * 2 + 2 * 32 * 2048 * 128 * (1 + 1 / 32)
+    out["bmm_qk_1x32x2048x2048x128"] = {"us": round(us_med, 1), "us_best": round(us_min, 1), "GB/s": round(qk_bytes / us_med / 1e3, 1),
+                                        "TFLOP/s": round(2.0 * 32 * 2048 * 2048 * 128 / us_med / 1e6, 1), "bound": "hbm (268 MB bf16 output)"}
+    del Q, Kt
+    # (3) decode-sized linear (batch 32 x Llama-3-8B gate_proj): weight streaming
+    X = MXTensor.to_mx(torch.randn(32, 4096, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.float8_e4m3, BLOCK)
+    W = MXTensor.to_mx(torch.randn(14336, 4096, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.float6_e3m2, BLOCK)
+    us_min, us_med = timed(lambda: torch.nn.functional.linear(X, W))
+    w_bytes = 14336 * 4096 * (1 + 1 / 32) + 32 * 4096 * (1 + 1 / 32) + 32 * 14336 * 2
+    out["linear_32x14336x4096_decode"] = {"us": round(us_med, 1), "us_best": round(us_min, 1), "GB/s": round(w_bytes / us_med / 1e3, 1),
+                                          "bound": "hbm (weight codes + scales read once)"}
+    out["tensor_core_calls"] = mx_gemm.stats["tensor_core"] - before["tensor_core"]
+    out["fallback_calls"] = mx_gemm.stats["fallback"] - before["fallback"]
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -299,6 +372,11 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e_value = world * step_bytes(n_elems) * e2e_steps / e2e_s / 1e9 if e2e_steps else 0.0
 
+    extras = None
+    if rank == 0 and not args.skip_gemm:
+        del xs, xh, yh, ch, sh
+        torch.cuda.empty_cache()
+        extras = mx_matmul_extras(dev)
     if rank == 0:
         cpu_threads = os.cpu_count() or 1
         cpu_rows = 2048
@@ -323,6 +401,7 @@ def run_b200(args):
                 "value": round(cpu_value, 3), "unit": "GB/s", "cores": cpu_threads, "kind": "port",
                 "sample": f"{cpu_rows}x{COLS} rows of the workload (1/8), all 5 elem dtypes, quantize+dequantize, best of 2, {cpu_dt:.2f} s"},
             "kernels": {k: {"us": round(v["ms"] * 1e3, 2), "GB/s": round(v["GB/s"], 1)} for k, v in kernels.items()},
+            "mx_matmul": extras,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -337,6 +416,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: skip the cpu_baseline leg")
+    ap.add_argument("--skip-gemm", action="store_true", help="skip the secondary MX matmul numbers (rank 0, after the timed sweep)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -52,6 +52,20 @@ CASES = [
     (512, 512, 128, "float8_e4m3", "float6_e3m2", False, 4, 0),
     (77, 300, 256, "float4_e2m1", "float4_e2m1", False, 3, 0),
     (1024, 2048, 2048, "float8_e4m3", "float6_e3m2", False, 0, 4),
+    # CTA-pair kernel (M > 128 and N > 128): ragged M / N with the TMA-store epilogue (N % 8 == 0) and the direct-store
+    # fallback (N % 8 != 0), bias, batches, a K that is not a multiple of the 4-K-block scale ring
+    (300, 520, 640, "float8_e4m3", "float6_e3m2", True, 0, 6),
+    (257, 129, 384, "float8_e4m3", "float4_e2m1", True, 0, 0),
+    (640, 300, 256, "float6_e3m2", "float6_e2m3", False, 2, 0),
+    (2048, 2048, 128, "float8_e4m3", "float6_e3m2", False, 3, 0),
+    # skinny weight-streaming kernel (M <= 128, not batched): all token-tile widths, cluster split-K, ragged N
+    (32, 4096, 4096, "float8_e4m3", "float6_e3m2", True, 0, 6),
+    (17, 1000, 1024, "float8_e4m3", "float4_e2m1", False, 0, 0),
+    (64, 1024, 4096, "float8_e4m3", "float6_e3m2", True, 0, 0),
+    (100, 384, 2048, "float6_e2m3", "float6_e3m2", False, 0, 12),
+    (128, 7168, 1024, "float8_e4m3", "float6_e3m2", False, 0, 0),
+    (5, 2048, 7168, "float8_e4m3", "float6_e3m2", True, 0, 0),
+    (8, 640, 384, "float8_e4m3", "float8_e4m3", False, 0, 0),
 ]
 
 
@@ -120,6 +134,43 @@ def test_matmul_entry_points_agree(mx):
     Vt = MXTensor.to_mx(v.transpose(2, 3).contiguous(), dtypes.float6_e3m2, 32)  # [.., 64, 128] blocked along seq
     o = torch.matmul(P, Vt.transpose(2, 3))
     _tol_check(o, P, Vt, None, "p @ v")
+
+
+@pytest.mark.parametrize("splits", ["1", "2", "4", "8"])
+def test_skinny_split_k_is_deterministic_and_consistent(mx, monkeypatch, splits):
+    """The K splits of the decode kernel are reduced through DSMEM in a fixed order: repeated launches are
+    bit-identical, and every split count stays within the matmul tolerance."""
+    from torchmx import dtypes
+    from torchmx.mx_tensor import MXTensor
+    monkeypatch.setenv("MXQ_SKINNY_SPLITS", splits)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(32, 4096, device=DEV, dtype=torch.bfloat16, generator=g)
+    w = torch.randn(1536, 4096, device=DEV, dtype=torch.bfloat16, generator=g)
+    X, W = MXTensor.to_mx(x, dtypes.float8_e4m3, 32), MXTensor.to_mx(w, dtypes.float6_e3m2, 32)
+    y0 = torch.nn.functional.linear(X, W)
+    for _ in range(3):
+        assert torch.equal(torch.nn.functional.linear(X, W), y0)
+    _tol_check(y0, X, W, None, f"skinny splits={splits}")
+
+
+def test_weight_shadow_is_cached_and_invalidated(mx):
+    """fp6 / fp4 weights are transcoded to the E4M3 container once per weight, not once per call (F.linear reaches the
+    kernel as aten.t + aten.mm on short-lived views), and again after the codes change in place."""
+    from torchmx import dtypes
+    from torchmx.mx_tensor import MXTensor
+    from torchmx_b200 import mx_gemm
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(64, 256, device=DEV, dtype=torch.bfloat16, generator=g)
+    w = torch.randn(512, 256, device=DEV, dtype=torch.bfloat16, generator=g)
+    X, W = MXTensor.to_mx(x, dtypes.float8_e4m3, 32), MXTensor.to_mx(w, dtypes.float6_e3m2, 32)
+    n0 = mx_gemm.stats["transcode"]
+    y = [torch.nn.functional.linear(X, W) for _ in range(4)] + [torch.mm(X, W.t())]
+    assert mx_gemm.stats["transcode"] == n0 + 1
+    assert all(torch.equal(y[0], t) for t in y[1:])
+    W._data.copy_(MXTensor.to_mx(-w, dtypes.float6_e3m2, 32)._data)  # in-place update bumps the version counter
+    y2 = torch.nn.functional.linear(X, W)
+    assert mx_gemm.stats["transcode"] == n0 + 2
+    assert torch.equal(y2, -y[0])
 
 
 @pytest.mark.parametrize("ea,ew", [("float8_e4m3", "float6_e3m2"), ("float8_e4m3", "float4_e2m1"), ("float6_e2m3", "float6_e3m2"),

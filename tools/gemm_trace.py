@@ -6,12 +6,15 @@ from torchmx_b200 import dtypes
 from torchmx_b200.mx_tensor import MXTensor
 for shape in os.environ.get("GT_SHAPES", "8192x8192x8192").split(","):
     M, N, K = (int(v) for v in shape.split("x"))
-    A = MXTensor.to_mx(torch.randn(M, K, device="cuda", dtype=torch.bfloat16), dtypes.float8_e4m3, 32)
-    B = MXTensor.to_mx(torch.randn(N, K, device="cuda", dtype=torch.bfloat16), dtypes.float6_e3m2, 32)
-    torch.nn.functional.linear(A, B)
+    batch = int(os.environ.get("GT_BATCH", "0"))
+    lead = (batch,) if batch else ()
+    A = MXTensor.to_mx(torch.randn(*lead, M, K, device="cuda", dtype=torch.bfloat16), dtypes.float8_e4m3, 32)
+    B = MXTensor.to_mx(torch.randn(*lead, N, K, device="cuda", dtype=torch.bfloat16), dtypes.float6_e3m2, 32)
+    run = (lambda: torch.bmm(A, B.transpose(1, 2))) if batch else (lambda: torch.nn.functional.linear(A, B))
+    run()
     tr = torch.zeros(1024, dtype=torch.int64, device="cuda")  # [0,256): 8 per tile; [256,512): tile 2, 4 per k-block
     os.environ["MXQ_GEMM_TRACE"] = hex(tr.data_ptr())
-    torch.nn.functional.linear(A, B)
+    run()
     torch.cuda.synchronize()
     del os.environ["MXQ_GEMM_TRACE"]
     kbt = tr[256:512].view(64, 4).cpu()
@@ -34,6 +37,6 @@ for shape in os.environ.get("GT_SHAPES", "8192x8192x8192").split(","):
     base = int(st[:npair].min())
     import statistics
     starts = [int(x) - base for x in st[:npair]]; ends = [int(x) - base for x in fin[:npair]]
-    tiles_total = ((M + 255) // 256) * ((N + 255) // 256)
+    tiles_total = ((M + 255) // 256) * ((N + 255) // 256) * max(batch, 1)
     print(f"pairs={npair} tiles={tiles_total}: start spread {max(starts)} ns; finish min {min(ends)} median {statistics.median(ends)} max {max(ends)} ns")
     print("finish by pair:", ends)
