@@ -125,8 +125,28 @@ typedef struct {
     const void *bias;
     void *d; int64_t ldd, d_batch_stride;
     int64_t batch, M, N, K;
+    int a_format, b_format; /* MXQ_OPERAND_*: how a_codes / b_codes are stored (0 = E4M3 container bytes) */
 } mxq_gemm_args_t;
 MXQ_API int mxq_gemm(const mxq_gemm_args_t *args, int device, void *stream);
+
+/* Operand storage formats of mxq_gemm.  The packed formats are what the sm_100a TMA unit expands on the fly
+ * (CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B / 16U6_ALIGN16B) and kind::mxf8f6f4 consumes natively, so a 4-bit operand
+ * costs 0.5 B and a 6-bit operand 0.75 B of HBM traffic per element instead of 1 B:
+ *   MXQ_OPERAND_E4M3_BYTES  : one E4M3 byte per element, row stride lda/ldb bytes (multiple of 16)
+ *   MXQ_OPERAND_E2M1_PACKED : two e2m1 codes per byte, element 2i in the LOW nibble (the reference keeps the even
+ *                             element in the HIGH nibble, torchmx/utils.py:145 -- mxq_pack_operand swaps them)
+ *   MXQ_OPERAND_E3M2_PACKED / MXQ_OPERAND_E2M3_PACKED : 6-bit codes as a little-endian bit stream, element i in bits
+ *                             [6i, 6i+6) of its row
+ * Packed operands need a 32-byte aligned base, row / batch strides that are multiples of 32 bytes and K % 128 == 0. */
+#define MXQ_OPERAND_E4M3_BYTES 0
+#define MXQ_OPERAND_E2M1_PACKED 1
+#define MXQ_OPERAND_E3M2_PACKED 2
+#define MXQ_OPERAND_E2M3_PACKED 3
+
+/* reference-layout element codes (MXQ_ELEM_E3M2 / E2M3: one byte each; MXQ_ELEM_E2M1: packed, even element high) ->
+ * the packed operand format above for that element type; n elements in, n*bits/8 bytes out.  Exact (a permutation of
+ * bits).  n_elements must be a multiple of 16. */
+MXQ_API int mxq_pack_operand(const void *codes, int elem, int64_t n_elements, void *out_packed, int device, void *stream);
 
 /* exact re-encoding of reference-layout element codes as E4M3 bytes (every e3m2 / e2m3 / e2m1
  * value is representable in e4m3): n elements in, n bytes out; MXQ_ELEM_E2M1 input is packed. */

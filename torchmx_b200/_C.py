@@ -14,7 +14,7 @@ HP_BF16, HP_F32 = 0, 1
 FLAG_HW_EXACT = 1
 MAX_DIMS = 6
 
-EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_transcode_to_e4m3",
+EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_transcode_to_e4m3", "mxq_pack_operand",
            "mxq_last_error", "mxq_version", "mxq_arch")
 
 
@@ -27,6 +27,7 @@ class GemmArgs(ctypes.Structure):
         ("bias", ctypes.c_void_p),
         ("d", ctypes.c_void_p), ("ldd", ctypes.c_int64), ("d_batch_stride", ctypes.c_int64),
         ("batch", ctypes.c_int64), ("M", ctypes.c_int64), ("N", ctypes.c_int64), ("K", ctypes.c_int64),
+        ("a_format", ctypes.c_int), ("b_format", ctypes.c_int),
     ]
 
 
@@ -62,6 +63,8 @@ def lib() -> ctypes.CDLL:
         L.mxq_gemm.argtypes = [ctypes.POINTER(GemmArgs), i32, vp]
         L.mxq_transcode_to_e4m3.restype = i32
         L.mxq_transcode_to_e4m3.argtypes = [vp, i32, i64, vp, i32, vp]
+        L.mxq_pack_operand.restype = i32
+        L.mxq_pack_operand.argtypes = [vp, i32, i64, vp, i32, vp]
         if L.mxq_arch() != 1000:
             raise RuntimeError(f"torchmx_b200: libmxq.so was built for arch {L.mxq_arch()}, expected sm_100a")
         _lib = L

@@ -13,6 +13,7 @@ cudaError_t launch_dequantize(const void*, const uint8_t*, int64_t, int, int, in
 cudaError_t launch_dequantize_strided(const void*, const uint8_t*, int, const int64_t*, const int64_t*, const int64_t*, int, int, int, int,
                                       void*, cudaStream_t);
 cudaError_t launch_transcode(const void*, int, int64_t, void*, int, cudaStream_t);
+cudaError_t launch_pack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 int launch_gemm(const mxq_gemm_args_t*, int, cudaStream_t, char*, size_t);
 }  // namespace mxq
 
@@ -143,11 +144,24 @@ int mxq_transcode_to_e4m3(const void* codes, int elem, int64_t n_elements, void*
     return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_transcode_to_e4m3: launch");
 }
 
+int mxq_pack_operand(const void* codes, int elem, int64_t n_elements, void* out, int device, void* stream) {
+    if (elem != MXQ_ELEM_E3M2 && elem != MXQ_ELEM_E2M3 && elem != MXQ_ELEM_E2M1) return fail(MXQ_ERR_INVALID, "mxq_pack_operand: element type %d has no packed operand form", elem);
+    if (n_elements < 0 || n_elements % 16) return fail(MXQ_ERR_INVALID, "mxq_pack_operand: element count must be a non-negative multiple of 16");
+    if (n_elements == 0) return MXQ_OK;
+    if (!codes || !out) return fail(MXQ_ERR_INVALID, "mxq_pack_operand: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_pack_operand: selecting device");
+    const cudaError_t e = mxq::launch_pack_operand(codes, elem, n_elements, out, sm_count_of(scope.cur), (cudaStream_t)stream);
+    return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_pack_operand: launch");
+}
+
 int mxq_gemm(const mxq_gemm_args_t* a, int device, void* stream) {
     if (!a) return fail(MXQ_ERR_INVALID, "mxq_gemm: null args");
     if (a->batch < 0 || a->M < 0 || a->N < 0 || a->K < 0) return fail(MXQ_ERR_INVALID, "mxq_gemm: negative extent");
     if (a->batch == 0 || a->M == 0 || a->N == 0) return MXQ_OK;
     if (!a->a_codes || !a->b_codes || !a->sfa || !a->sfb || !a->d) return fail(MXQ_ERR_INVALID, "mxq_gemm: null pointer");
+    if (a->a_format < 0 || a->a_format > MXQ_OPERAND_E2M3_PACKED || a->b_format < 0 || a->b_format > MXQ_OPERAND_E2M3_PACKED)
+        return fail(MXQ_ERR_INVALID, "mxq_gemm: unknown operand format %d / %d", a->a_format, a->b_format);
     DeviceScope scope(device);
     if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_gemm: selecting device");
     char msg[400] = "";

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
                 tile_coords(tile, b, mb, nb);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], L::A_STAGE + L::B_STAGE);
+                    mbar_arrive_expect_tx(&full[stage], p.tx_a + (BLOCK_N / 128) * p.tx_b);
                     tma_load_3d(&map_a, &full[stage], smem + L::OFF_A + stage * L::A_STAGE, kb * BLOCK_K, mb * BLOCK_M, b);
                     tma_load_3d(&map_b, &full[stage], smem + L::OFF_B + stage * L::B_STAGE, kb * BLOCK_K, nb * BLOCK_N, b);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+        const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N) | p.idesc_fmt;
         uint32_t stage = 0, phase = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             mbar_wait(tmem_empty, acc_phase ^ 1);
@@ -335,7 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 tile_coords(tile, b, mb, nb);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (L::A_STAGE + L::B_STAGE));
+                    if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (p.tx_a + p.tx_b));
                     const uint32_t full_leader = mapa_shared(smem_u32(&full[stage]), 0);
                     tma_load_3d_pair(&map_a, full_leader, smem + L::OFF_A + stage * L::A_STAGE, kb * BLOCK_K, mb * TILE_M + (int)rank * 128, b);
                     tma_load_3d_pair(&map_b, full_leader, smem + L::OFF_B + stage * L::B_STAGE, kb * BLOCK_K, nb * TILE_N + (int)rank * 128, b);
@@ -348,7 +348,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         // uniform registers -- a single-lane loop makes ptxas wrap each tcgen05 instruction in a lane-serialising
         // R2UR loop -- and one elected lane issues) =================
         if (leader) {
-            constexpr uint32_t idesc = make_idesc(TILE_M, TILE_N);
+            const uint32_t idesc = make_idesc(TILE_M, TILE_N) | p.idesc_fmt;
             // descriptor words: the high halves are constants, the low halves are (shared address >> 4) + offsets
             constexpr uint64_t HI_OPERAND = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutSw128 << 61);
             constexpr uint64_t HI_SF = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutNone << 61);
@@ -579,6 +579,9 @@ static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUt
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
     p.trace = nullptr;
     p.dbg = 0;
+    p.idesc_fmt = idesc_formats(a->a_format, a->b_format);
+    p.tx_a = 128 * BLOCK_K * operand_bits(a->a_format) / 8;
+    p.tx_b = 128 * BLOCK_K * operand_bits(a->b_format) / 8;
     p.m_blocks = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
     p.n_blocks = (int)((a->N + BLOCK_N - 1) / BLOCK_N);
     const int64_t tiles = (int64_t)p.m_blocks * p.n_blocks * p.batch;
@@ -603,6 +606,9 @@ static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CU
     p.ld_sfa = a->ld_sfa; p.ld_sfb = a->ld_sfb; p.sfa_batch = a->sfa_batch_stride; p.sfb_batch = a->sfb_batch_stride;
     p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
+    p.idesc_fmt = idesc_formats(a->a_format, a->b_format);
+    p.tx_a = 128 * BLOCK_K * operand_bits(a->a_format) / 8;
+    p.tx_b = 128 * BLOCK_K * operand_bits(a->b_format) / 8;
     p.dbg = getenv("MXQ_GEMM_DBG") ? atoi(getenv("MXQ_GEMM_DBG")) : 0;
     p.trace = getenv("MXQ_GEMM_TRACE") ? reinterpret_cast<long long*>(strtoull(getenv("MXQ_GEMM_TRACE"), nullptr, 0)) : nullptr;
     p.m_blocks = (int)((a->M + pair::TILE_M - 1) / pair::TILE_M);
@@ -634,6 +640,15 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
         snprintf(msg, msg_len, "operand pointers / strides must be 16-byte aligned for TMA");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
+    for (int side = 0; side < 2; ++side) {
+        const int fmt = side ? a->b_format : a->a_format;
+        const int64_t ld = side ? a->ldb : a->lda, bs = side ? a->b_batch_stride : a->a_batch_stride;
+        const uintptr_t base = (uintptr_t)(side ? a->b_codes : a->a_codes);
+        if (fmt != MXQ_OPERAND_E4M3_BYTES && ((ld % 32) || (bs % 32) || (base % 32))) {
+            snprintf(msg, msg_len, "packed operands need 32-byte aligned pointers / strides");
+            return MXQ_ERR_UNSUPPORTED_SHAPE;
+        }
+    }
     if ((a->ld_sfa % 4) || (a->ld_sfb % 4) || ((uintptr_t)a->sfa % 4) || ((uintptr_t)a->sfb % 4) || (a->sfa_batch_stride % 4) || (a->sfb_batch_stride % 4)) {
         snprintf(msg, msg_len, "scale pointers / strides must be 4-byte aligned");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
@@ -649,16 +664,16 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
     CUtensorMap ma, mb;
     const bool use_pair = wide && a->M > 128 && sm_count >= 2 && (cfg == 0 || cfg / 10 == 2);
     if (use_pair) {
-        if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, 128) ||
-            !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, 128)) {
+        if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, 128, a->a_format) ||
+            !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, 128, a->b_format)) {
             snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
             return MXQ_ERR_UNSUPPORTED_SHAPE;
         }
         if (cfg == 24) return launch_pair<4>(a, ma, mb, sm_count, stream, msg, msg_len);
         return launch_pair<5>(a, ma, mb, sm_count, stream, msg, msg_len);
     }
-    if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M) ||
-        !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128)) {
+    if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M, a->a_format) ||
+        !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128, a->b_format)) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }

@@ -28,6 +28,7 @@ struct Params {
     int64_t ld_sfx, ld_sfw, ldd;
     int M, N, K, splits;
     int w_tiled;  // W codes are the tile-major shadow ([N/128][K/128][128][128 B])
+    uint32_t idesc_fmt, tx_w, tx_x;  // element formats of the descriptor; bytes a W / X box posts on the mbarrier
     int pf_dist;  // L2 prefetch distance of the W stream, in K blocks
     int sf_tma;   // scales are 16-byte aligned with a 16-byte multiple row pitch: fetch them with TMA (deep prefetch)
 };
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
             for (int kb = kb0; kb < kb1; ++kb) {
                 if (kb + pf_dist < kb1) tma_prefetch_l2_3d(&map_w, (kb + pf_dist) * BLOCK_K, n0, 0);
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], L::W_STAGE + L::X_STAGE);
+                mbar_arrive_expect_tx(&full[stage], p.tx_w + p.tx_x);
                 if (p.w_tiled)
                     tma_load_4d(&map_w, &full[stage], smem + L::OFF_W + stage * L::W_STAGE, 0, 0, kb, tile);
                 else
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
-        constexpr uint32_t idesc = make_idesc(TILE_W, N_TOK);
+        const uint32_t idesc = make_idesc(TILE_W, N_TOK) | p.idesc_fmt;
         constexpr uint64_t HI_OPERAND = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutSw128 << 61);
         constexpr uint64_t HI_SF = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutNone << 61);
         const uint32_t w_lo0 = smem_u32(smem + L::OFF_W) >> 4, x_lo0 = smem_u32(smem + L::OFF_X) >> 4;
@@ -255,8 +256,8 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
     using L = Smem<N_TOK, STAGES, RAW_W>;
     CUtensorMap mw, mx;
     const int fake_tiled = getenv("MXQ_SKINNY_FAKE_TILED") ? atoi(getenv("MXQ_SKINNY_FAKE_TILED")) : 0;  // timing experiment only (wrong results)
-    const bool w_ok = fake_tiled ? make_tiled_operand_map(&mw, a->b_codes, a->K, a->N / 128 * 128, 1) : make_operand_map(&mw, a->b_codes, a->K, a->N, 1, a->ldb, 0, TILE_W);
-    if (!w_ok || !make_operand_map(&mx, a->a_codes, a->K, a->M, 1, a->lda, 0, N_TOK)) {
+    const bool w_ok = fake_tiled ? make_tiled_operand_map(&mw, a->b_codes, a->K, a->N / 128 * 128, 1) : make_operand_map(&mw, a->b_codes, a->K, a->N, 1, a->ldb, 0, TILE_W, a->b_format);
+    if (!w_ok || !make_operand_map(&mx, a->a_codes, a->K, a->M, 1, a->lda, 0, N_TOK, a->a_format)) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
@@ -274,6 +275,10 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
     p.ld_sfx = a->ld_sfa; p.ld_sfw = a->ld_sfb; p.ldd = a->ldd;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.splits = splits;
     p.w_tiled = fake_tiled;
+    // the weights are the MMA A operand here, the tokens the B operand
+    p.idesc_fmt = idesc_formats(a->b_format, a->a_format);
+    p.tx_w = TILE_W * BLOCK_K * operand_bits(a->b_format) / 8;
+    p.tx_x = N_TOK * BLOCK_K * operand_bits(a->a_format) / 8;
     p.sf_tma = sf_tma;
     p.pf_dist = getenv("MXQ_SKINNY_PF") ? atoi(getenv("MXQ_SKINNY_PF")) : 0;  // measured: no gain on B200 (0 = off)
     const int n_tiles = (int)((a->N + TILE_W - 1) / TILE_W);

@@ -209,6 +209,15 @@ constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2;
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24);
 }
+// operand storage format (MXQ_OPERAND_*) -> element format field of the descriptor (a_format bits [7,10), b_format bits
+// [10,13)): E4M3 = 0, E2M3 = 3, E3M2 = 4, E2M1 = 5; and -> bits per element as TMA counts them in complete_tx
+__host__ __device__ constexpr uint32_t umma_format(int operand_format) {
+    return operand_format == MXQ_OPERAND_E2M1_PACKED ? 5u : (operand_format == MXQ_OPERAND_E3M2_PACKED ? 4u : (operand_format == MXQ_OPERAND_E2M3_PACKED ? 3u : 0u));
+}
+__host__ __device__ constexpr int operand_bits(int operand_format) {
+    return operand_format == MXQ_OPERAND_E2M1_PACKED ? 4 : (operand_format == MXQ_OPERAND_E4M3_BYTES ? 8 : 6);
+}
+__host__ __device__ constexpr uint32_t idesc_formats(int a_format, int b_format) { return (umma_format(a_format) << 7) | (umma_format(b_format) << 10); }
 __device__ __forceinline__ uint32_t idesc_with_sf(uint32_t idesc, uint32_t sfa_id, uint32_t sfb_id) {
     return idesc | (sfb_id << 4) | (sfa_id << 29);
 }
@@ -217,6 +226,8 @@ struct Params {
     const uint8_t* sfa; const uint8_t* sfb; const uint16_t* bias; uint16_t* d;
     int64_t ld_sfa, ld_sfb, sfa_batch, sfb_batch, ldd, d_batch;
     int M, N, K, batch, m_blocks, n_blocks;
+    uint32_t idesc_fmt;  // element-format bits of the instruction descriptor (idesc_formats)
+    uint32_t tx_a, tx_b; // bytes one 128-row x 128-element box of A / B posts on the mbarrier (packed formats count packed bytes)
     int dbg;           // developer hook (MXQ_GEMM_DBG): bit0 = epilogue skips the global stores
     long long* trace;  // developer hook (MXQ_GEMM_TRACE=<device pointer>): clock64 stamps of pair 0's leader, 8 slots per tile
 };
@@ -406,16 +417,20 @@ static inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// [batch][rows][K bytes] uint8, K contiguous, box = 128 bytes x box_rows, 128B swizzle, OOB rows read as zero
+// [batch][rows][K elements], K contiguous, box = 128 elements x box_rows, 128B swizzle, OOB rows read as zero.  The shared
+// memory image is always 128 bytes per row and K block: one byte per element for E4M3 bytes, and for the packed 4 / 6-bit
+// formats the TMA unit expands every 16 elements (8 / 12 bytes) to a 16-byte slot -- the layout kind::mxf8f6f4 reads.
 static inline bool make_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows, int64_t batch, int64_t ld, int64_t batch_stride,
-                             int box_rows) {
+                             int box_rows, int operand_format = MXQ_OPERAND_E4M3_BYTES) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
+    const CUtensorMapDataType dt = operand_format == MXQ_OPERAND_E4M3_BYTES ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                   : (operand_format == MXQ_OPERAND_E2M1_PACKED ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_16U6_ALIGN16B);
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)(batch > 1 ? batch_stride : ld * rows)};
     cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

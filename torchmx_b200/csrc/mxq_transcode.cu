@@ -80,4 +80,51 @@ cudaError_t launch_transcode(const void* codes, int elem, int64_t n_elements, vo
     return cudaGetLastError();
 }
 
+// ---- hardware-packed operand formats (include/mxq.h: MXQ_OPERAND_*_PACKED) -------------------------------------
+// fp4: swap the nibbles of every byte (reference: even element high; TMA / UMMA: element 2i low).  16 bytes per thread.
+__global__ void __launch_bounds__(256) pack_fp4_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int64_t n_bytes) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_vec = n_bytes / 16;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const uint4 v = ldg128_stream(in + i * 16);
+        auto sw = [](uint32_t w) { return ((w & 0x0F0F0F0Fu) << 4) | ((w >> 4) & 0x0F0F0F0Fu); };
+        stg128_stream(out + i * 16, make_uint4(sw(v.x), sw(v.y), sw(v.z), sw(v.w)));
+    }
+    for (int64_t b = n_vec * 16 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bytes; b += stride) {
+        const uint32_t c = in[b];
+        out[b] = (uint8_t)((c << 4) | (c >> 4));
+    }
+}
+
+// fp6: 16 one-byte codes (bits [5:0]) -> 12 bytes, element i in bits [6i, 6i+6) of the group
+__global__ void __launch_bounds__(256) pack_fp6_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int64_t n_groups) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += stride) {
+        const uint4 v = ldg128_stream(in + i * 16);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t t[4];  // 24 packed bits per input word (4 codes)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = (w[j] & 0x3F) | ((w[j] >> 2) & 0xFC0) | ((w[j] >> 4) & 0x3F000) | ((w[j] >> 6) & 0xFC0000);
+        uint32_t* o = reinterpret_cast<uint32_t*>(out + i * 12);  // 12-byte groups: 4-byte aligned
+        o[0] = t[0] | (t[1] << 24);
+        o[1] = (t[1] >> 8) | (t[2] << 16);
+        o[2] = (t[2] >> 16) | (t[3] << 8);
+    }
+}
+
+cudaError_t launch_pack_operand(const void* codes, int elem, int64_t n_elements, void* out, int sm_count, cudaStream_t stream) {
+    if (((uintptr_t)codes % 16) || ((uintptr_t)out % 16)) return cudaErrorMisalignedAddress;
+    const int64_t cap = (int64_t)sm_count * 32;
+    if (elem == MXQ_ELEM_E2M1) {
+        const int64_t n_bytes = n_elements / 2;
+        const int64_t want = (n_bytes / 16 + 255) / 256 + 1;
+        pack_fp4_kernel<<<(int)(want < cap ? want : cap), 256, 0, stream>>>((const uint8_t*)codes, (uint8_t*)out, n_bytes);
+    } else {
+        const int64_t n_groups = n_elements / 16;
+        const int64_t want = (n_groups + 255) / 256 + 1;
+        pack_fp6_kernel<<<(int)(want < cap ? want : cap), 256, 0, stream>>>((const uint8_t*)codes, (uint8_t*)out, n_groups);
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace mxq

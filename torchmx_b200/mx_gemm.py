@@ -32,30 +32,54 @@ def set_enabled(flag: bool) -> None:
     _DISABLED = not flag
 
 
-def _e4m3_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[MXTensor]) -> Optional[torch.Tensor]:
-    """codes: [..., rows, Kb] with unit stride along Kb -> uint8 [..., rows, K] E4M3-container bytes.
-    float8_e4m3 passes through untouched (a view); fp6 / fp4 are transcoded exactly by the CUDA
-    transcoder.  When `cache_on` is given (the long-lived MXTensor the operand is a view of, i.e. a layer's
-    weight) the result is cached on that Python object, keyed by the view geometry and the version counter
-    of the codes, so a weight is transcoded once, not once per forward."""
+# operand storage formats of mxq_gemm (include/mxq.h: MXQ_OPERAND_*)
+FMT_E4M3_BYTES, FMT_E2M1_PACKED, FMT_E3M2_PACKED, FMT_E2M3_PACKED = 0, 1, 2, 3
+_PACKED_FORMAT = {"float4_e2m1": FMT_E2M1_PACKED, "float6_e3m2": FMT_E3M2_PACKED, "float6_e2m3": FMT_E2M3_PACKED}
+_PACKED_BITS = {FMT_E2M1_PACKED: 4, FMT_E3M2_PACKED: 6, FMT_E2M3_PACKED: 6}
+# MXQ_PACKED_OPERANDS=0 keeps every fp6 / fp4 operand in the one-byte E4M3 container (the first implementation)
+_USE_PACKED = os.environ.get("MXQ_PACKED_OPERANDS", "1") != "0"
+
+
+def set_packed_operands(flag: bool) -> None:
+    global _USE_PACKED
+    _USE_PACKED = bool(flag)
+
+
+def _operand_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[MXTensor]):
+    """codes: [..., rows, Kb] reference-layout element codes with unit stride along Kb -> (uint8 operand tensor, format).
+
+    float8_e4m3 passes through untouched (a view).  fp4 / fp6 codes become the packed 4 / 6-bit streams the sm_100a TMA
+    unit expands and kind::mxf8f6f4 consumes natively (`mxq_pack_operand`: a nibble swap / a 6-bit pack, exact), so they
+    cost 0.5 / 0.75 B of HBM traffic per element; with MXQ_PACKED_OPERANDS=0 they are re-encoded exactly as E4M3 bytes
+    instead (`mxq_transcode_to_e4m3`).  When `cache_on` is given (the long-lived MXTensor the operand is a view of, i.e. a
+    layer's weight) the result is cached on that Python object, keyed by the view geometry, the format and the version
+    counter of the codes, so a weight is converted once, not once per forward."""
     if elem == dtypes.float8_e4m3:
-        return codes
+        return codes, FMT_E4M3_BYTES
+    fmt = _PACKED_FORMAT[elem.name] if _USE_PACKED else FMT_E4M3_BYTES
     key = None
     if cache_on is not None:
-        key = (codes.data_ptr(), tuple(codes.shape), tuple(codes.stride()), cache_on._data._version)
+        key = (codes.data_ptr(), tuple(codes.shape), tuple(codes.stride()), cache_on._data._version, fmt)
         hit = cache_on.__dict__.get(_SHADOW_ATTR)
         if hit is not None and hit[0] == key:
-            return hit[1]
+            return hit[1], fmt
     stats["transcode"] += 1
     src = codes.contiguous()
     per = 2 if elem == dtypes.float4_e2m1 else 1
-    out = torch.empty(tuple(src.shape[:-1]) + (src.shape[-1] * per,), dtype=torch.uint8, device=src.device)
-    rc = _C.lib().mxq_transcode_to_e4m3(src.data_ptr(), dtypes.ELEM_ID[elem.name], out.numel(), out.data_ptr(), src.device.index,
-                                        _stream_ptr(src))
-    _C.check(rc, "mxq_transcode_to_e4m3")
+    n_elements = src.numel() * per
+    if fmt == FMT_E4M3_BYTES:
+        out = torch.empty(tuple(src.shape[:-1]) + (src.shape[-1] * per,), dtype=torch.uint8, device=src.device)
+        rc = _C.lib().mxq_transcode_to_e4m3(src.data_ptr(), dtypes.ELEM_ID[elem.name], n_elements, out.data_ptr(), src.device.index,
+                                            _stream_ptr(src))
+        _C.check(rc, "mxq_transcode_to_e4m3")
+    else:
+        k = src.shape[-1] * per
+        out = torch.empty(tuple(src.shape[:-1]) + (k * _PACKED_BITS[fmt] // 8,), dtype=torch.uint8, device=src.device)
+        rc = _C.lib().mxq_pack_operand(src.data_ptr(), dtypes.ELEM_ID[elem.name], n_elements, out.data_ptr(), src.device.index, _stream_ptr(src))
+        _C.check(rc, "mxq_pack_operand")
     if cache_on is not None:
         cache_on.__dict__[_SHADOW_ATTR] = (key, out)
-    return out
+    return out, fmt
 
 
 def _rows_k(t: MXTensor, k_dim_from_end: int):
@@ -73,8 +97,9 @@ def _qualifies(t: MXTensor) -> bool:
             and t._data.is_cuda and t._orig_dtype == torch.bfloat16)
 
 
-def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs, sfb_bs, out) -> bool:
+def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs, sfb_bs, out, a_fmt=FMT_E4M3_BYTES, b_fmt=FMT_E4M3_BYTES) -> bool:
     g = _C.GemmArgs()
+    g.a_format, g.b_format = a_fmt, b_fmt
     g.a_codes, g.sfa, g.lda, g.ld_sfa = a_codes.data_ptr(), sfa.data_ptr(), a_codes.stride(-2), sfa.stride(-2)
     g.a_batch_stride, g.sfa_batch_stride = a_bs, sfa_bs
     g.b_codes, g.sfb, g.ldb, g.ld_sfb = b_codes.data_ptr(), sfb.data_ptr(), b_codes.stride(-2), sfb.stride(-2)
@@ -143,10 +168,10 @@ def _dispatch(aten_op, a, b, extra_front, extra_back):
         batch, M = 1, a_codes.shape[0]
         lead_shape = tuple(a.shape[:-1])
 
-    # E4M3-container operands (exact transcode of fp6 / fp4 codes; weights cache theirs on the storage tensor)
+    # tensor-core operand forms (packed 4 / 6-bit streams or E4M3 bytes; a weight caches its shadow on the origin MXTensor)
     b_origin = getattr(b, "_mxq_origin", b)
-    a_e = _e4m3_rows(a_codes, a._elem_dtype, None)
-    b_e = _e4m3_rows(b_codes, b._elem_dtype, b_origin if not batched else None)
+    a_e, a_fmt = _operand_rows(a_codes, a._elem_dtype, None)
+    b_e, b_fmt = _operand_rows(b_codes, b._elem_dtype, b_origin if not batched else None)
     if a_e.stride(-1) != 1 or b_e.stride(-1) != 1:
         return None
     out = torch.empty(lead_shape + (N,), dtype=torch.bfloat16, device=a._data.device)
@@ -158,5 +183,5 @@ def _dispatch(aten_op, a, b, extra_front, extra_back):
             return None  # expanded (stride 0) batch: not expressible as a TMA stride
     else:
         strides = (0, 0, 0, 0)
-    ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out)
+    ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out, a_fmt, b_fmt)
     return out if ok else None

@@ -31,7 +31,7 @@ def _rewrap(old: MXTensor, scale, data, *, block_dim=None, orig_dtype=None) -> M
     new = MXTensor(scale, data, old._elem_dtype, old._block_size, orig_dtype or old._orig_dtype, old._padding,
                    old._block_dim if block_dim is None else block_dim)
     # Layout ops produce short-lived views (F.linear decomposes into aten.t + aten.mm).  Remember the long-lived tensor
-    # they came from: the tensor-core operand shadow of a weight is cached on THAT Python object (mx_gemm._e4m3_rows).
+    # they came from: the tensor-core operand shadow of a weight is cached on THAT Python object (mx_gemm._operand_rows).
     new._mxq_origin = getattr(old, "_mxq_origin", old)
     return new
 
