@@ -228,3 +228,47 @@ def test_mx_inference_linear_and_quantize_linear(mx):
     # state_dict round trip keeps the MXTensor storage (reference: mx_tensor.py:526-528)
     sd = model.state_dict()
     assert isinstance(sd["0.weight"], MXTensor)
+
+
+def test_pack_operand_is_an_exact_bit_permutation(mx):
+    """mxq_pack_operand: fp4 = nibble swap of every byte (reference keeps the even element in the high nibble, the TMA /
+    tensor-core order is low nibble first), fp6 = 16 one-byte codes -> 12 bytes, element i in bits [6i, 6i+6)."""
+    from torchmx import dtypes
+    from torchmx_b200 import _C
+    from torchmx_b200.mx_tensor import _stream_ptr
+    g = torch.Generator(device=DEV).manual_seed(21)
+    n = 128 * 96
+    c6 = torch.randint(0, 64, (n,), device=DEV, dtype=torch.uint8, generator=g)
+    out6 = torch.empty(n * 6 // 8, device=DEV, dtype=torch.uint8)
+    _C.check(_C.lib().mxq_pack_operand(c6.data_ptr(), dtypes.ELEM_ID["float6_e3m2"], n, out6.data_ptr(), 0, _stream_ptr(c6)), "pack6")
+    bits = ((c6.cpu().numpy()[:, None] >> np.arange(6)) & 1).astype(np.uint8).reshape(-1)      # LSB-first bit stream
+    want6 = np.packbits(bits, bitorder="little")
+    assert np.array_equal(out6.cpu().numpy(), want6)
+    c4 = torch.randint(0, 256, (n // 2,), device=DEV, dtype=torch.uint8, generator=g)
+    out4 = torch.empty_like(c4)
+    _C.check(_C.lib().mxq_pack_operand(c4.data_ptr(), dtypes.ELEM_ID["float4_e2m1"], n, out4.data_ptr(), 0, _stream_ptr(c4)), "pack4")
+    h = c4.cpu().numpy()
+    assert np.array_equal(out4.cpu().numpy(), ((h << 4) | (h >> 4)).astype(np.uint8))
+
+
+@pytest.mark.parametrize("wdt", ["float4_e2m1", "float6_e3m2", "float6_e2m3"])
+def test_packed_and_container_operands_agree_bit_for_bit(mx, wdt):
+    """The packed 4 / 6-bit operand path and the E4M3-container path feed the tensor core the same values: identical outputs
+    (same kernel, same accumulation order) for the pair, single-CTA and skinny kernels."""
+    from torchmx import dtypes
+    from torchmx.mx_tensor import MXTensor
+    from torchmx_b200 import mx_gemm
+    g = torch.Generator(device=DEV).manual_seed(8)
+    for (M, N, K, batch) in [(300, 520, 640, 0), (48, 1000, 1024, 0), (96, 200, 256, 3)]:
+        sa, sb = ((batch, M, K), (batch, N, K)) if batch else ((M, K), (N, K))
+        X = MXTensor.to_mx(torch.randn(*sa, device=DEV, dtype=torch.bfloat16, generator=g), dtypes.float8_e4m3, 32)
+        outs = []
+        for packed in (True, False):
+            mx_gemm.set_packed_operands(packed)
+            try:
+                W = MXTensor.to_mx(torch.randn(*sb, device=DEV, dtype=torch.bfloat16, generator=torch.Generator(device=DEV).manual_seed(9)),
+                                   dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[wdt], 32)
+                outs.append(torch.bmm(X, W.transpose(1, 2)) if batch else torch.nn.functional.linear(X, W))
+            finally:
+                mx_gemm.set_packed_operands(True)
+        assert torch.equal(outs[0], outs[1]), (M, N, K, batch)

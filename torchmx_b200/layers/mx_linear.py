@@ -6,11 +6,40 @@ kernel, or the dequantize path when the operands do not qualify).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
 from ..config import QLinearConfig
 from ..mx_tensor import MXTensor
+
+
+# q/k/v (and gate/up) projections of a decoder layer quantize the SAME activation tensor with the same config; the
+# reference quantizes it once per layer (mx_linear.py:63-66), i.e. three (two) times.  One entry is remembered: if the next
+# layer is handed the very same tensor (object identity, storage pointer, geometry and version counter all equal) the MX
+# tensor is reused -- bit-identical by construction, one K1 launch instead of three.  The entry keeps `x` alive, so its
+# storage cannot be recycled under the key; MXQ_ACT_REUSE=0 turns it off.
+_ACT_REUSE = os.environ.get("MXQ_ACT_REUSE", "1") != "0"
+_last_act = None
+
+
+def _quantize_activation(x: torch.Tensor, elem_dtype, block_size: int) -> MXTensor:
+    global _last_act
+    if not _ACT_REUSE or type(x) is not torch.Tensor:
+        return MXTensor.to_mx(x, elem_dtype, block_size)
+    key = (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()), x.dtype, elem_dtype.name, block_size)
+    hit = _last_act
+    if hit is not None and hit[0] is x and hit[1] == key:
+        return hit[2]
+    x_mx = MXTensor.to_mx(x, elem_dtype, block_size)
+    _last_act = (x, key, x_mx)
+    return x_mx
+
+
+def clear_activation_cache() -> None:
+    global _last_act
+    _last_act = None
 
 
 class MXInferenceLinear(torch.nn.Linear):
@@ -54,7 +83,7 @@ class MXInferenceLinear(torch.nn.Linear):
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         ac = self.qconfig.activations_config
-        x_mx = MXTensor.to_mx(x, ac.elem_dtype, ac.block_size)
+        x_mx = _quantize_activation(x, ac.elem_dtype, ac.block_size)
         bias = self.bias
         if not isinstance(self.weight.data, MXTensor) and bias is not None:
             bias = bias.to(torch.bfloat16)
