@@ -126,6 +126,13 @@ typedef struct {
     void *d; int64_t ldd, d_batch_stride;
     int64_t batch, M, N, K;
     int a_format, b_format; /* MXQ_OPERAND_*: how a_codes / b_codes are stored (0 = E4M3 container bytes) */
+    /* Fused row-parallel all-reduce (tensor parallelism over NVLink / NVSwitch): when non-NULL, `d_multicast` is the
+     * MULTICAST address of a symmetric [M, N] bf16 buffer mapped on every rank of the group (ldd / d_batch_stride describe
+     * it; `d` is ignored).  The epilogue does not store: it adds this rank's bf16 partial tile into the buffer of EVERY
+     * rank with multimem.red (the reduction happens in the switch), so after all ranks' launches have completed and a
+     * cross-rank barrier has passed, each rank's copy holds the sum.  The buffer must be zero on every rank before the
+     * first launch that targets it; needs N % 8 == 0, a 16-byte aligned buffer and batch == 1. */
+    void *d_multicast;
 } mxq_gemm_args_t;
 MXQ_API int mxq_gemm(const mxq_gemm_args_t *args, int device, void *stream);
 

@@ -146,11 +146,23 @@ def run_infer(args, world, rank):
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
     h = cfg["hidden"]
+    pool = None
+    if args.fused and world > 1:
+        from torchmx_b200.layers.tp_linear import FusedAllReducePool
+        pool = FusedAllReducePool(h, max(args.prefill, args.batch), None)
+        for l in layers:
+            l.o.enable_fused_allreduce(pool)
+            l.down.enable_fused_allreduce(pool)
+    for l in layers:
+        if pool is None:
+            l.o._fused_pool = l.down._fused_pool = None
     gen = torch.Generator(device="cuda").manual_seed(5)
-    res = {"mode": "infer", "model": args.model, "layers": cfg["layers"], "world": world, "weights": args.wdtype, "activations": args.adtype,
+    res = {"mode": "infer", "fused_allreduce": bool(args.fused and world > 1), "model": args.model, "layers": cfg["layers"], "world": world, "weights": args.wdtype, "activations": args.adtype,
            "build_s": round(build_s, 2), "weight_GB_per_rank": round(torch.cuda.memory_allocated() / 1e9, 2)}
 
     def stack(x, pos, caches, cache_len):
+        if pool is not None and layers[0].o._fused_pool is not None:
+            pool.reset()
         for l, (kc, vc) in zip(layers, caches):
             x = l(x, pos, kc, vc, cache_len)
         return x
@@ -181,6 +193,8 @@ def run_infer(args, world, rank):
     elems = cfg["layers"] * (2 * h * h + 2 * (h // cfg["heads"]) * cfg["kv_heads"] * h + 3 * h * cfg["inter"])
     bpe = (0.5 if args.wdtype == "float4_e2m1" else 1.0) + 1 / 32
     res["decode_weight_stream_floor_ms_per_rank"] = round(elems * bpe / world / 6.5e12 * 1e3, 3)
+    from torchmx_b200 import mx_gemm
+    res["gemm_stats"] = dict(mx_gemm.stats)
     if args.check:
         # every rank evaluated the same seeds; compare rank 0's TP result with a one-rank evaluation of the same stack
         ref_layers = [TPDecoderLayer(cfg, qc, 1, 0, seed=1000 + i) for i in range(cfg["layers"])]
@@ -190,7 +204,26 @@ def run_infer(args, world, rank):
         for l, (kc, vc) in zip(ref_layers, c1):
             xr = l(xr, pos, kc, vc, 0)
         c2 = make_caches(1, P)
-        xt = stack(x, pos, c2, 0)
+        xt = stack(x, pos, c2, 0).clone()
+        if pool is not None:
+            # the same TP stack with the NCCL all-reduce instead of the fused epilogue: only the summation differs (switch
+            # vs ring order), everything else is bit-identical
+            for l in layers:
+                l.o._fused_pool = l.down._fused_pool = None
+            xn = stack(x, pos, make_caches(1, P), 0)
+            res["check_rel_err_fused_vs_nccl"] = float((xt.float() - xn.float()).norm() / xn.float().norm())
+            # single row-parallel layer, decode and prefill sized: fused vs NCCL on identical inputs
+            for rows in (args.batch, P):
+                a = torch.randn(rows, layers[0].o.in_features, device="cuda", dtype=torch.bfloat16, generator=gen)
+                y_n = layers[0].o(a).clone()
+                layers[0].o._fused_pool = pool
+                pool.reset()
+                y_f = layers[0].o(a).clone()
+                layers[0].o._fused_pool = None
+                res[f"check_layer_rows{rows}_max_abs_diff"] = float((y_f.float() - y_n.float()).abs().max())
+                res[f"check_layer_rows{rows}_ref_absmax"] = float(y_n.float().abs().max())
+                assert (y_f.float() - y_n.float()).abs().max() <= 2.0 ** -6 * y_n.float().abs().max() + 1e-3
+            assert res["check_rel_err_fused_vs_nccl"] < 6e-2
         err = (xt.float() - xr.float()).norm() / xr.float().norm()
         res["check_rel_err_vs_1rank"] = float(err)
         # activations are re-quantized (fp8) between layers, so a last-bit difference of a bf16 partial sum can flip a code:
@@ -261,6 +294,7 @@ def main():
     ap.add_argument("--wdtype", default="float4_e2m1")
     ap.add_argument("--adtype", default="float8_e4m3")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="row-parallel layers reduce in the GEMM epilogue (NVLink multicast) instead of NCCL")
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)

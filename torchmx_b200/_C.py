@@ -28,6 +28,7 @@ class GemmArgs(ctypes.Structure):
         ("d", ctypes.c_void_p), ("ldd", ctypes.c_int64), ("d_batch_stride", ctypes.c_int64),
         ("batch", ctypes.c_int64), ("M", ctypes.c_int64), ("N", ctypes.c_int64), ("K", ctypes.c_int64),
         ("a_format", ctypes.c_int), ("b_format", ctypes.c_int),
+        ("d_multicast", ctypes.c_void_p),
     ]
 
 

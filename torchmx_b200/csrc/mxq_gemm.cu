@@ -461,7 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                     }
                     const int col0 = nb * TILE_N + g * 64;
                     uint8_t* buf = ebuf + (h & 1) * 4096;
-                    if (lane == 0) tma_store_wait_read<1>();  // the store that last read this buffer (two groups ago) is done with it
+                    if (p.d_mc == nullptr && lane == 0) tma_store_wait_read<1>();  // the store that last read this buffer (two groups ago) is done
                     __syncwarp();
                     uint32_t pk[32];
 #pragma unroll
@@ -482,6 +482,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         *reinterpret_cast<uint4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    if (p.d_mc != nullptr) {
+                        // Fused tensor-parallel all-reduce: this rank's partial tile is ADDED into the output buffer of every
+                        // rank through the NVLink multicast address (the sum is formed in the switch).  Read the staging rows
+                        // back with eight lanes per row so each instruction carries four complete 128-byte row segments.
+                        __syncwarp();
+                        const int row_base = mb * TILE_M + (int)rank * 128 + quad * 32;
+                        const int c = lane & 7;
+                        if (col0 + 8 * c < p.N) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int rr = 4 * j + (lane >> 3);
+                                const uint4 val = *reinterpret_cast<const uint4*>(buf + rr * 128 + ((c ^ (rr & 7)) << 4));
+                                if (row_base + rr < p.M) multimem_red_add_bf16x8(p.d_mc + (int64_t)(row_base + rr) * p.ldd + col0 + 8 * c, val);
+                            }
+                        }
+                        continue;
+                    }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -574,6 +591,7 @@ static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUt
     }
     Params p;
     p.sfa = a->sfa; p.sfb = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
+    p.d_mc = nullptr;
     p.ld_sfa = a->ld_sfa; p.ld_sfb = a->ld_sfb; p.sfa_batch = a->sfa_batch_stride; p.sfb_batch = a->sfb_batch_stride;
     p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
@@ -603,6 +621,7 @@ static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CU
     }
     Params p;
     p.sfa = a->sfa; p.sfb = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
+    p.d_mc = (uint16_t*)a->d_multicast;
     p.ld_sfa = a->ld_sfa; p.ld_sfb = a->ld_sfb; p.sfa_batch = a->sfa_batch_stride; p.sfb_batch = a->sfb_batch_stride;
     p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
@@ -621,7 +640,14 @@ static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CU
     // coalesced TMA-store epilogue needs a 16-byte aligned D with a 16-byte multiple row pitch; otherwise direct stores
     CUtensorMap md;
     int tma_store = ((uintptr_t)a->d % 16 == 0) && (a->ldd % 8 == 0) && (a->d_batch_stride % 8 == 0) && !(p.dbg & 2);
-    if (tma_store && !make_d_map(&md, a->d, a->N, a->M, a->batch, a->ldd, a->d_batch_stride)) tma_store = 0;
+    if (a->d_multicast != nullptr) {  // fused all-reduce epilogue: staging path without the tensor map
+        if (((uintptr_t)a->d_multicast % 16) || (a->ldd % 8) || (a->N % 8) || a->batch != 1) {
+            snprintf(msg, msg_len, "d_multicast needs a 16-byte aligned buffer, N %% 8 == 0, ldd %% 8 == 0 and batch == 1");
+            return MXQ_ERR_UNSUPPORTED_SHAPE;
+        }
+        tma_store = 1;
+        md = ma;
+    } else if (tma_store && !make_d_map(&md, a->d, a->N, a->M, a->batch, a->ldd, a->d_batch_stride)) tma_store = 0;
     if (!tma_store) md = ma;  // unused placeholder
     pair::mx_gemm_pair_kernel<STAGES><<<2 * pairs, pair::kThreads, L::DYN_BYTES, stream>>>(ma, mb, md, p, group_m, tma_store);
     const cudaError_t e = cudaGetLastError();
@@ -658,11 +684,15 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
         const int rc = launch_gemm_skinny(a, sm_count, stream, msg, msg_len);
         if (rc != MXQ_ERR_UNSUPPORTED_SHAPE) return rc;
     }
+    if (a->d_multicast != nullptr && !(a->M > 128 && a->N > 128)) {
+        snprintf(msg, msg_len, "d_multicast (fused all-reduce) is implemented by the CTA-pair and skinny kernels only");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
     const int force_narrow = getenv("MXQ_GEMM_NARROW") ? atoi(getenv("MXQ_GEMM_NARROW")) : 0;  // developer knobs, re-read per call
     const int cfg = getenv("MXQ_GEMM_CFG") ? atoi(getenv("MXQ_GEMM_CFG")) : 0;  // developer knob: <BLOCK_N><STAGES>, 2<STAGES> = CTA pair
     const bool wide = a->N > 128 && !force_narrow;
     CUtensorMap ma, mb;
-    const bool use_pair = wide && a->M > 128 && sm_count >= 2 && (cfg == 0 || cfg / 10 == 2);
+    const bool use_pair = wide && a->M > 128 && sm_count >= 2 && (cfg == 0 || cfg / 10 == 2 || a->d_multicast != nullptr);
     if (use_pair) {
         if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, 128, a->a_format) ||
             !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, 128, a->b_format)) {

@@ -25,6 +25,7 @@ constexpr int SF_KB_BYTES = 512;  // one K block of scale factors for (up to) 12
 
 struct Params {
     const uint8_t* sfx; const uint8_t* sfw; const uint16_t* bias; uint16_t* d;
+    uint16_t* d_mc;  // multicast alias of the output on every rank: add (multimem.red) instead of store
     int64_t ld_sfx, ld_sfw, ldd;
     int M, N, K, splits;
     int w_tiled;  // W codes are the tile-major shadow ([N/128][K/128][128][128 B])
@@ -209,7 +210,16 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 32, v);
             tmem_ld_wait();
             if (S == 1) {
-                if (n < p.N) {
+                if (p.d_mc != nullptr) {
+                    // fused tensor-parallel all-reduce: adjacent lanes (weight rows n, n+1) pair up into one bf16x2 add
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int t = c * 32 + i;
+                        const float mine = __uint_as_float(v[i]) + bias;
+                        const float next = __shfl_down_sync(0xFFFFFFFFu, mine, 1);
+                        if (!(lane & 1) && t < p.M && n < p.N) multimem_red_add_bf16x2(p.d_mc + (int64_t)t * p.ldd + n, pack_bf16x2(mine, next));
+                    }
+                } else if (n < p.N) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int t = c * 32 + i;
@@ -236,7 +246,13 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
             for (int t = split; t < p.M; t += S) {  // this CTA finishes tokens split, split + S, ...
                 float acc = 0.0f;
                 for (int s = 0; s < S; ++s) acc += ld_dsmem_f32(mapa_shared(part_addr + (uint32_t)(t * TILE_W + r) * 4u, (uint32_t)s));
-                if (n < p.N) p.d[(int64_t)t * p.ldd + n] = (uint16_t)pack_bf16x2(acc + bias, 0.0f);
+                if (p.d_mc != nullptr) {
+                    const float mine = acc + bias;
+                    const float next = __shfl_down_sync(0xFFFFFFFFu, mine, 1);
+                    if (!(lane & 1) && n < p.N) multimem_red_add_bf16x2(p.d_mc + (int64_t)t * p.ldd + n, pack_bf16x2(mine, next));
+                } else if (n < p.N) {
+                    p.d[(int64_t)t * p.ldd + n] = (uint16_t)pack_bf16x2(acc + bias, 0.0f);
+                }
             }
         }
         __syncwarp();
@@ -272,6 +288,7 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
     if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     Params p;
     p.sfx = a->sfa; p.sfw = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
+    p.d_mc = (uint16_t*)a->d_multicast;
     p.ld_sfx = a->ld_sfa; p.ld_sfw = a->ld_sfb; p.ldd = a->ldd;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.splits = splits;
     p.w_tiled = fake_tiled;
@@ -305,6 +322,10 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
 int launch_gemm_skinny(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, char* msg, size_t msg_len) {
     using namespace skinny;
     if (a->batch != 1 || a->M > 128 || a->K % BLOCK_K) return MXQ_ERR_UNSUPPORTED_SHAPE;
+    if (a->d_multicast != nullptr && (((uintptr_t)a->d_multicast % 4) || (a->ldd % 2) || (a->N % 2))) {
+        snprintf(msg, msg_len, "d_multicast needs an even N / ldd and a 4-byte aligned buffer");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
     const int k_blocks = (int)(a->K / BLOCK_K);
     const int n_tiles = (int)((a->N + TILE_W - 1) / TILE_W);
     // split K across a cluster until about one CTA per SM is streaming; keep >= 4 K blocks per CTA and 4-K-block aligned

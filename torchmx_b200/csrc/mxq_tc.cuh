@@ -131,6 +131,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- NVLink multicast (NVLS): add into the same address of every GPU mapped behind a multicast pointer ------------
+__device__ __forceinline__ void multimem_red_add_bf16x8(void* mc_addr, uint4 v) {
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void multimem_red_add_bf16x2(void* mc_addr, uint32_t v) {
+    asm volatile("multimem.red.relaxed.sys.global.add.bf16x2 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+
 // ---- cluster / cta_group::2 flavours ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -224,6 +233,7 @@ __device__ __forceinline__ uint32_t idesc_with_sf(uint32_t idesc, uint32_t sfa_i
 
 struct Params {
     const uint8_t* sfa; const uint8_t* sfb; const uint16_t* bias; uint16_t* d;
+    uint16_t* d_mc;  // multicast alias of the output on every rank: the epilogue adds (multimem.red) instead of storing
     int64_t ld_sfa, ld_sfb, sfa_batch, sfb_batch, ldd, d_batch;
     int M, N, K, batch, m_blocks, n_blocks;
     uint32_t idesc_fmt;  // element-format bits of the instruction descriptor (idesc_formats)

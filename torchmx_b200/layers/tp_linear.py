@@ -8,6 +8,11 @@
   partial products are summed with one all-reduce over NVLink (NCCL).  Only the summation order differs
   from the single-GPU layer (G bf16 partials instead of one fp32 accumulation).
 
+Fused mode (`RowParallelMXLinear.enable_fused_allreduce(pool)`): the GEMM epilogue itself performs the reduction -- every
+rank adds its bf16 partial tile into a symmetric output buffer of ALL ranks through the NVLink multicast address
+(`multimem.red`, the sum is formed in the NVSwitch), tile by tile while the remaining tiles are still being computed; one
+cross-rank barrier replaces the NCCL all-reduce kernel and the partials never take a round trip through HBM.
+
 One process per GPU; `group=None` means the default process group.  With world_size 1 both classes
 degenerate to `MXInferenceLinear`.
 """
@@ -35,6 +40,57 @@ def _world_rank(group) -> Tuple[int, int]:
     if not (dist.is_available() and dist.is_initialized()):
         return 1, 0
     return dist.get_world_size(group), dist.get_rank(group)
+
+
+class FusedAllReducePool:
+    """Three rotating symmetric [max_rows, features] bf16 output buffers (torch symmetric memory: mapped on every rank of the
+    group, with a multicast address) shared by all row-parallel layers of one width.
+
+    Step k uses buffer k % 3.  Before the launch of step k this rank zeroes the rows buffer (k+1) % 3 had dirtied (last used
+    at step k-2, long consumed on this stream); the other ranks can only add into that buffer at step k+1, i.e. after the
+    barrier of step k, which this rank enters after the zeroing in stream order -- so one barrier per layer is enough.  The
+    tensor a layer returns is a view of the buffer: it is valid until two more fused layers of the same pool have run."""
+
+    def __init__(self, features: int, max_rows: int, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.features, self.max_rows, self.group = features, max_rows, group
+        self.bufs, self.hdls, self.dirty = [], [], [0, 0, 0]
+        for _ in range(3):
+            t = symm_mem.empty((max_rows, features), dtype=torch.bfloat16, device=dev)
+            h = symm_mem.rendezvous(t, group.group_name)
+            if not h.multicast_ptr:
+                raise RuntimeError("FusedAllReducePool: this system exposes no NVLink multicast (NVLS) address")
+            t.zero_()
+            self.bufs.append(t)
+            self.hdls.append(h)
+        self.step = 0
+        torch.cuda.synchronize()
+        dist.barrier(group)
+
+    def reset(self) -> None:
+        """Start a new sequence of fused layers (call once per forward pass, e.g. at the top of a captured CUDA graph): zero
+        whatever earlier steps left behind, restart the rotation at buffer 0 and meet the other ranks, so a replayed graph
+        always begins from the same, clean state whatever its number of layers."""
+        for i in range(3):
+            if self.dirty[i]:
+                self.bufs[i][: self.dirty[i]].zero_()
+                self.dirty[i] = 0
+        self.step = 0
+        self.hdls[0].barrier(channel=1)
+
+    def next(self, rows: int):
+        assert rows <= self.max_rows
+        k = self.step
+        self.step += 1
+        cur, nxt = k % 3, (k + 1) % 3
+        if self.dirty[nxt]:
+            self.bufs[nxt][: self.dirty[nxt]].zero_()
+            self.dirty[nxt] = 0
+        self.dirty[cur] = max(self.dirty[cur], rows)
+        return self.bufs[cur][:rows], self.hdls[cur]
 
 
 class ColumnParallelMXLinear(MXInferenceLinear):
@@ -72,9 +128,25 @@ class RowParallelMXLinear(MXInferenceLinear):
         new.full_in_features = mod.in_features
         return new
 
+    def enable_fused_allreduce(self, pool: "FusedAllReducePool") -> None:
+        assert pool.features == self.out_features
+        self._fused_pool = pool
+
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = super().forward(x)
+        pool = getattr(self, "_fused_pool", None)
+        if self.tp_world > 1 and pool is not None and x.numel() // x.shape[-1] <= pool.max_rows:
+            from .. import mx_gemm
+            rows = x.numel() // x.shape[-1]
+            view, hdl = pool.next(rows)
+            mx_gemm.set_fused_output(view, hdl.multicast_ptr)
+            y = super().forward(x)
+            if mx_gemm.take_fused_output() is None:  # the GEMM took the buffer: its epilogue already reduced across ranks
+                hdl.barrier(channel=0)               # every rank's adds have landed everywhere
+                return y
+            # the operands did not qualify for the fused epilogue: y is a plain local partial
+        else:
+            y = super().forward(x)
         if self.tp_world > 1:
             import torch.distributed as dist
             dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.tp_group)

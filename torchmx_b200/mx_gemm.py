@@ -24,7 +24,24 @@ aten = torch.ops.aten
 _DISABLED = os.environ.get("MXQ_DISABLE_TC", "0") == "1"
 _SHADOW_ATTR = "_mxq_e4m3_shadow"
 
-stats = {"tensor_core": 0, "fallback": 0, "transcode": 0}
+stats = {"tensor_core": 0, "fallback": 0, "transcode": 0, "fused_allreduce": 0}
+
+# Set by RowParallelMXLinear (fused all-reduce mode) around its F.linear call: (output view of a symmetric buffer, multicast
+# address of that view).  The next tensor-core launch writes nothing locally: it adds its partial into every rank's buffer
+# through the multicast address (mxq_gemm_args_t.d_multicast) and clears the slot, which tells the layer it was taken.
+_fused_out = None
+
+
+def set_fused_output(out_view, multicast_ptr: int) -> None:
+    global _fused_out
+    _fused_out = (out_view, multicast_ptr)
+
+
+def take_fused_output():
+    """-> the pending (view, ptr) if no launch consumed it (the layer then falls back to NCCL), else None"""
+    global _fused_out
+    pending, _fused_out = _fused_out, None
+    return pending
 
 
 def set_enabled(flag: bool) -> None:
@@ -97,9 +114,11 @@ def _qualifies(t: MXTensor) -> bool:
             and t._data.is_cuda and t._orig_dtype == torch.bfloat16)
 
 
-def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs, sfb_bs, out, a_fmt=FMT_E4M3_BYTES, b_fmt=FMT_E4M3_BYTES) -> bool:
+def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs, sfb_bs, out, a_fmt=FMT_E4M3_BYTES, b_fmt=FMT_E4M3_BYTES,
+            d_multicast: int = 0) -> bool:
     g = _C.GemmArgs()
     g.a_format, g.b_format = a_fmt, b_fmt
+    g.d_multicast = d_multicast or None
     g.a_codes, g.sfa, g.lda, g.ld_sfa = a_codes.data_ptr(), sfa.data_ptr(), a_codes.stride(-2), sfa.stride(-2)
     g.a_batch_stride, g.sfa_batch_stride = a_bs, sfa_bs
     g.b_codes, g.sfb, g.ldb, g.ld_sfb = b_codes.data_ptr(), sfb.data_ptr(), b_codes.stride(-2), sfb.stride(-2)
@@ -174,7 +193,13 @@ def _dispatch(aten_op, a, b, extra_front, extra_back):
     b_e, b_fmt = _operand_rows(b_codes, b._elem_dtype, b_origin if not batched else None)
     if a_e.stride(-1) != 1 or b_e.stride(-1) != 1:
         return None
-    out = torch.empty(lead_shape + (N,), dtype=torch.bfloat16, device=a._data.device)
+    global _fused_out
+    fused = _fused_out
+    if fused is not None and not batched and fused[0].shape == (M, N) and fused[0].is_contiguous():
+        out, d_mc = fused[0], fused[1]
+    else:
+        fused, d_mc = None, 0
+        out = torch.empty(lead_shape + (N,), dtype=torch.bfloat16, device=a._data.device)
     if out.numel() == 0:
         return out
     if batched:
@@ -183,5 +208,12 @@ def _dispatch(aten_op, a, b, extra_front, extra_back):
             return None  # expanded (stride 0) batch: not expressible as a TMA stride
     else:
         strides = (0, 0, 0, 0)
-    ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out, a_fmt, b_fmt)
+    ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out, a_fmt, b_fmt, d_mc)
+    if ok and fused is not None:
+        _fused_out = None  # consumed
+        stats["fused_allreduce"] += 1
+        return out.view(lead_shape + (N,))
+    if not ok and fused is not None:  # shape not supported with the fused epilogue: plain output, the layer all-reduces it
+        out = torch.empty(lead_shape + (N,), dtype=torch.bfloat16, device=a._data.device)
+        ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out, a_fmt, b_fmt, 0)
     return out if ok else None
