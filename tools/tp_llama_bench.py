@@ -37,17 +37,22 @@ SHAPES = {
 
 
 def rms_norm(x, w, eps=1e-5):
-    v = x.float()
-    return (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype) * w
+    return F.rms_norm(x, (x.shape[-1],), w, eps)
 
 
-def rope(x, pos, theta=500000.0):
-    # x: [B, H, T, D]; pos: [T]
-    d = x.shape[-1]
-    inv = 1.0 / (theta ** (torch.arange(0, d, 2, device=x.device, dtype=torch.float32) / d))
+def rope_tables(pos, d, theta=500000.0):
+    """cos / sin for the positions of this forward pass, shared by every layer: [1, 1, T, d/2] fp32"""
+    inv = 1.0 / (theta ** (torch.arange(0, d, 2, device=pos.device, dtype=torch.float32) / d))
     ang = pos.float()[:, None] * inv[None, :]
-    cos, sin = ang.cos()[None, None], ang.sin()[None, None]
-    x1, x2 = x.float()[..., : d // 2], x.float()[..., d // 2:]
+    return ang.cos()[None, None], ang.sin()[None, None]
+
+
+def rope(x, cs):
+    # x: [B, H, T, D] (query and key heads concatenated along H), rotate-half convention
+    cos, sin = cs
+    d = x.shape[-1]
+    xf = x.float()
+    x1, x2 = xf[..., : d // 2], xf[..., d // 2:]
     return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], -1).to(x.dtype)
 
 
@@ -87,14 +92,15 @@ class TPDecoderLayer(torch.nn.Module):
         self.n1 = torch.ones(h, device="cuda", dtype=torch.bfloat16)
         self.n2 = torch.ones(h, device="cuda", dtype=torch.bfloat16)
 
-    def forward(self, x, pos, kc, vc, cache_len):
+    def forward(self, x, pos, kc, vc, cache_len, cs):
         # x: [B, T, hidden] replicated; kc/vc: [B, nkv_local, S, hd] this rank's KV cache; tokens are written at pos
         B, T, _ = x.shape
         y = rms_norm(x, self.n1)
         q = self.q(y).view(B, T, self.nh_local, self.hd).transpose(1, 2)
         k = self.k(y).view(B, T, self.nkv_local, self.hd).transpose(1, 2)
         v = self.v(y).view(B, T, self.nkv_local, self.hd).transpose(1, 2)
-        q, k = rope(q, pos), rope(k, pos)
+        qk = rope(torch.cat([q, k], 1), cs)
+        q, k = qk[:, : self.nh_local], qk[:, self.nh_local:]
         kc.index_copy_(2, pos, k)
         vc.index_copy_(2, pos, v)
         if T > 1:  # prefill from an empty cache: causal attention over the new tokens
@@ -149,7 +155,7 @@ def run_infer(args, world, rank):
     pool = None
     if args.fused and world > 1:
         from torchmx_b200.layers.tp_linear import FusedAllReducePool
-        pool = FusedAllReducePool(h, max(args.prefill, args.batch), None)
+        pool = FusedAllReducePool(h, max(args.prefill, args.batch), None, fused_max_rows=args.fused_max_rows)
         for l in layers:
             l.o.enable_fused_allreduce(pool)
             l.down.enable_fused_allreduce(pool)
@@ -163,8 +169,9 @@ def run_infer(args, world, rank):
     def stack(x, pos, caches, cache_len):
         if pool is not None and layers[0].o._fused_pool is not None:
             pool.reset()
+        cs = rope_tables(pos, layers[0].hd)
         for l, (kc, vc) in zip(layers, caches):
-            x = l(x, pos, kc, vc, cache_len)
+            x = l(x, pos, kc, vc, cache_len, cs)
         return x
 
     def make_caches(B, S):
@@ -202,7 +209,7 @@ def run_infer(args, world, rank):
         c1 = [(torch.zeros(1, l.nkv_local, P, l.hd, device="cuda", dtype=torch.bfloat16), torch.zeros(1, l.nkv_local, P, l.hd, device="cuda", dtype=torch.bfloat16))
               for l in ref_layers]
         for l, (kc, vc) in zip(ref_layers, c1):
-            xr = l(xr, pos, kc, vc, 0)
+            xr = l(xr, pos, kc, vc, 0, rope_tables(pos, l.hd))
         c2 = make_caches(1, P)
         xt = stack(x, pos, c2, 0).clone()
         if pool is not None:
@@ -213,6 +220,7 @@ def run_infer(args, world, rank):
             xn = stack(x, pos, make_caches(1, P), 0)
             res["check_rel_err_fused_vs_nccl"] = float((xt.float() - xn.float()).norm() / xn.float().norm())
             # single row-parallel layer, decode and prefill sized: fused vs NCCL on identical inputs
+            pool.fused_max_rows = pool.max_rows  # exercise the CTA-pair kernel's fused epilogue too
             for rows in (args.batch, P):
                 a = torch.randn(rows, layers[0].o.in_features, device="cuda", dtype=torch.bfloat16, generator=gen)
                 y_n = layers[0].o(a).clone()
@@ -294,6 +302,7 @@ def main():
     ap.add_argument("--wdtype", default="float4_e2m1")
     ap.add_argument("--adtype", default="float8_e4m3")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--fused-max-rows", type=int, default=128, help="fused all-reduce for at most this many tokens, NCCL above")
     ap.add_argument("--fused", action="store_true", help="row-parallel layers reduce in the GEMM epilogue (NVLink multicast) instead of NCCL")
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
