@@ -119,6 +119,12 @@ __device__ __forceinline__ float f16hi_to_f32(uint32_t h2) {
     return f;
 }
 // two fp32 -> bf16x2 (RNE, subnormals kept): low half = first
+// Programmatic dependent launch (sm_90+): a grid launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; it must execute pdl_wait() before touching anything the predecessor
+// wrote (or may still read).  pdl_launch_dependents() lets a following such grid be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float first, float second) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));

@@ -30,6 +30,7 @@ struct Params {
     int M, N, K, splits;
     int w_tiled;  // W codes are the tile-major shadow ([N/128][K/128][128][128 B])
     uint32_t idesc_fmt, tx_w, tx_x;  // element formats of the descriptor; bytes a W / X box posts on the mbarrier
+    int pdl;      // launched with programmatic stream serialization: X / its scales may only be read after griddepcontrol.wait
     int pf_dist;  // L2 prefetch distance of the W stream, in K blocks
     int sf_tma;   // scales are 16-byte aligned with a 16-byte multiple row pitch: fetch them with TMA (deep prefetch)
 };
@@ -117,17 +118,31 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();  // the next launch of the stream (if it opted in) may set itself up and start streaming ITS weights
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
+            // Programmatic dependent launch: this grid may be running before the kernel that produces the activation has
+            // finished.  The weights do not depend on it, so the first ring of W tiles is requested right away; everything
+            // that reads X (and, transitively, every write of D) comes after pdl_wait().
+            const int n_pre = p.pdl ? min(k_blocks, STAGES) : 0;
+            for (int i = 0; i < n_pre; ++i) {
+                mbar_arrive_expect_tx(&full[i], p.tx_w + p.tx_x);
+                tma_load_3d(&map_w, &full[i], smem + L::OFF_W + i * L::W_STAGE, (kb0 + i) * BLOCK_K, n0, 0);
+            }
+            if (p.pdl) pdl_wait();
+            for (int i = 0; i < n_pre; ++i) {
+                tma_load_3d(&map_x, &full[i], smem + L::OFF_X + i * L::X_STAGE, (kb0 + i) * BLOCK_K, 0, 0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
             // The TMA unit keeps only a few tens of KB of loads in flight per SM, which at DRAM latency is ~1/3 of the HBM
             // rate; L2 prefetches are fire-and-forget, so W is pulled DRAM -> L2 `pf_dist` K blocks ahead of the ring and
             // the ring's own loads become L2 hits.
             const int pf_dist = p.pf_dist;
             for (int kb = kb0; kb < kb1 && kb < kb0 + pf_dist; ++kb) tma_prefetch_l2_3d(&map_w, kb * BLOCK_K, n0, 0);
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int kb = kb0 + n_pre; kb < kb1; ++kb) {
                 if (kb + pf_dist < kb1) tma_prefetch_l2_3d(&map_w, (kb + pf_dist) * BLOCK_K, n0, 0);
                 mbar_wait(&empty[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full[stage], p.tx_w + p.tx_x);
@@ -185,6 +200,7 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&sf_full[st]);
         };
+        if (warp == 3 && p.pdl) pdl_wait();  // the token scales are written by the preceding quantize kernel
         if (p.sf_tma) {
             if (warp == 2)
                 sf_tma_tile4<RAW_W>(&map_sfw, kb0 * 4, n0, k_blocks, smem + L::OFF_RAW_W, raw_w, smem + L::OFF_SFW, sf_empty, sfs, sf_phase, lane, arrive);
@@ -297,6 +313,7 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
     p.tx_w = TILE_W * BLOCK_K * operand_bits(a->b_format) / 8;
     p.tx_x = N_TOK * BLOCK_K * operand_bits(a->a_format) / 8;
     p.sf_tma = sf_tma;
+    p.pdl = getenv("MXQ_PDL") ? atoi(getenv("MXQ_PDL")) : 1;
     p.pf_dist = getenv("MXQ_SKINNY_PF") ? atoi(getenv("MXQ_SKINNY_PF")) : 0;  // measured: no gain on B200 (0 = off)
     const int n_tiles = (int)((a->N + TILE_W - 1) / TILE_W);
     cudaLaunchConfig_t cfg = {};
@@ -304,13 +321,15 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = L::DYN_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)splits;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = p.pdl ? 2 : 1;
     e = cudaLaunchKernelEx(&cfg, kernel, mw, mx, msw, msx, p);
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (skinny): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;

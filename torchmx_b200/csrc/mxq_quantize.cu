@@ -84,6 +84,7 @@ __device__ __forceinline__ void nanblock_words(const uint32_t (&w)[NW], bool hw_
 template <int ELEM, int EPT>
 __global__ void __launch_bounds__(kQuantThreads) quantize_b32_bf16_kernel(const uint16_t* __restrict__ src, uint8_t* __restrict__ codes,
                                                                            uint8_t* __restrict__ scales, int64_t n_blocks, uint32_t flags) {
+    pdl_launch_dependents();       // a dependent MX GEMM may start streaming its weights while the activation is quantized
     constexpr int LPB = 32 / EPT;  // lanes per MX block
     constexpr int NW = EPT / 2;    // 32-bit words of bf16 pairs per thread
     constexpr int NO = (ELEM == MXQ_ELEM_E2M1) ? NW / 4 : NW / 2;
