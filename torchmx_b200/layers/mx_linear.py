@@ -11,6 +11,7 @@ import os
 import torch
 import torch.nn.functional as F
 
+from .. import mx_gemm
 from ..config import QLinearConfig
 from ..mx_tensor import MXTensor
 
@@ -72,9 +73,9 @@ class MXInferenceLinear(torch.nn.Linear):
         return new
 
     def _weight_mx(self) -> MXTensor:
-        w = self.weight.data
-        if isinstance(w, MXTensor):
+        if isinstance(self.weight, MXTensor):  # (a Parameter made from an MXTensor IS that subclass; `.data` would dispatch a detach)
             return self.weight
+        w = self.weight.data
         # weights that were on `meta` at conversion time arrive high-precision (often fp32) at call time
         # (reference: mx_linear.py:68-92): quantize on the fly, leave self.weight untouched
         wc = self.qconfig.weights_config
@@ -85,6 +86,12 @@ class MXInferenceLinear(torch.nn.Linear):
         ac = self.qconfig.activations_config
         x_mx = _quantize_activation(x, ac.elem_dtype, ac.block_size)
         bias = self.bias
-        if not isinstance(self.weight.data, MXTensor) and bias is not None:
+        if not isinstance(self.weight, MXTensor) and bias is not None:
             bias = bias.to(torch.bfloat16)
-        return F.linear(x_mx, self._weight_mx(), bias)
+        w_mx = self._weight_mx()
+        # F.linear(x_mx, w_mx, bias) reaches the same kernel through the dispatcher (aten.t + aten.mm / addmm on MXTensor
+        # views, ~50 us of host time per layer); hand the operands to the tensor-core path directly when they qualify
+        out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x_mx, w_mx, (), (bias,), count_fallback=False)
+        if out is not None:
+            return out
+        return F.linear(x_mx, w_mx, bias)

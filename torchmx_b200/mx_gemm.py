@@ -133,11 +133,14 @@ def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs
     return True
 
 
-def try_tensor_core(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back) -> Optional[torch.Tensor]:
+def try_tensor_core(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back, count_fallback: bool = True) -> Optional[torch.Tensor]:
     out = None
     if not _DISABLED and _qualifies(a) and _qualifies(b):
         out = _dispatch(aten_op, a, b, extra_front, extra_back)
-    stats["tensor_core" if out is not None else "fallback"] += 1
+    if out is not None:
+        stats["tensor_core"] += 1
+    elif count_fallback:
+        stats["fallback"] += 1
     return out
 
 
