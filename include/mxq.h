@@ -133,6 +133,13 @@ typedef struct {
      * cross-rank barrier has passed, each rank's copy holds the sum.  The buffer must be zero on every rank before the
      * first launch that targets it; needs N % 8 == 0, a 16-byte aligned buffer and batch == 1. */
     void *d_multicast;
+    /* Fused activation quantization (MXInferenceLinear.forward, torchmx/layers/mx_linear.py:63-94): when non-NULL, `x_bf16`
+     * is the HIGH-PRECISION activation [M, K] (bf16, row stride ldx elements, 16-byte aligned rows) and a_codes / sfa are
+     * ignored: the kernel computes quantize_mx(x, float8_e4m3, 32) itself, block by block, on its way into shared memory
+     * (same arithmetic as mxq_quantize, bit-identical), so the activation never makes a round trip through HBM as codes and
+     * the separate quantize launch disappears.  x_quant_flags = MXQ_FLAG_* of mxq_quantize.  Decode shapes only
+     * (M <= 64, batch == 1); otherwise MXQ_ERR_UNSUPPORTED_SHAPE and the caller quantizes first. */
+    const void *x_bf16; int64_t ldx; int x_quant_flags;
 } mxq_gemm_args_t;
 MXQ_API int mxq_gemm(const mxq_gemm_args_t *args, int device, void *stream);
 

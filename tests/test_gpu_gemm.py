@@ -272,3 +272,35 @@ def test_packed_and_container_operands_agree_bit_for_bit(mx, wdt):
             finally:
                 mx_gemm.set_packed_operands(True)
         assert torch.equal(outs[0], outs[1]), (M, N, K, batch)
+
+
+@pytest.mark.parametrize("rows,N,K,wdt,bias", [(32, 1536, 4096, "float6_e3m2", True), (1, 640, 1024, "float4_e2m1", False), (64, 4096, 2048, "float8_e4m3", True),
+                                              (17, 1000, 512, "float6_e2m3", False), (48, 256, 14336, "float6_e3m2", False)])
+@pytest.mark.parametrize("mode", ["False", "True"])
+def test_fused_activation_quantization_is_bit_identical(mx, rows, N, K, wdt, bias, mode):
+    """MXInferenceLinear.forward with the activation quantized inside the decode GEMM == quantize_mx (K1) followed by the MX
+    matmul, bit for bit -- including blocks that hold Inf / NaN (scale 255) under both values of the hw_exact toggle."""
+    from torchmx import env_variables as env
+    from torchmx.config import MXConfig, QLinearConfig
+    from torchmx.layers.mx_linear import MXInferenceLinear
+    from torchmx_b200 import mx_gemm
+    env.MX_EXACT_QUANTIZATION = mode
+    g = torch.Generator(device=DEV).manual_seed(rows * 31 + N)
+    lin = torch.nn.Linear(K, N, bias=bias).to(DEV, torch.bfloat16)
+    layer = MXInferenceLinear.from_float(lin, QLinearConfig(weights_config=MXConfig(wdt, 32), activations_config=MXConfig("float8_e4m3", 32)))
+    x = torch.randn(rows, K, device=DEV, dtype=torch.bfloat16, generator=g)
+    x *= torch.exp2(torch.randint(-12, 12, (rows, K // 32), device=DEV, generator=g).float()).repeat_interleave(32, -1).to(torch.bfloat16)
+    x[0, 5] = float("inf")
+    x[-1, K - 3] = float("nan")
+    n0 = mx_gemm.stats.get("fused_act_quant", 0)
+    y_fused = layer(x)
+    assert mx_gemm.stats.get("fused_act_quant", 0) == n0 + 1, "expected the fused path"
+    old = mx_gemm._FUSED_ACT
+    mx_gemm._FUSED_ACT = False
+    try:
+        y_two = layer(x)
+    finally:
+        mx_gemm._FUSED_ACT = old
+    assert mx_gemm.stats.get("fused_act_quant", 0) == n0 + 1
+    assert torch.equal(torch.nan_to_num(y_fused.float(), nan=12345.0), torch.nan_to_num(y_two.float(), nan=12345.0))
+    assert torch.isnan(y_fused[0]).all() and torch.isnan(y_fused[-1]).all() and (rows < 3 or not torch.isnan(y_fused[1]).any())

@@ -29,6 +29,7 @@ class GemmArgs(ctypes.Structure):
         ("batch", ctypes.c_int64), ("M", ctypes.c_int64), ("N", ctypes.c_int64), ("K", ctypes.c_int64),
         ("a_format", ctypes.c_int), ("b_format", ctypes.c_int),
         ("d_multicast", ctypes.c_void_p),
+        ("x_bf16", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("x_quant_flags", ctypes.c_int),
     ]
 
 

@@ -684,6 +684,10 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
         const int rc = launch_gemm_skinny(a, sm_count, stream, msg, msg_len);
         if (rc != MXQ_ERR_UNSUPPORTED_SHAPE) return rc;
     }
+    if (a->x_bf16 != nullptr) {
+        snprintf(msg, msg_len, "fused activation quantization is implemented by the skinny (decode) kernel only");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
     if (a->d_multicast != nullptr && !(a->M > 128 && a->N > 128)) {
         snprintf(msg, msg_len, "d_multicast (fused all-reduce) is implemented by the CTA-pair and skinny kernels only");
         return MXQ_ERR_UNSUPPORTED_SHAPE;

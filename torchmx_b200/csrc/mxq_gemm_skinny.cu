@@ -13,6 +13,7 @@
 // Per CTA: warp 0 TMA producer (W 128 x 128 B + X N_TOK x 128 B per K block, STAGES-deep ring), warp 1 MMA issuer
 // (tcgen05.mma cta_group::1 kind::mxf8f6f4.block_scale, M=128, N=N_TOK), warps 2/3 scale-factor loaders (W rows /
 // token rows, four K blocks per ring stage), warps 4..7 epilogue.
+#include "mxq_quant_core.cuh"
 #include "mxq_tc.cuh"
 
 namespace mxq {
@@ -26,6 +27,7 @@ constexpr int SF_KB_BYTES = 512;  // one K block of scale factors for (up to) 12
 struct Params {
     const uint8_t* sfx; const uint8_t* sfw; const uint16_t* bias; uint16_t* d;
     uint16_t* d_mc;  // multicast alias of the output on every rank: add (multimem.red) instead of store
+    const uint16_t* x_hp; int64_t ldx; int x_flags;  // fused mode: bf16 activation, quantized to e4m3 / block 32 in the kernel
     int64_t ld_sfx, ld_sfw, ldd;
     int M, N, K, splits;
     int w_tiled;  // W codes are the tile-major shadow ([N/128][K/128][128][128 B])
@@ -99,12 +101,15 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
         tma_prefetch_desc(&map_x);
     }
     if (warp == 1 && elect_one()) {
+        // fused activation quantization: the four epilogue warps produce the X tile and its scales themselves and arrive
+        // on the stage barriers in place of the X TMA bytes / the token-scale loader warp
+        const uint32_t xq = p.x_hp != nullptr ? 4u : 0u;
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&full[i], 1);
+            mbar_init(&full[i], 1 + xq);
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < SF_STAGES; ++i) {
-            mbar_init(&sf_full[i], 2);
+            mbar_init(&sf_full[i], xq ? 1 + xq : 2);
             mbar_init(&sf_empty[i], 1);
         }
         mbar_init(tmem_full, 1);
@@ -128,13 +133,15 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
             // finished.  The weights do not depend on it, so the first ring of W tiles is requested right away; everything
             // that reads X (and, transitively, every write of D) comes after pdl_wait().
             const int n_pre = p.pdl ? min(k_blocks, STAGES) : 0;
+            const bool xq = p.x_hp != nullptr;
+            const uint32_t tx = p.tx_w + (xq ? 0u : p.tx_x);
             for (int i = 0; i < n_pre; ++i) {
-                mbar_arrive_expect_tx(&full[i], p.tx_w + p.tx_x);
+                mbar_arrive_expect_tx(&full[i], tx);
                 tma_load_3d(&map_w, &full[i], smem + L::OFF_W + i * L::W_STAGE, (kb0 + i) * BLOCK_K, n0, 0);
             }
             if (p.pdl) pdl_wait();
             for (int i = 0; i < n_pre; ++i) {
-                tma_load_3d(&map_x, &full[i], smem + L::OFF_X + i * L::X_STAGE, (kb0 + i) * BLOCK_K, 0, 0);
+                if (!xq) tma_load_3d(&map_x, &full[i], smem + L::OFF_X + i * L::X_STAGE, (kb0 + i) * BLOCK_K, 0, 0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             // The TMA unit keeps only a few tens of KB of loads in flight per SM, which at DRAM latency is ~1/3 of the HBM
@@ -145,12 +152,12 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
             for (int kb = kb0 + n_pre; kb < kb1; ++kb) {
                 if (kb + pf_dist < kb1) tma_prefetch_l2_3d(&map_w, (kb + pf_dist) * BLOCK_K, n0, 0);
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], p.tx_w + p.tx_x);
+                mbar_arrive_expect_tx(&full[stage], tx);
                 if (p.w_tiled)
                     tma_load_4d(&map_w, &full[stage], smem + L::OFF_W + stage * L::W_STAGE, 0, 0, kb, tile);
                 else
                     tma_load_3d(&map_w, &full[stage], smem + L::OFF_W + stage * L::W_STAGE, kb * BLOCK_K, n0, 0);
-                tma_load_3d(&map_x, &full[stage], smem + L::OFF_X + stage * L::X_STAGE, kb * BLOCK_K, 0, 0);
+                if (!xq) tma_load_3d(&map_x, &full[stage], smem + L::OFF_X + stage * L::X_STAGE, kb * BLOCK_K, 0, 0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -200,8 +207,13 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&sf_full[st]);
         };
-        if (warp == 3 && p.pdl) pdl_wait();  // the token scales are written by the preceding quantize kernel
-        if (p.sf_tma) {
+        if (warp == 3 && p.x_hp != nullptr) {
+            // fused mode: the token scales are produced by the quantizer (epilogue) warps
+        } else if (warp == 3 && p.pdl) {
+            pdl_wait();  // the token scales are written by the preceding quantize kernel
+        }
+        if (warp == 3 && p.x_hp != nullptr) {
+        } else if (p.sf_tma) {
             if (warp == 2)
                 sf_tma_tile4<RAW_W>(&map_sfw, kb0 * 4, n0, k_blocks, smem + L::OFF_RAW_W, raw_w, smem + L::OFF_SFW, sf_empty, sfs, sf_phase, lane, arrive);
             else
@@ -212,6 +224,72 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
             sf_load_tile4<1>(p.sfx + (int64_t)kb0 * 4, p.ld_sfx, 0, p.M, k_blocks, smem + L::OFF_SFX, SF_KB_BYTES, sf_empty, sfs, sf_phase, lane, arrive);
         }
     } else {
+        if constexpr (N_TOK <= 64) if (p.x_hp != nullptr) {
+            // ================= fused activation quantization (K1 arithmetic, one MX block per thread and K block) =================
+            // 128 threads cover the N_TOK x 4 blocks of a K block: block b -> token row b / 4, K sub-block b % 4, so four
+            // lanes read one row's 256 contiguous bytes.  Codes go straight into the 128B-swizzled K-major X tile the MMA
+            // reads (16-byte chunk c of row t at chunk c ^ (t & 7)), the scale byte into the tcgen05.cp chunk layout.
+            constexpr int NB = (N_TOK * 4 + 127) / 128;  // blocks per thread and K block
+            const int tid = (warp - 4) * 32 + lane;
+            const bool hw_exact = (p.x_flags & MXQ_FLAG_HW_EXACT) != 0;
+            if (p.pdl) pdl_wait();  // the activation is written by the preceding kernel of the stream
+            uint32_t cur[NB][16], nxt[NB][16];
+            auto load = [&](int kb, uint32_t (&dst)[NB][16]) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int b = tid + 128 * i, t = b >> 2, j = b & 3;
+                    if (b < N_TOK * 4 && t < p.M) {
+                        const uint4* src = reinterpret_cast<const uint4*>(p.x_hp + (int64_t)t * p.ldx + (int64_t)(kb0 + kb) * BLOCK_K + j * 32);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 v = src[q];
+                            dst[i][4 * q] = v.x; dst[i][4 * q + 1] = v.y; dst[i][4 * q + 2] = v.z; dst[i][4 * q + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) dst[i][q] = 0;
+                    }
+                }
+            };
+            uint32_t stage = 0, phase = 0, sfs = 0, sf_phase = 0, sf_j = 0;
+            load(0, cur);
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                if (kb + 1 < k_blocks) load(kb + 1, nxt);
+                if (sf_j == 0) mbar_wait(&sf_empty[sfs], sf_phase ^ 1);
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* xt = smem + L::OFF_X + stage * L::X_STAGE;
+                uint8_t* sfx = smem + L::OFF_SFX + sfs * L::SF_STAGE + sf_j * SF_KB_BYTES;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int b = tid + 128 * i, t = b >> 2, j = b & 3;
+                    if (b < N_TOK * 4) {
+                        uint32_t out[8];
+                        const int s = quantize_block32<MXQ_ELEM_E4M3>(cur[i], hw_exact, out);
+                        *reinterpret_cast<uint4*>(xt + t * 128 + (((2 * j) ^ (t & 7)) << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
+                        *reinterpret_cast<uint4*>(xt + t * 128 + (((2 * j + 1) ^ (t & 7)) << 4)) = make_uint4(out[4], out[5], out[6], out[7]);
+                        sfx[(t & 31) * 16 + (t >> 5) * 4 + j] = (uint8_t)s;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                const bool sf_done = sf_j == SF_KB - 1 || kb == k_blocks - 1;
+                if (lane == 0) {
+                    mbar_arrive(&full[stage]);
+                    if (sf_done) mbar_arrive(&sf_full[sfs]);
+                }
+                if (sf_done) {
+                    sf_j = 0;
+                    if (++sfs == SF_STAGES) { sfs = 0; sf_phase ^= 1; }
+                } else {
+                    ++sf_j;
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) cur[i][q] = nxt[i][q];
+            }
+        }
         // ================= epilogue, part 1: accumulator -> global (S == 1) or -> partial-sum buffer (S > 1) =================
         const int quad = warp & 3;
         const int r = quad * 32 + lane;  // accumulator lane == weight row within the tile
@@ -289,27 +367,30 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
     CUtensorMap mw, mx;
     const int fake_tiled = getenv("MXQ_SKINNY_FAKE_TILED") ? atoi(getenv("MXQ_SKINNY_FAKE_TILED")) : 0;  // timing experiment only (wrong results)
     const bool w_ok = fake_tiled ? make_tiled_operand_map(&mw, a->b_codes, a->K, a->N / 128 * 128, 1) : make_operand_map(&mw, a->b_codes, a->K, a->N, 1, a->ldb, 0, TILE_W, a->b_format);
-    if (!w_ok || !make_operand_map(&mx, a->a_codes, a->K, a->M, 1, a->lda, 0, N_TOK, a->a_format)) {
+    const bool xq = a->x_bf16 != nullptr;
+    if (xq) mx = mw;  // unused placeholders in fused-quantization mode
+    if (!w_ok || (!xq && !make_operand_map(&mx, a->a_codes, a->K, a->M, 1, a->lda, 0, N_TOK, a->a_format))) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
     // scales by TMA when their layout allows it (every split then starts on a 16-byte boundary: splits are 4-K-block aligned)
     CUtensorMap msw = mw, msx = mx;
     const int k_blocks_total = (int)(a->K / BLOCK_K);
-    int sf_tma = ((uintptr_t)a->sfa % 16 == 0) && ((uintptr_t)a->sfb % 16 == 0) && (a->ld_sfa % 16 == 0) && (a->ld_sfb % 16 == 0) &&
+    int sf_tma = (xq || (((uintptr_t)a->sfa % 16 == 0) && (a->ld_sfa % 16 == 0))) && ((uintptr_t)a->sfb % 16 == 0) && (a->ld_sfb % 16 == 0) &&
                  (k_blocks_total % (splits * SF_KB) == 0) && !getenv("MXQ_SKINNY_NO_SFTMA");
-    if (sf_tma && (!make_scale_map(&msw, a->sfb, a->K / 32, a->N, a->ld_sfb) || !make_scale_map(&msx, a->sfa, a->K / 32, a->M, a->ld_sfa))) sf_tma = 0;
+    if (sf_tma && (!make_scale_map(&msw, a->sfb, a->K / 32, a->N, a->ld_sfb) || (!xq && !make_scale_map(&msx, a->sfa, a->K / 32, a->M, a->ld_sfa)))) sf_tma = 0;
     auto kernel = mx_gemm_skinny_kernel<N_TOK, STAGES, RAW_W>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     Params p;
     p.sfx = a->sfa; p.sfw = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
     p.d_mc = (uint16_t*)a->d_multicast;
+    p.x_hp = (const uint16_t*)a->x_bf16; p.ldx = a->ldx; p.x_flags = a->x_quant_flags;
     p.ld_sfx = a->ld_sfa; p.ld_sfw = a->ld_sfb; p.ldd = a->ldd;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.splits = splits;
     p.w_tiled = fake_tiled;
     // the weights are the MMA A operand here, the tokens the B operand
-    p.idesc_fmt = idesc_formats(a->b_format, a->a_format);
+    p.idesc_fmt = idesc_formats(a->b_format, xq ? MXQ_OPERAND_E4M3_BYTES : a->a_format);
     p.tx_w = TILE_W * BLOCK_K * operand_bits(a->b_format) / 8;
     p.tx_x = N_TOK * BLOCK_K * operand_bits(a->a_format) / 8;
     p.sf_tma = sf_tma;
@@ -341,6 +422,10 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
 int launch_gemm_skinny(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, char* msg, size_t msg_len) {
     using namespace skinny;
     if (a->batch != 1 || a->M > 128 || a->K % BLOCK_K) return MXQ_ERR_UNSUPPORTED_SHAPE;
+    if (a->x_bf16 != nullptr && (a->M > 64 || ((uintptr_t)a->x_bf16 % 16) || (a->ldx % 8))) {
+        snprintf(msg, msg_len, "fused activation quantization needs M <= 64 and 16-byte aligned activation rows");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
     if (a->d_multicast != nullptr && (((uintptr_t)a->d_multicast % 4) || (a->ldd % 2) || (a->N % 2))) {
         snprintf(msg, msg_len, "d_multicast needs an even N / ldd and a 4-byte aligned buffer");
         return MXQ_ERR_UNSUPPORTED_SHAPE;

@@ -11,6 +11,7 @@ import os
 import torch
 import torch.nn.functional as F
 
+from .. import env_variables as env
 from .. import mx_gemm
 from ..config import QLinearConfig
 from ..mx_tensor import MXTensor
@@ -84,11 +85,16 @@ class MXInferenceLinear(torch.nn.Linear):
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         ac = self.qconfig.activations_config
-        x_mx = _quantize_activation(x, ac.elem_dtype, ac.block_size)
         bias = self.bias
         if not isinstance(self.weight, MXTensor) and bias is not None:
             bias = bias.to(torch.bfloat16)
         w_mx = self._weight_mx()
+        if ac.elem_dtype_name == "float8_e4m3" and ac.block_size == 32:
+            # decode-sized activations: quantization fused into the weight-streaming GEMM (one launch, no code round trip)
+            out = mx_gemm.linear_fused_act_quant(x, w_mx, bias, env.MX_EXACT_QUANTIZATION == "True")
+            if out is not None:
+                return out
+        x_mx = _quantize_activation(x, ac.elem_dtype, ac.block_size)
         # F.linear(x_mx, w_mx, bias) reaches the same kernel through the dispatcher (aten.t + aten.mm / addmm on MXTensor
         # views, ~50 us of host time per layer); hand the operands to the tensor-core path directly when they qualify
         out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x_mx, w_mx, (), (bias,), count_fallback=False)

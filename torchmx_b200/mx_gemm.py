@@ -115,11 +115,14 @@ def _qualifies(t: MXTensor) -> bool:
 
 
 def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs, sfb_bs, out, a_fmt=FMT_E4M3_BYTES, b_fmt=FMT_E4M3_BYTES,
-            d_multicast: int = 0) -> bool:
+            d_multicast: int = 0, x_hp: Optional[torch.Tensor] = None, x_flags: int = 0) -> bool:
     g = _C.GemmArgs()
     g.a_format, g.b_format = a_fmt, b_fmt
     g.d_multicast = d_multicast or None
-    g.a_codes, g.sfa, g.lda, g.ld_sfa = a_codes.data_ptr(), sfa.data_ptr(), a_codes.stride(-2), sfa.stride(-2)
+    if x_hp is not None:  # fused activation quantization: the kernel reads the bf16 activation itself
+        g.x_bf16, g.ldx, g.x_quant_flags = x_hp.data_ptr(), x_hp.stride(-2), x_flags
+    else:
+        g.a_codes, g.sfa, g.lda, g.ld_sfa = a_codes.data_ptr(), sfa.data_ptr(), a_codes.stride(-2), sfa.stride(-2)
     g.a_batch_stride, g.sfa_batch_stride = a_bs, sfa_bs
     g.b_codes, g.sfb, g.ldb, g.ld_sfb = b_codes.data_ptr(), sfb.data_ptr(), b_codes.stride(-2), sfb.stride(-2)
     g.b_batch_stride, g.sfb_batch_stride = b_bs, sfb_bs
@@ -220,3 +223,48 @@ def _dispatch(aten_op, a, b, extra_front, extra_back):
         out = torch.empty(lead_shape + (N,), dtype=torch.bfloat16, device=a._data.device)
         ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out, a_fmt, b_fmt, 0)
     return out if ok else None
+
+
+# MXQ_FUSED_ACT_QUANT=0 keeps the separate activation-quantize launch in MXInferenceLinear.forward
+_FUSED_ACT = os.environ.get("MXQ_FUSED_ACT_QUANT", "1") != "0"
+FUSED_ACT_MAX_ROWS = 64
+
+
+def linear_fused_act_quant(x: torch.Tensor, w: MXTensor, bias, hw_exact: bool) -> Optional[torch.Tensor]:
+    """MXInferenceLinear.forward for decode-sized activations in ONE launch: y = quantize_mx(x, float8_e4m3, 32) @ w^T (+ bias)
+    with the quantization done inside the weight-streaming kernel (bit-identical to the two-launch path).  Returns None when
+    the operands do not qualify; the caller then quantizes with K1 and goes through `try_tensor_core`."""
+    global _fused_out
+    if _DISABLED or not _FUSED_ACT or type(x) is not torch.Tensor or not x.is_cuda or x.dtype != torch.bfloat16 or not _qualifies(w):
+        return None
+    K = x.shape[-1]
+    if w._data.dim() != 2 or w._block_dim != 1 or K % 128 != 0 or w.shape[-1] != K or not x.is_contiguous():
+        return None
+    rows = x.numel() // K
+    if rows == 0 or rows > FUSED_ACT_MAX_ROWS:
+        return None
+    wk = _rows_k(w, 1)
+    if wk is None:
+        return None
+    if bias is not None and (isinstance(bias, MXTensor) or bias.dtype != torch.bfloat16 or bias.dim() != 1 or not bias.is_contiguous()):
+        return None
+    b_e, b_fmt = _operand_rows(wk[0], w._elem_dtype, getattr(w, "_mxq_origin", w))
+    N = w.shape[0]
+    x2 = x.view(rows, K)
+    fused = _fused_out
+    if fused is not None and fused[0].shape == (rows, N) and fused[0].is_contiguous():
+        out, d_mc = fused[0], fused[1]
+    else:
+        fused, d_mc = None, 0
+        out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.bfloat16, device=x.device)
+    ok = _launch(None, None, b_e, wk[1], bias, 1, rows, N, K, 0, 0, 0, 0, out, FMT_E4M3_BYTES, b_fmt, d_mc, x_hp=x2,
+                 x_flags=_C.FLAG_HW_EXACT if hw_exact else 0)
+    if not ok:
+        return None
+    stats["tensor_core"] += 1
+    stats["fused_act_quant"] = stats.get("fused_act_quant", 0) + 1
+    if fused is not None:
+        _fused_out = None
+        stats["fused_allreduce"] += 1
+        return out.view(tuple(x.shape[:-1]) + (N,))
+    return out
