@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
         // on the stage barriers in place of the X TMA bytes / the token-scale loader warp
         const uint32_t xq = p.x_hp != nullptr ? 4u : 0u;
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&full[i], 1 + xq);
+            mbar_init(&full[i], xq ? 2 : 1);  // producer (+ tx bytes) and, in fused mode, the quantizer warp that owns the K block
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < SF_STAGES; ++i) {
@@ -225,69 +225,63 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
         }
     } else {
         if constexpr (N_TOK <= 64) if (p.x_hp != nullptr) {
-            // ================= fused activation quantization (K1 arithmetic, one MX block per thread and K block) =================
-            // 128 threads cover the N_TOK x 4 blocks of a K block: block b -> token row b / 4, K sub-block b % 4, so four
-            // lanes read one row's 256 contiguous bytes.  Codes go straight into the 128B-swizzled K-major X tile the MMA
-            // reads (16-byte chunk c of row t at chunk c ^ (t & 7)), the scale byte into the tcgen05.cp chunk layout.
-            constexpr int NB = (N_TOK * 4 + 127) / 128;  // blocks per thread and K block
-            const int tid = (warp - 4) * 32 + lane;
+            // ================= fused activation quantization (K1 arithmetic, one thread per MX block) =================
+            // Quantizer warp w owns K blocks w, w+4, ... (= slot w of every 4-K-block scale-factor stage), so four K blocks
+            // are in flight at once and each warp can afford to wait for its own L2 round trip.  Within a K block lane l
+            // takes sub-block l & 3 of token rows (l >> 2) + 8 i: four lanes read one row's 256 contiguous bytes.  Codes go
+            // straight into the 128B-swizzled K-major X tile the MMA reads (16-byte chunk c of row t at chunk c ^ (t & 7)),
+            // the scale byte into the tcgen05.cp chunk layout.
+            const int qw = warp - 4;
             const bool hw_exact = (p.x_flags & MXQ_FLAG_HW_EXACT) != 0;
+            const int j = lane & 3;
             if (p.pdl) pdl_wait();  // the activation is written by the preceding kernel of the stream
-            uint32_t cur[NB][16], nxt[NB][16];
-            auto load = [&](int kb, uint32_t (&dst)[NB][16]) {
-#pragma unroll
-                for (int i = 0; i < NB; ++i) {
-                    const int b = tid + 128 * i, t = b >> 2, j = b & 3;
-                    if (b < N_TOK * 4 && t < p.M) {
-                        const uint4* src = reinterpret_cast<const uint4*>(p.x_hp + (int64_t)t * p.ldx + (int64_t)(kb0 + kb) * BLOCK_K + j * 32);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 v = src[q];
-                            dst[i][4 * q] = v.x; dst[i][4 * q + 1] = v.y; dst[i][4 * q + 2] = v.z; dst[i][4 * q + 3] = v.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) dst[i][q] = 0;
-                    }
-                }
-            };
-            uint32_t stage = 0, phase = 0, sfs = 0, sf_phase = 0, sf_j = 0;
-            load(0, cur);
-            for (int kb = 0; kb < k_blocks; ++kb) {
-                if (kb + 1 < k_blocks) load(kb + 1, nxt);
-                if (sf_j == 0) mbar_wait(&sf_empty[sfs], sf_phase ^ 1);
-                mbar_wait(&empty[stage], phase ^ 1);
+            const int n_groups = (k_blocks + SF_KB - 1) / SF_KB;
+            uint32_t sfs = 0, sf_phase = 0;
+            for (int g = 0; g < n_groups; ++g) {
+                const int kb = g * SF_KB + qw;
+                const bool live = kb < k_blocks;
+                const uint32_t stage = (uint32_t)(kb % STAGES), par = (uint32_t)((kb / STAGES) & 1);
                 uint8_t* xt = smem + L::OFF_X + stage * L::X_STAGE;
-                uint8_t* sfx = smem + L::OFF_SFX + sfs * L::SF_STAGE + sf_j * SF_KB_BYTES;
+                uint8_t* sfx = smem + L::OFF_SFX + sfs * L::SF_STAGE + qw * SF_KB_BYTES;
+                mbar_wait(&sf_empty[sfs], sf_phase ^ 1);
+#pragma unroll 1
+                for (int half = 0; half < N_TOK / 32; ++half) {
+                    uint32_t w[4][16];
 #pragma unroll
-                for (int i = 0; i < NB; ++i) {
-                    const int b = tid + 128 * i, t = b >> 2, j = b & 3;
-                    if (b < N_TOK * 4) {
-                        uint32_t out[8];
-                        const int s = quantize_block32<MXQ_ELEM_E4M3>(cur[i], hw_exact, out);
-                        *reinterpret_cast<uint4*>(xt + t * 128 + (((2 * j) ^ (t & 7)) << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
-                        *reinterpret_cast<uint4*>(xt + t * 128 + (((2 * j + 1) ^ (t & 7)) << 4)) = make_uint4(out[4], out[5], out[6], out[7]);
-                        sfx[(t & 31) * 16 + (t >> 5) * 4 + j] = (uint8_t)s;
+                    for (int i = 0; i < 4; ++i) {
+                        const int t = half * 32 + (lane >> 2) + 8 * i;
+                        if (live && t < p.M) {
+                            const uint4* src = reinterpret_cast<const uint4*>(p.x_hp + (int64_t)t * p.ldx + (int64_t)(kb0 + kb) * BLOCK_K + j * 32);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 v = src[q];
+                                w[i][4 * q] = v.x; w[i][4 * q + 1] = v.y; w[i][4 * q + 2] = v.z; w[i][4 * q + 3] = v.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) w[i][q] = 0;
+                        }
+                    }
+                    if (live && half == 0) mbar_wait(&empty[stage], par ^ 1);  // the loads above are already in flight
+                    if (live) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int t = half * 32 + (lane >> 2) + 8 * i;
+                            uint32_t out[8];
+                            const int sc = quantize_block32<MXQ_ELEM_E4M3>(w[i], hw_exact, out);
+                            *reinterpret_cast<uint4*>(xt + t * 128 + (((2 * j) ^ (t & 7)) << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
+                            *reinterpret_cast<uint4*>(xt + t * 128 + (((2 * j + 1) ^ (t & 7)) << 4)) = make_uint4(out[4], out[5], out[6], out[7]);
+                            sfx[(t & 31) * 16 + (t >> 5) * 4 + j] = (uint8_t)sc;
+                        }
                     }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                const bool sf_done = sf_j == SF_KB - 1 || kb == k_blocks - 1;
                 if (lane == 0) {
-                    mbar_arrive(&full[stage]);
-                    if (sf_done) mbar_arrive(&sf_full[sfs]);
+                    if (live) mbar_arrive(&full[stage]);
+                    mbar_arrive(&sf_full[sfs]);  // every quantizer warp reports for every group, with or without a K block in it
                 }
-                if (sf_done) {
-                    sf_j = 0;
-                    if (++sfs == SF_STAGES) { sfs = 0; sf_phase ^= 1; }
-                } else {
-                    ++sf_j;
-                }
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-#pragma unroll
-                for (int i = 0; i < NB; ++i)
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) cur[i][q] = nxt[i][q];
+                if (++sfs == SF_STAGES) { sfs = 0; sf_phase ^= 1; }
             }
         }
         // ================= epilogue, part 1: accumulator -> global (S == 1) or -> partial-sum buffer (S > 1) =================
