@@ -8,9 +8,13 @@ import sys
 
 import torchmx_b200 as _impl
 
-_ALIASES = ("dtypes", "env_variables", "config", "utils", "mx_tensor", "ops", "mx_gemm", "quant_api", "layers", "layers.mx_linear")
+_ALIASES = ("dtypes", "env_variables", "config", "utils", "mx_tensor", "ops", "mx_gemm", "quant_api", "layers", "layers.mx_linear", "layers.mx_llama_attention", "layers.tp_linear")
 for _name in _ALIASES:
-    sys.modules[f"{__name__}.{_name}"] = importlib.import_module(f"torchmx_b200.{_name}")
+    try:
+        sys.modules[f"{__name__}.{_name}"] = importlib.import_module(f"torchmx_b200.{_name}")
+    except ImportError:  # the attention blocks need `transformers`; everything else does not
+        if _name != "layers.mx_llama_attention":
+            raise
 
 from torchmx_b200 import MXTensor, config, dtypes, env_variables, mx_tensor, ops, utils  # noqa: E402,F401
 from torchmx_b200 import layers, quant_api  # noqa: E402,F401

@@ -1,0 +1,151 @@
+"""MX inference versions of the Llama (and Qwen2) attention / MLP blocks for `quantize_llm_`
+(reference: /root/reference/torchmx/layers/mx_llama_attention.py:19-262, mx_qwen2_attention.py), written against the
+attention interface of the installed transformers (5.x: `forward(hidden_states, position_embeddings, attention_mask,
+past_key_values, **kwargs) -> (attn_output, attn_weights)`), not the 4.44 internals the reference subclasses.
+
+* the four projections (and the three MLP linears) become `MXInferenceLinear` (K1 + K3, or the fused decode kernel);
+* with a full `QAttentionConfig` (query / key / value / attention-weights configs) the attention itself runs on MX operands
+  exactly as the reference spells it out (:195-243): Q and K are quantized along head_dim, V along the key/value sequence
+  (quantize the transpose, transpose back), scores = Q_mx @ K_mx^T * scaling (+ mask), softmax in fp32, P quantized along
+  the key/value sequence, out = P_mx @ V_mx -- both contractions reach the tcgen05 block-scaled bmm when the blocked
+  extents are multiples of 128 (otherwise the dequantize path, like the reference);
+* without it the module keeps the model's configured attention function (sdpa / flash / eager) on the rotated bf16 Q, K, V.
+The KV cache stays in high precision (reference :186-187).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from ..config import QAttentionConfig, QLinearConfig
+from ..mx_tensor import MXTensor
+from .mx_linear import MXInferenceLinear
+
+
+def _swap_linears(dst: nn.Module, src: nn.Module, names, qconfig: QLinearConfig) -> None:
+    for n in names:
+        setattr(dst, n, MXInferenceLinear.from_float(getattr(src, n), qconfig))
+
+
+def _shell_like(cls, mod: nn.Module, skip=()) -> nn.Module:
+    """An instance of `cls` that shares every attribute / submodule of `mod` except the ones in `skip` -- the same result as
+    the reference's 'construct on meta, then overwrite the projections', without re-running the HF constructor."""
+    new = cls.__new__(cls)
+    nn.Module.__init__(new)
+    for k, v in mod.__dict__.items():
+        if k in ("_modules", "_parameters", "_buffers"):
+            continue
+        new.__dict__[k] = v
+    for k, v in mod._parameters.items():
+        new._parameters[k] = v
+    for k, v in mod._buffers.items():
+        new._buffers[k] = v
+    for k, v in mod._modules.items():
+        if k not in skip:
+            new._modules[k] = v
+    return new
+
+
+class _MXMLPMixin:
+    @classmethod
+    @torch.no_grad()
+    def from_float(cls, mod: nn.Module, qconfig: QLinearConfig):
+        assert isinstance(mod, cls.__mro__[2]), f"mod must be an instance of {cls.__mro__[2].__name__}, but got {type(mod)}"
+        new = _shell_like(cls, mod, skip=("gate_proj", "up_proj", "down_proj"))
+        new.qconfig = qconfig
+        _swap_linears(new, mod, ("gate_proj", "up_proj", "down_proj"), qconfig)
+        return new
+
+
+class _MXAttentionMixin:
+    @classmethod
+    @torch.no_grad()
+    def from_float(cls, mod: nn.Module, qconfig: QAttentionConfig):
+        assert isinstance(mod, cls.__mro__[2]), f"mod must be an instance of {cls.__mro__[2].__name__}, but got {type(mod)}"
+        new = _shell_like(cls, mod, skip=("q_proj", "k_proj", "v_proj", "o_proj"))
+        new.qconfig = qconfig
+        _swap_linears(new, mod, ("q_proj", "k_proj", "v_proj", "o_proj"), qconfig.projection_config)
+        return new
+
+    def extra_repr(self) -> str:
+        return ", ".join(s for s in (super().extra_repr(), f"qconfig={self.qconfig}") if s)
+
+    def _mx_attention(self, query_states, key_states, value_states, attention_mask, scaling: float) -> torch.Tensor:
+        """reference :195-243; inputs [bs, heads, len, head_dim] after rotary / cache update -> [bs, q_len, heads, head_dim]"""
+        from transformers.models.llama.modeling_llama import repeat_kv
+        qc = self.qconfig
+        key_states = repeat_kv(key_states, self.num_key_value_groups)
+        value_states = repeat_kv(value_states, self.num_key_value_groups)
+        dtype = query_states.dtype
+        q_mx = MXTensor.to_mx(query_states.contiguous(), qc.query_config.elem_dtype, qc.query_config.block_size)
+        k_mx = MXTensor.to_mx(key_states.contiguous(), qc.key_config.elem_dtype, qc.key_config.block_size)
+        v_mx = MXTensor.to_mx(value_states.transpose(2, 3).contiguous(), qc.value_config.elem_dtype, qc.value_config.block_size).transpose(2, 3)
+        attn_weights = torch.matmul(q_mx, k_mx.transpose(2, 3)) * scaling
+        if attention_mask is not None:
+            attn_weights = attn_weights + attention_mask[:, :, :, : key_states.shape[-2]]
+        attn_weights = nn.functional.softmax(attn_weights, dim=-1, dtype=torch.float32).to(dtype)
+        if self.training and getattr(self, "attention_dropout", 0.0):
+            attn_weights = nn.functional.dropout(attn_weights, p=self.attention_dropout, training=True)
+        p_mx = MXTensor.to_mx(attn_weights, qc.attention_weights_config.elem_dtype, qc.attention_weights_config.block_size)
+        attn_output = torch.matmul(p_mx, v_mx)
+        return attn_output.transpose(1, 2).contiguous()
+
+    def forward(self, hidden_states: torch.Tensor, position_embeddings: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                attention_mask: Optional[torch.Tensor] = None, past_key_values=None, **kwargs):
+        mod_llama = self._hf_module()
+        input_shape = hidden_states.shape[:-1]
+        hidden_shape = (*input_shape, -1, self.head_dim)
+        query_states = self.q_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        key_states = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        value_states = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        cos, sin = position_embeddings
+        query_states, key_states = mod_llama.apply_rotary_pos_emb(query_states, key_states, cos, sin)
+        if past_key_values is not None:
+            key_states, value_states = past_key_values.update(key_states, value_states, self.layer_idx)
+        if self.qconfig.is_qkv_quantization_enabled:
+            attn_output, attn_weights = self._mx_attention(query_states, key_states, value_states, attention_mask, self.scaling), None
+        else:
+            fn = mod_llama.eager_attention_forward
+            impl = getattr(self.config, "_attn_implementation", "eager")
+            if impl != "eager":
+                fn = mod_llama.ALL_ATTENTION_FUNCTIONS.get_interface(impl, fn) if hasattr(mod_llama.ALL_ATTENTION_FUNCTIONS, "get_interface") \
+                    else mod_llama.ALL_ATTENTION_FUNCTIONS[impl]
+            attn_output, attn_weights = fn(self, query_states, key_states, value_states, attention_mask,
+                                           dropout=0.0 if not self.training else self.attention_dropout, scaling=self.scaling, **kwargs)
+        attn_output = attn_output.reshape(*input_shape, -1).contiguous()
+        return self.o_proj(attn_output), attn_weights
+
+
+def _make_classes():
+    from transformers.models.llama import modeling_llama as ml
+    from transformers.models.qwen2 import modeling_qwen2 as mq
+
+    class MXInferenceLlamaMLP(_MXMLPMixin, ml.LlamaMLP):
+        """The MX inference version of LlamaMLP (reference: mx_llama_attention.py:19-59)."""
+
+    class MXInferenceLlamaAttention(_MXAttentionMixin, ml.LlamaAttention):
+        """The MX inference version of LlamaAttention (reference: mx_llama_attention.py:62-262)."""
+
+        @staticmethod
+        def _hf_module():
+            return ml
+
+    class MXInferenceQwen2MLP(_MXMLPMixin, mq.Qwen2MLP):
+        """The MX inference version of Qwen2MLP (reference: mx_qwen2_attention.py)."""
+
+    class MXInferenceQwen2Attention(_MXAttentionMixin, mq.Qwen2Attention):
+        """The MX inference version of Qwen2Attention (reference: mx_qwen2_attention.py); sliding-window layers keep the
+        model's configured attention function unless every layer uses full attention."""
+
+        @staticmethod
+        def _hf_module():
+            return mq
+
+    return ml, mq, MXInferenceLlamaMLP, MXInferenceLlamaAttention, MXInferenceQwen2MLP, MXInferenceQwen2Attention
+
+
+_ml, _mq, MXInferenceLlamaMLP, MXInferenceLlamaAttention, MXInferenceQwen2MLP, MXInferenceQwen2Attention = _make_classes()
+ATTENTION_LAYERS = {_ml.LlamaAttention: MXInferenceLlamaAttention, _mq.Qwen2Attention: MXInferenceQwen2Attention}
+MLP_LAYERS = {_ml.LlamaMLP: MXInferenceLlamaMLP, _mq.Qwen2MLP: MXInferenceQwen2MLP}

@@ -1,9 +1,10 @@
 """Model surgery: swap nn.Linear for MXInferenceLinear in place
 (reference: /root/reference/torchmx/quant_api.py:161-215).
 
-`quantize_llm_` / the torchao tensor-subclass inserter of the reference depend on
-transformers==4.44 attention internals and on torchao; they are outside the hot-path scope
- and are not provided.
+`quantize_llm_` (reference: quant_api.py:218-271) swaps the attention and MLP blocks of Llama / Qwen2 models for their MX
+versions (`layers/mx_llama_attention.py`, written against the installed transformers' attention interface) and then every
+remaining nn.Linear.  The torchao tensor-subclass inserter of the reference (quant_api.py:96-147) depends on torchao and is
+not provided.
 """
 from __future__ import annotations
 
@@ -12,7 +13,7 @@ from typing import Callable, Optional
 
 import torch
 
-from .config import QLinearConfig
+from .config import QAttentionConfig, QLinearConfig
 from .layers.mx_linear import MXInferenceLinear
 from .utils import get_logger
 
@@ -58,3 +59,23 @@ def quantize_linear_(model: torch.nn.Module, qconfig: QLinearConfig, layer_filte
     )
     if bar is not None:
         bar.close()
+
+
+def quantize_llm_(model: torch.nn.Module, qattention_config: QAttentionConfig, qmlp_config: QLinearConfig) -> None:
+    """Quantize an LLM in place: every Llama / Qwen2 attention block becomes its MX version with `qattention_config`
+    (projections as MXInferenceLinear; Q / K / V / attention-weights quantization when all four configs are given), every
+    MLP block its MX version with `qmlp_config`, and whatever nn.Linear is left (lm_head) an MXInferenceLinear with
+    `qmlp_config` (reference: quant_api.py:218-271)."""
+    from .layers.mx_llama_attention import ATTENTION_LAYERS, MLP_LAYERS
+    logger.info("Quantizing the model by swapping the Attention and MLP layers")
+    logger.info(f"Attention Layer Quantization config:\n{pformat(qattention_config)}\n")
+    logger.info(f"MLP Layer Quantization config:\n{pformat(qmlp_config)}\n")
+    table = dict(ATTENTION_LAYERS)
+    table.update(MLP_LAYERS)
+
+    def replace(mod):
+        cls = table[type(mod)]
+        return cls.from_float(mod, qattention_config if type(mod) in ATTENTION_LAYERS else qmlp_config)
+
+    _swap_children(model, replacement_fn=replace, filter_fn=lambda mod, fqn: type(mod) in table)
+    quantize_linear_(model, qmlp_config)
