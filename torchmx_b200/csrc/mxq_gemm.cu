@@ -233,12 +233,12 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
 // tcgen05.commit.
 namespace pair {
 constexpr int TILE_M = 256, TILE_N = 256;
-constexpr int kThreads = 256;
 constexpr uint32_t ACC_SLOT1 = 192;
 constexpr uint32_t TM_SF = 448, SF_BUF_COLS = 12;
-constexpr int kEpilogueWarps = 4;
 
-template <int STAGES>
+// EW = epilogue warps: 4 (one per TMEM lane quadrant; large K, the mainloop hides the epilogue) or 8 (quadrant x column half;
+// small K, where the single-warp-per-SMSP latency chain TMEM -> bf16 -> staging of a 64 KB output tile bounds the kernel)
+template <int STAGES, int EW>
 struct Smem {
     static constexpr int A_STAGE = 128 * BLOCK_K;  // 16 KB
     static constexpr int B_STAGE = 128 * BLOCK_K;  // 16 KB: this CTA's half of the 256 B rows
@@ -250,18 +250,18 @@ struct Smem {
     static constexpr int OFF_SFB = OFF_SFA + SF_STAGES * SFA_STAGE;
     static constexpr int EPI_WARP = 2 * 4096;  // per epilogue warp: two buffers of 32 rows x 64 bf16 columns (128B-swizzled rows)
     static constexpr int OFF_EPI = OFF_SFB + SF_STAGES * SFB_STAGE;
-    static constexpr int OFF_BAR = OFF_EPI + kEpilogueWarps * EPI_WARP;
+    static constexpr int OFF_BAR = OFF_EPI + EW * EPI_WARP;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * SF_STAGES + 2;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM_PTR + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int STAGES, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
     mx_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_d,
                         const Params p, const int group_m, const int tma_store) {
-    using L = Smem<STAGES>;
+    using L = Smem<STAGES, EW>;
     extern __shared__ uint8_t smem_raw[];
     // the dynamic shared window starts at the same offset in both CTAs, so the aligned carve-up matches too
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -297,7 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             mbar_init(&sf_empty[i], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 2 * kEpilogueWarps);
+        mbar_init(tmem_empty, 2 * EW);
         fence_barrier_init();
     }
     __syncwarp();
@@ -444,16 +444,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
                 // group (32 rows x 128 B; rows / columns past the matrix edge are clipped by the tensor map).  Direct
                 // 16-byte st.global from one row per lane costs 32 partial-sector L2 writes per instruction and was
                 // measured to stall the TMA loads of the next tile.
-                uint8_t* ebuf = smem + L::OFF_EPI + quad * L::EPI_WARP;
-                const int first_g = slot ? 0 : 3;  // the 64-column group inside [192,256) of TMEM comes first
+                uint8_t* ebuf = smem + L::OFF_EPI + (warp - 4) * L::EPI_WARP;
+                // The two accumulator slots share TMEM columns [192,256): 64-column group 3 of slot 0, group 0 of slot 1.  With
+                // four warps each drains all four groups, the shared one first; with eight, warp (quadrant, half) drains the two
+                // groups of its column half -- the half that holds the shared group takes it first, the other half never touches
+                // shared columns and hands the slot over at once.
+                constexpr int GROUPS_PER_WARP = 16 / EW;
+                const int half = (warp - 4) >> 2;
+                const bool owns = EW == 4 || (slot ? half == 0 : half == 1);
+                const int first_g = EW == 4 ? (slot ? 0 : 3) : (owns ? (slot ? 0 : 3) : 2 * half);
+                const int step_g = (EW == 8 && owns && !slot) ? -1 : 1;  // (3, 2) for the owning half of slot 0
+                if (!owns) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+                }
 #pragma unroll 1
-                for (int h = 0; h < 4; ++h) {
-                    const int g = (first_g + h) & 3;
+                for (int h = 0; h < GROUPS_PER_WARP; ++h) {
+                    const int g = (first_g + step_g * h) & 3;
                     uint32_t v0[32], v1[32];
                     tmem_ld_32x32b_x32(tmem_acc + g * 64, v0);
                     tmem_ld_32x32b_x32(tmem_acc + g * 64 + 32, v1);
                     tmem_ld_wait();
-                    if (h == 0) {  // the columns shared with the other slot are in registers: the next tile's MMAs may start
+                    if (h == 0 && owns) {  // the columns shared with the other slot are in registers: the next tile's MMAs may start
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
@@ -611,12 +624,12 @@ static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUt
 }
 
 
-template <int STAGES>
+template <int STAGES, int EW>
 static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t stream, char* msg,
                        size_t msg_len) {
-    using L = pair::Smem<STAGES>;
+    using L = pair::Smem<STAGES, EW>;
     {
-        const cudaError_t e = cudaFuncSetAttribute(pair::mx_gemm_pair_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+        const cudaError_t e = cudaFuncSetAttribute(pair::mx_gemm_pair_kernel<STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     }
     Params p;
@@ -649,7 +662,8 @@ static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CU
         md = ma;
     } else if (tma_store && !make_d_map(&md, a->d, a->N, a->M, a->batch, a->ldd, a->d_batch_stride)) tma_store = 0;
     if (!tma_store) md = ma;  // unused placeholder
-    pair::mx_gemm_pair_kernel<STAGES><<<2 * pairs, pair::kThreads, L::DYN_BYTES, stream>>>(ma, mb, md, p, group_m, tma_store);
+    if (EW == 8 && !tma_store) return MXQ_ERR_UNSUPPORTED_SHAPE;  // the eight-warp epilogue exists for the staged path only (caller retries with EW = 4)
+    pair::mx_gemm_pair_kernel<STAGES, EW><<<2 * pairs, 128 + 32 * EW, L::DYN_BYTES, stream>>>(ma, mb, md, p, group_m, tma_store);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (pair): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;
@@ -703,8 +717,15 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
             snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
             return MXQ_ERR_UNSUPPORTED_SHAPE;
         }
-        if (cfg == 24) return launch_pair<4>(a, ma, mb, sm_count, stream, msg, msg_len);
-        return launch_pair<5>(a, ma, mb, sm_count, stream, msg, msg_len);
+        if (cfg == 24) return launch_pair<4, 4>(a, ma, mb, sm_count, stream, msg, msg_len);
+        // short K loops are bound by the epilogue (a 64 KB output tile per CTA for a few hundred MMA cycles): eight
+        // epilogue warps and a shallower operand ring; long K loops hide the epilogue and want the deeper ring
+        const int ew8_max_kb = getenv("MXQ_GEMM_EW8_KB") ? atoi(getenv("MXQ_GEMM_EW8_KB")) : 2;  // measured: helps at K = 128 (Q@K^T: 85 -> 79 us), hurts at K = 1024
+        if (a->K / BLOCK_K <= ew8_max_kb && cfg != 25) {
+            const int rc = launch_pair<3, 8>(a, ma, mb, sm_count, stream, msg, msg_len);
+            if (rc != MXQ_ERR_UNSUPPORTED_SHAPE) return rc;
+        }
+        return launch_pair<5, 4>(a, ma, mb, sm_count, stream, msg, msg_len);
     }
     if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M, a->a_format) ||
         !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128, a->b_format)) {
