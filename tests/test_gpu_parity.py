@@ -233,3 +233,44 @@ def test_full_size_properties(mx, oracle, elem):
     assert torch.equal(y32.to(torch.bfloat16), y)
     del y32, y, m, m2, x
     torch.cuda.empty_cache()
+
+
+def test_ops_are_cuda_graph_capturable_and_stream_correct():
+    """quantize / dequantize / MX linear enqueue on the CURRENT stream and never synchronise: they can be captured into a
+    CUDA graph (what an inference server does with a decode step) and replayed on new data with identical results."""
+    import torchmx_b200  # noqa: F401
+    from torchmx_b200 import dtypes
+    from torchmx_b200.config import MXConfig, QLinearConfig
+    from torchmx_b200.layers.mx_linear import MXInferenceLinear
+    from torchmx_b200.mx_tensor import MXTensor
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(512, 384, bias=True).to(dev, torch.bfloat16)
+    layer = MXInferenceLinear.from_float(lin, QLinearConfig(weights_config=MXConfig("float6_e3m2", 32), activations_config=MXConfig("float8_e4m3", 32)))
+    x = torch.randn(16, 512, device=dev, dtype=torch.bfloat16)
+    xl = torch.randn(200, 512, device=dev, dtype=torch.bfloat16)
+
+    def work():
+        m = MXTensor.to_mx(x, dtypes.float4_e2m1, 32)
+        return m.to_dtype(torch.bfloat16), layer(x), layer(xl)   # decode-sized (fused quantize) and prefill-sized linears
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        for _ in range(2):
+            work()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.graph(g):
+        outs = work()
+    for trial in range(2):
+        x.copy_(torch.randn(16, 512, device=dev, dtype=torch.bfloat16))
+        xl.copy_(torch.randn(200, 512, device=dev, dtype=torch.bfloat16))
+        g.replay()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            want = work()
+        torch.cuda.synchronize()
+        for a, b in zip(outs, want):
+            assert torch.equal(a, b), trial

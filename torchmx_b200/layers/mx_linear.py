@@ -17,33 +17,6 @@ from ..config import QLinearConfig
 from ..mx_tensor import MXTensor
 
 
-# q/k/v (and gate/up) projections of a decoder layer quantize the SAME activation tensor with the same config; the
-# reference quantizes it once per layer (mx_linear.py:63-66), i.e. three (two) times.  One entry is remembered: if the next
-# layer is handed the very same tensor (object identity, storage pointer, geometry and version counter all equal) the MX
-# tensor is reused -- bit-identical by construction, one K1 launch instead of three.  The entry keeps `x` alive, so its
-# storage cannot be recycled under the key; MXQ_ACT_REUSE=0 turns it off.
-_ACT_REUSE = os.environ.get("MXQ_ACT_REUSE", "1") != "0"
-_last_act = None
-
-
-def _quantize_activation(x: torch.Tensor, elem_dtype, block_size: int) -> MXTensor:
-    global _last_act
-    if not _ACT_REUSE or type(x) is not torch.Tensor:
-        return MXTensor.to_mx(x, elem_dtype, block_size)
-    key = (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()), x.dtype, elem_dtype.name, block_size)
-    hit = _last_act
-    if hit is not None and hit[0] is x and hit[1] == key:
-        return hit[2]
-    x_mx = MXTensor.to_mx(x, elem_dtype, block_size)
-    _last_act = (x, key, x_mx)
-    return x_mx
-
-
-def clear_activation_cache() -> None:
-    global _last_act
-    _last_act = None
-
-
 class MXInferenceLinear(torch.nn.Linear):
     def extra_repr(self) -> str:
         return f"{super().extra_repr()}, qconfig={self.qconfig}"
@@ -82,10 +55,29 @@ class MXInferenceLinear(torch.nn.Linear):
         wc = self.qconfig.weights_config
         return MXTensor.to_mx(w.to(torch.bfloat16), wc.elem_dtype, wc.block_size)
 
+    def prepare_input(self, x: torch.Tensor):
+        """Quantize an activation that SEVERAL layers with this layer's activation config will consume (q/k/v, gate/up): the
+        reference quantizes it once per layer (mx_linear.py:63-66); a block that owns its projections can quantize it once
+        and hand the MXTensor to each of them.  Decode-sized inputs are returned as they are -- for those every layer fuses
+        the quantization into its GEMM, which is cheaper than a separate launch."""
+        ac = self.qconfig.activations_config
+        rows = x.numel() // x.shape[-1] if x.dim() else 0
+        if isinstance(x, MXTensor) or (mx_gemm._FUSED_ACT and ac.elem_dtype_name == "float8_e4m3" and ac.block_size == 32
+                                        and rows <= mx_gemm.FUSED_ACT_MAX_ROWS):
+            return x
+        return MXTensor.to_mx(x, ac.elem_dtype, ac.block_size)
+
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         ac = self.qconfig.activations_config
         bias = self.bias
+        if isinstance(x, MXTensor):  # already quantized by the owning block (prepare_input)
+            assert x._elem_dtype == ac.elem_dtype and x._block_size == ac.block_size, "activation was quantized with another config"
+            if not isinstance(self.weight, MXTensor) and bias is not None:
+                bias = bias.to(torch.bfloat16)
+            w_mx = self._weight_mx()
+            out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x, w_mx, (), (bias,), count_fallback=False)
+            return out if out is not None else F.linear(x, w_mx, bias)
         if not isinstance(self.weight, MXTensor) and bias is not None:
             bias = bias.to(torch.bfloat16)
         w_mx = self._weight_mx()
@@ -94,7 +86,7 @@ class MXInferenceLinear(torch.nn.Linear):
             out = mx_gemm.linear_fused_act_quant(x, w_mx, bias, env.MX_EXACT_QUANTIZATION == "True")
             if out is not None:
                 return out
-        x_mx = _quantize_activation(x, ac.elem_dtype, ac.block_size)
+        x_mx = MXTensor.to_mx(x, ac.elem_dtype, ac.block_size)
         # F.linear(x_mx, w_mx, bias) reaches the same kernel through the dispatcher (aten.t + aten.mm / addmm on MXTensor
         # views, ~50 us of host time per layer); hand the operands to the tensor-core path directly when they qualify
         out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x_mx, w_mx, (), (bias,), count_fallback=False)

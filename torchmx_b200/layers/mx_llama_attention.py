@@ -58,6 +58,10 @@ class _MXMLPMixin:
         _swap_linears(new, mod, ("gate_proj", "up_proj", "down_proj"), qconfig)
         return new
 
+    def forward(self, x):
+        x_in = self.gate_proj.prepare_input(x)  # gate and up read the same activation: quantize it once
+        return self.down_proj(self.act_fn(self.gate_proj(x_in)) * self.up_proj(x_in))
+
 
 class _MXAttentionMixin:
     @classmethod
@@ -97,9 +101,10 @@ class _MXAttentionMixin:
         mod_llama = self._hf_module()
         input_shape = hidden_states.shape[:-1]
         hidden_shape = (*input_shape, -1, self.head_dim)
-        query_states = self.q_proj(hidden_states).view(hidden_shape).transpose(1, 2)
-        key_states = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
-        value_states = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        x_in = self.q_proj.prepare_input(hidden_states)  # one activation quantization for the three projections
+        query_states = self.q_proj(x_in).view(hidden_shape).transpose(1, 2)
+        key_states = self.k_proj(x_in).view(hidden_shape).transpose(1, 2)
+        value_states = self.v_proj(x_in).view(hidden_shape).transpose(1, 2)
         cos, sin = position_embeddings
         query_states, key_states = mod_llama.apply_rotary_pos_emb(query_states, key_states, cos, sin)
         if past_key_values is not None:

@@ -94,7 +94,10 @@ def _operand_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[MX
         out = torch.empty(tuple(src.shape[:-1]) + (k * _PACKED_BITS[fmt] // 8,), dtype=torch.uint8, device=src.device)
         rc = _C.lib().mxq_pack_operand(src.data_ptr(), dtypes.ELEM_ID[elem.name], n_elements, out.data_ptr(), src.device.index, _stream_ptr(src))
         _C.check(rc, "mxq_pack_operand")
-    if cache_on is not None:
+    # A shadow created while a CUDA graph is being captured lives in that graph's private memory pool (and its conversion
+    # kernel in the graph): it must not outlive the graph through this cache.  Warm a model up once before capturing it --
+    # the shadows then exist as ordinary tensors and the graph contains no conversion kernels.
+    if cache_on is not None and not torch.cuda.is_current_stream_capturing():
         cache_on.__dict__[_SHADOW_ATTR] = (key, out)
     return out, fmt
 
