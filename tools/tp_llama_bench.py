@@ -95,7 +95,7 @@ class TPDecoderLayer(torch.nn.Module):
     def forward(self, x, pos, kc, vc, cache_len, cs):
         # x: [B, T, hidden] replicated; kc/vc: [B, nkv_local, S, hd] this rank's KV cache; tokens are written at pos
         B, T, _ = x.shape
-        y = rms_norm(x, self.n1)
+        y = self.q.prepare_input(rms_norm(x, self.n1))  # one activation quantization for q / k / v (prefill); bf16 for decode
         q = self.q(y).view(B, T, self.nh_local, self.hd).transpose(1, 2)
         k = self.k(y).view(B, T, self.nkv_local, self.hd).transpose(1, 2)
         v = self.v(y).view(B, T, self.nkv_local, self.hd).transpose(1, 2)
@@ -108,7 +108,7 @@ class TPDecoderLayer(torch.nn.Module):
         else:      # decode: attend to the first cache_len + 1 cache positions
             a = F.scaled_dot_product_attention(q, kc[:, :, : cache_len + 1], vc[:, :, : cache_len + 1], enable_gqa=True)
         x = x + self.o(a.transpose(1, 2).reshape(B, T, self.nh_local * self.hd))
-        y = rms_norm(x, self.n2)
+        y = self.gate.prepare_input(rms_norm(x, self.n2))
         return x + self.down(F.silu(self.gate(y)) * self.up(y))
 
 
