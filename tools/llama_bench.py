@@ -26,7 +26,7 @@ SHAPES = {
 }
 
 
-def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: bool = True):
+def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: bool = True, llm_api: bool = False):
     from transformers import LlamaConfig, LlamaForCausalLM
 
     import torchmx_b200  # noqa: F401
@@ -55,7 +55,12 @@ def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: boo
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        quantize_linear_(model, qc)
+        if llm_api:  # attention / MLP blocks swapped for their MX versions (projection quantization only), then lm_head
+            from torchmx_b200.config import QAttentionConfig
+            from torchmx_b200.quant_api import quantize_llm_
+            quantize_llm_(model, QAttentionConfig(projection_config=qc), qc)
+        else:
+            quantize_linear_(model, qc)
         e1.record()
         torch.cuda.synchronize()
         info["quantize_wall_s"] = time.perf_counter() - t0
@@ -104,8 +109,8 @@ def capture(fn):
 def run(args) -> dict:
     from transformers.cache_utils import StaticCache
 
-    model, cfg, info = build(args.model, args.layers, args.wdtype, args.adtype, quantize=not args.no_quant)
-    res = {"model": args.model, "layers": cfg.num_hidden_layers, "weights": args.wdtype, "activations": args.adtype, **info}
+    model, cfg, info = build(args.model, args.layers, args.wdtype, args.adtype, quantize=not args.no_quant, llm_api=args.llm_api)
+    res = {"api": "none (bf16 HF)" if args.no_quant else ("quantize_llm_" if args.llm_api else "quantize_linear_"), "model": args.model, "layers": cfg.num_hidden_layers, "weights": args.wdtype, "activations": args.adtype, **info}
     dev = "cuda"
 
     # ---- prefill: one prompt of `prefill` tokens, fresh static cache each run -------------------------------
@@ -181,6 +186,7 @@ if __name__ == "__main__":
     ap.add_argument("--wdtype", default="float6_e3m2")
     ap.add_argument("--adtype", default="float8_e4m3")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--llm-api", action="store_true", help="quantize_llm_ (MX attention / MLP blocks) instead of quantize_linear_")
     ap.add_argument("--no-quant", action="store_true", help="plain bf16 HF model (context line, not the product)")
     a = ap.parse_args()
     print(json.dumps(run(a)), flush=True)
