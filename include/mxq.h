@@ -156,6 +156,7 @@ MXQ_API int mxq_gemm(const mxq_gemm_args_t *args, int device, void *stream);
 #define MXQ_OPERAND_E2M1_PACKED 1
 #define MXQ_OPERAND_E3M2_PACKED 2
 #define MXQ_OPERAND_E2M3_PACKED 3
+#define MXQ_OPERAND_E5M2_BYTES 4 /* one E5M2 byte per element (the float8_e5m2 extension element type) */
 
 /* reference-layout element codes (MXQ_ELEM_E3M2 / E2M3: one byte each; MXQ_ELEM_E2M1: packed, even element high) ->
  * the packed operand format above for that element type; n elements in, n*bits/8 bytes out.  Exact (a permutation of

@@ -66,6 +66,10 @@ CASES = [
     (128, 7168, 1024, "float8_e4m3", "float6_e3m2", False, 0, 0),
     (5, 2048, 7168, "float8_e4m3", "float6_e3m2", True, 0, 0),
     (8, 640, 384, "float8_e4m3", "float8_e4m3", False, 0, 0),
+    # float8_e5m2 (labelled extension element type) as a native one-byte operand, all three kernels
+    (300, 520, 640, "float8_e5m2", "float6_e3m2", True, 0, 10),
+    (48, 1000, 512, "float8_e4m3", "float8_e5m2", False, 0, 0),
+    (96, 200, 256, "float8_e5m2", "float8_e5m2", False, 2, 0),
 ]
 
 
@@ -82,8 +86,8 @@ def test_tensor_core_matmul(mx, M, N, K, ea, eb, bias, batch, spread):
         for t in (a, b):
             e = torch.randint(-spread, spread, (*t.shape[:-1], K // 32), device=DEV, generator=g).float()
             t *= torch.exp2(e).repeat_interleave(32, -1).to(torch.bfloat16)
-    A = MXTensor.to_mx(a, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[ea], 32)
-    B = MXTensor.to_mx(b, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[eb], 32)
+    A = MXTensor.to_mx(a, dtypes.STR_TO_ELEM_DTYPE[ea], 32)
+    B = MXTensor.to_mx(b, dtypes.STR_TO_ELEM_DTYPE[eb], 32)
     bias_t = torch.randn(N, device=DEV, dtype=torch.bfloat16, generator=g) if bias else None
     before = dict(mx_gemm.stats)
     if batch:

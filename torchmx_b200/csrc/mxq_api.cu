@@ -162,7 +162,7 @@ int mxq_gemm(const mxq_gemm_args_t* a, int device, void* stream) {
     const bool xq = a->x_bf16 != nullptr;
     if ((!xq && (!a->a_codes || !a->sfa)) || !a->b_codes || !a->sfb || (!a->d && !a->d_multicast)) return fail(MXQ_ERR_INVALID, "mxq_gemm: null pointer");
     if (xq && (a->M > 64 || a->batch != 1)) return fail(MXQ_ERR_UNSUPPORTED_SHAPE, "mxq_gemm: fused activation quantization handles M <= 64, batch == 1");
-    if (a->a_format < 0 || a->a_format > MXQ_OPERAND_E2M3_PACKED || a->b_format < 0 || a->b_format > MXQ_OPERAND_E2M3_PACKED)
+    if (a->a_format < 0 || a->a_format > MXQ_OPERAND_E5M2_BYTES || a->b_format < 0 || a->b_format > MXQ_OPERAND_E5M2_BYTES)
         return fail(MXQ_ERR_INVALID, "mxq_gemm: unknown operand format %d / %d", a->a_format, a->b_format);
     DeviceScope scope(device);
     if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_gemm: selecting device");

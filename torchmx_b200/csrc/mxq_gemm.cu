@@ -684,7 +684,7 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
         const int fmt = side ? a->b_format : a->a_format;
         const int64_t ld = side ? a->ldb : a->lda, bs = side ? a->b_batch_stride : a->a_batch_stride;
         const uintptr_t base = (uintptr_t)(side ? a->b_codes : a->a_codes);
-        if (fmt != MXQ_OPERAND_E4M3_BYTES && ((ld % 32) || (bs % 32) || (base % 32))) {
+        if (fmt != MXQ_OPERAND_E4M3_BYTES && fmt != MXQ_OPERAND_E5M2_BYTES && ((ld % 32) || (bs % 32) || (base % 32))) {
             snprintf(msg, msg_len, "packed operands need 32-byte aligned pointers / strides");
             return MXQ_ERR_UNSUPPORTED_SHAPE;
         }

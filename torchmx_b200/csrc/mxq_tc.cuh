@@ -221,10 +221,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 // operand storage format (MXQ_OPERAND_*) -> element format field of the descriptor (a_format bits [7,10), b_format bits
 // [10,13)): E4M3 = 0, E2M3 = 3, E3M2 = 4, E2M1 = 5; and -> bits per element as TMA counts them in complete_tx
 __host__ __device__ constexpr uint32_t umma_format(int operand_format) {
-    return operand_format == MXQ_OPERAND_E2M1_PACKED ? 5u : (operand_format == MXQ_OPERAND_E3M2_PACKED ? 4u : (operand_format == MXQ_OPERAND_E2M3_PACKED ? 3u : 0u));
+    return operand_format == MXQ_OPERAND_E2M1_PACKED ? 5u
+           : (operand_format == MXQ_OPERAND_E3M2_PACKED ? 4u : (operand_format == MXQ_OPERAND_E2M3_PACKED ? 3u : (operand_format == MXQ_OPERAND_E5M2_BYTES ? 1u : 0u)));
 }
 __host__ __device__ constexpr int operand_bits(int operand_format) {
-    return operand_format == MXQ_OPERAND_E2M1_PACKED ? 4 : (operand_format == MXQ_OPERAND_E4M3_BYTES ? 8 : 6);
+    return operand_format == MXQ_OPERAND_E2M1_PACKED ? 4 : ((operand_format == MXQ_OPERAND_E4M3_BYTES || operand_format == MXQ_OPERAND_E5M2_BYTES) ? 8 : 6);
 }
 __host__ __device__ constexpr uint32_t idesc_formats(int a_format, int b_format) { return (umma_format(a_format) << 7) | (umma_format(b_format) << 10); }
 __device__ __forceinline__ uint32_t idesc_with_sf(uint32_t idesc, uint32_t sfa_id, uint32_t sfb_id) {
@@ -434,7 +435,7 @@ static inline bool make_operand_map(CUtensorMap* map, const void* base, int64_t 
                              int box_rows, int operand_format = MXQ_OPERAND_E4M3_BYTES) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
-    const CUtensorMapDataType dt = operand_format == MXQ_OPERAND_E4M3_BYTES ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+    const CUtensorMapDataType dt = (operand_format == MXQ_OPERAND_E4M3_BYTES || operand_format == MXQ_OPERAND_E5M2_BYTES) ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                    : (operand_format == MXQ_OPERAND_E2M1_PACKED ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_16U6_ALIGN16B);
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)(batch > 1 ? batch_stride : ld * rows)};

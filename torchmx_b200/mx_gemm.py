@@ -50,7 +50,7 @@ def set_enabled(flag: bool) -> None:
 
 
 # operand storage formats of mxq_gemm (include/mxq.h: MXQ_OPERAND_*)
-FMT_E4M3_BYTES, FMT_E2M1_PACKED, FMT_E3M2_PACKED, FMT_E2M3_PACKED = 0, 1, 2, 3
+FMT_E4M3_BYTES, FMT_E2M1_PACKED, FMT_E3M2_PACKED, FMT_E2M3_PACKED, FMT_E5M2_BYTES = 0, 1, 2, 3, 4
 _PACKED_FORMAT = {"float4_e2m1": FMT_E2M1_PACKED, "float6_e3m2": FMT_E3M2_PACKED, "float6_e2m3": FMT_E2M3_PACKED}
 _PACKED_BITS = {FMT_E2M1_PACKED: 4, FMT_E3M2_PACKED: 6, FMT_E2M3_PACKED: 6}
 # MXQ_PACKED_OPERANDS=0 keeps every fp6 / fp4 operand in the one-byte E4M3 container (the first implementation)
@@ -73,6 +73,8 @@ def _operand_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[MX
     counter of the codes, so a weight is converted once, not once per forward."""
     if elem == dtypes.float8_e4m3:
         return codes, FMT_E4M3_BYTES
+    if elem == dtypes.float8_e5m2:  # labelled extension element type: one byte per element, native MMA format
+        return codes, FMT_E5M2_BYTES
     fmt = _PACKED_FORMAT[elem.name] if _USE_PACKED else FMT_E4M3_BYTES
     key = None
     if cache_on is not None:
@@ -113,7 +115,7 @@ def _rows_k(t: MXTensor, k_dim_from_end: int):
 
 
 def _qualifies(t: MXTensor) -> bool:
-    return (isinstance(t, MXTensor) and t._elem_dtype in dtypes.SUPPORTED_FP_ELEM_DTYPES and t._block_size == 32 and t._padding == 0
+    return (isinstance(t, MXTensor) and (t._elem_dtype in dtypes.SUPPORTED_FP_ELEM_DTYPES or t._elem_dtype == dtypes.float8_e5m2) and t._block_size == 32 and t._padding == 0
             and t._data.is_cuda and t._orig_dtype == torch.bfloat16)
 
 
