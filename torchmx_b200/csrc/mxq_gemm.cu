@@ -238,7 +238,9 @@ constexpr uint32_t TM_SF = 448, SF_BUF_COLS = 12;
 
 // EW = epilogue warps: 4 (one per TMEM lane quadrant; large K, the mainloop hides the epilogue) or 8 (quadrant x column half;
 // small K, where the single-warp-per-SMSP latency chain TMEM -> bf16 -> staging of a 64 KB output tile bounds the kernel)
-template <int STAGES, int EW>
+// NBUF = staging buffers per epilogue warp: a TMA store takes ~1.4 k cycles from issue until it has read its 4 KB of shared
+// memory; with 2 buffers a warp waits ~600 cycles per 64-column group for its second-to-last store (measured by clock64 stamps)
+template <int STAGES, int EW, int NBUF>
 struct Smem {
     static constexpr int A_STAGE = 128 * BLOCK_K;  // 16 KB
     static constexpr int B_STAGE = 128 * BLOCK_K;  // 16 KB: this CTA's half of the 256 B rows
@@ -248,7 +250,7 @@ struct Smem {
     static constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
     static constexpr int OFF_SFA = OFF_B + STAGES * B_STAGE;
     static constexpr int OFF_SFB = OFF_SFA + SF_STAGES * SFA_STAGE;
-    static constexpr int EPI_WARP = 2 * 4096;  // per epilogue warp: two buffers of 32 rows x 64 bf16 columns (128B-swizzled rows)
+    static constexpr int EPI_WARP = NBUF * 4096;  // per epilogue warp: NBUF buffers of 32 rows x 64 bf16 columns (128B-swizzled rows)
     static constexpr int OFF_EPI = OFF_SFB + SF_STAGES * SFB_STAGE;
     static constexpr int OFF_BAR = OFF_EPI + EW * EPI_WARP;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * SF_STAGES + 2;
@@ -257,11 +259,11 @@ struct Smem {
     static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
-template <int STAGES, int EW>
+template <int STAGES, int EW, int NBUF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
     mx_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_d,
                         const Params p, const int group_m, const int tma_store) {
-    using L = Smem<STAGES, EW>;
+    using L = Smem<STAGES, EW, NBUF>;
     extern __shared__ uint8_t smem_raw[];
     // the dynamic shared window starts at the same offset in both CTAs, so the aligned carve-up matches too
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -473,23 +475,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
                         if (tracing) p.trace[tile_iter * 8 + 5] = clock64();
                     }
                     const int col0 = nb * TILE_N + g * 64;
-                    uint8_t* buf = ebuf + (h & 1) * 4096;
-                    if (p.d_mc == nullptr && lane == 0) tma_store_wait_read<1>();  // the store that last read this buffer (two groups ago) is done
+                    uint8_t* buf = ebuf + (NBUF == 2 ? (h & 1) : h) * 4096;  // NBUF == 4 goes with four groups per warp and tile
+                    if (p.d_mc == nullptr && lane == 0) tma_store_wait_read<NBUF - 1>();  // the store that last read this buffer (two groups ago) is done
                     __syncwarp();
                     uint32_t pk[32];
+                    // two separate loops: with the bias test inside one loop ptxas predicates the whole bias path (80 ISETP +
+                    // 320 predicated instructions per group) and the no-bias case pays ~600 issue cycles for nothing (measured)
+                    if (p.bias == nullptr) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float f0 = __uint_as_float(v0[2 * i]), f1 = __uint_as_float(v0[2 * i + 1]);
-                        float f2 = __uint_as_float(v1[2 * i]), f3 = __uint_as_float(v1[2 * i + 1]);
-                        if (p.bias != nullptr) {
+                        for (int i = 0; i < 16; ++i) {
+                            pk[i] = pack_bf16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+                            pk[16 + i] = pack_bf16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float f0 = __uint_as_float(v0[2 * i]), f1 = __uint_as_float(v0[2 * i + 1]);
+                            float f2 = __uint_as_float(v1[2 * i]), f3 = __uint_as_float(v1[2 * i + 1]);
                             const int c = col0 + 2 * i;
                             if (c < p.N) f0 += __uint_as_float((uint32_t)p.bias[c] << 16);
                             if (c + 1 < p.N) f1 += __uint_as_float((uint32_t)p.bias[c + 1] << 16);
                             if (c + 32 < p.N) f2 += __uint_as_float((uint32_t)p.bias[c + 32] << 16);
                             if (c + 33 < p.N) f3 += __uint_as_float((uint32_t)p.bias[c + 33] << 16);
+                            pk[i] = pack_bf16x2(f0, f1);
+                            pk[16 + i] = pack_bf16x2(f2, f3);
                         }
-                        pk[i] = pack_bf16x2(f0, f1);
-                        pk[16 + i] = pack_bf16x2(f2, f3);
                     }
                     // lane = row of the 32-row box; 16-byte chunk c of the row lives at chunk (c ^ (row & 7)) (SWIZZLE_128B)
 #pragma unroll
@@ -624,12 +634,12 @@ static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUt
 }
 
 
-template <int STAGES, int EW>
+template <int STAGES, int EW, int NBUF>
 static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t stream, char* msg,
                        size_t msg_len) {
-    using L = pair::Smem<STAGES, EW>;
+    using L = pair::Smem<STAGES, EW, NBUF>;
     {
-        const cudaError_t e = cudaFuncSetAttribute(pair::mx_gemm_pair_kernel<STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+        const cudaError_t e = cudaFuncSetAttribute(pair::mx_gemm_pair_kernel<STAGES, EW, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     }
     Params p;
@@ -663,7 +673,7 @@ static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CU
     } else if (tma_store && !make_d_map(&md, a->d, a->N, a->M, a->batch, a->ldd, a->d_batch_stride)) tma_store = 0;
     if (!tma_store) md = ma;  // unused placeholder
     if (EW == 8 && !tma_store) return MXQ_ERR_UNSUPPORTED_SHAPE;  // the eight-warp epilogue exists for the staged path only (caller retries with EW = 4)
-    pair::mx_gemm_pair_kernel<STAGES, EW><<<2 * pairs, 128 + 32 * EW, L::DYN_BYTES, stream>>>(ma, mb, md, p, group_m, tma_store);
+    pair::mx_gemm_pair_kernel<STAGES, EW, NBUF><<<2 * pairs, 128 + 32 * EW, L::DYN_BYTES, stream>>>(ma, mb, md, p, group_m, tma_store);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (pair): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;
@@ -717,15 +727,17 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
             snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
             return MXQ_ERR_UNSUPPORTED_SHAPE;
         }
-        if (cfg == 24) return launch_pair<4, 4>(a, ma, mb, sm_count, stream, msg, msg_len);
+        if (cfg == 24) return launch_pair<4, 4, 2>(a, ma, mb, sm_count, stream, msg, msg_len);
         // short K loops are bound by the epilogue (a 64 KB output tile per CTA for a few hundred MMA cycles): eight
         // epilogue warps and a shallower operand ring; long K loops hide the epilogue and want the deeper ring
+        const int ew8 = getenv("MXQ_GEMM_EW8") ? atoi(getenv("MXQ_GEMM_EW8")) : 0;  // small-K variant (3 stages): 0 = 4 epilogue warps x 2 buffers (best once the bias code was un-predicated), 1 = 8 warps, 2 = 4 warps x 4 buffers
         const int ew8_max_kb = getenv("MXQ_GEMM_EW8_KB") ? atoi(getenv("MXQ_GEMM_EW8_KB")) : 2;  // measured: helps at K = 128 (Q@K^T: 85 -> 79 us), hurts at K = 1024
         if (a->K / BLOCK_K <= ew8_max_kb && cfg != 25) {
-            const int rc = launch_pair<3, 8>(a, ma, mb, sm_count, stream, msg, msg_len);
+            const int rc = ew8 == 1 ? launch_pair<3, 8, 2>(a, ma, mb, sm_count, stream, msg, msg_len)
+                           : (ew8 == 2 ? launch_pair<3, 4, 4>(a, ma, mb, sm_count, stream, msg, msg_len) : launch_pair<3, 4, 2>(a, ma, mb, sm_count, stream, msg, msg_len));
             if (rc != MXQ_ERR_UNSUPPORTED_SHAPE) return rc;
         }
-        return launch_pair<5, 4>(a, ma, mb, sm_count, stream, msg, msg_len);
+        return launch_pair<5, 4, 2>(a, ma, mb, sm_count, stream, msg, msg_len);
     }
     if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M, a->a_format) ||
         !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128, a->b_format)) {
