@@ -19,6 +19,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
+FUSE_NORM = os.environ.get("LB_FUSE_NORM", "0") == "1"
+
 SHAPES = {
     "8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8, vocab_size=128256),
     "70b": dict(hidden_size=8192, intermediate_size=28672, num_hidden_layers=80, num_attention_heads=64, num_key_value_heads=8, vocab_size=128256),
@@ -58,7 +60,7 @@ def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: boo
         if llm_api:  # attention / MLP blocks swapped for their MX versions (projection quantization only), then lm_head
             from torchmx_b200.config import QAttentionConfig
             from torchmx_b200.quant_api import quantize_llm_
-            quantize_llm_(model, QAttentionConfig(projection_config=qc), qc)
+            quantize_llm_(model, QAttentionConfig(projection_config=qc), qc, fuse_rmsnorm=FUSE_NORM)
         else:
             quantize_linear_(model, qc)
         e1.record()

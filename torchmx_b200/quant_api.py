@@ -61,7 +61,23 @@ def quantize_linear_(model: torch.nn.Module, qconfig: QLinearConfig, layer_filte
         bar.close()
 
 
-def quantize_llm_(model: torch.nn.Module, qattention_config: QAttentionConfig, qmlp_config: QLinearConfig) -> None:
+class FusedRMSNorm(torch.nn.Module):
+    """Drop-in for the transformers `LlamaRMSNorm` / `Qwen2RMSNorm` module: same parameters, one fused `F.rms_norm` launch
+    (fp32 statistics inside) instead of the six elementwise / reduction launches of the eager module.  Not part of the
+    reference; `quantize_llm_(..., fuse_rmsnorm=True)` opts in."""
+
+    def __init__(self, weight: torch.nn.Parameter, eps: float):
+        super().__init__()
+        self.weight, self.variance_epsilon = weight, eps
+
+    def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        return torch.nn.functional.rms_norm(hidden_states, (hidden_states.shape[-1],), self.weight, self.variance_epsilon)
+
+    def extra_repr(self) -> str:
+        return f"{tuple(self.weight.shape)}, eps={self.variance_epsilon}"
+
+
+def quantize_llm_(model: torch.nn.Module, qattention_config: QAttentionConfig, qmlp_config: QLinearConfig, fuse_rmsnorm: bool = False) -> None:
     """Quantize an LLM in place: every Llama / Qwen2 attention block becomes its MX version with `qattention_config`
     (projections as MXInferenceLinear; Q / K / V / attention-weights quantization when all four configs are given), every
     MLP block its MX version with `qmlp_config`, and whatever nn.Linear is left (lm_head) an MXInferenceLinear with
@@ -79,3 +95,6 @@ def quantize_llm_(model: torch.nn.Module, qattention_config: QAttentionConfig, q
 
     _swap_children(model, replacement_fn=replace, filter_fn=lambda mod, fqn: type(mod) in table)
     quantize_linear_(model, qmlp_config)
+    if fuse_rmsnorm:
+        _swap_children(model, replacement_fn=lambda mod: FusedRMSNorm(mod.weight, mod.variance_epsilon),
+                       filter_fn=lambda mod, fqn: type(mod).__name__ in ("LlamaRMSNorm", "Qwen2RMSNorm"))
