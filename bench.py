@@ -395,7 +395,7 @@ def run_b200(args):
     e2e_value = world * step_bytes(n_elems) * e2e_steps / e2e_s / 1e9 if e2e_steps else 0.0
 
     extras = None
-    if rank == 0 and not args.skip_gemm:
+    if rank == 0 and not args.skip_gemm and world == 1:  # single-GPU numbers; under torchrun the other ranks would only wait
         del xs, xh, yhs, chs
         torch.cuda.empty_cache()
         extras = mx_matmul_extras(dev)
