@@ -266,18 +266,24 @@ def run_quantize(args, world, rank):
     # (cudaMalloc of fresh segments is synchronous, ~1 ms per GB, and is not what is being measured)
     out_bytes = (hi - lo) * sum(n * k for n, k in shapes) * ((0.5 if args.wdtype == "float4_e2m1" else 1.0) + 1 / 32)
     reserve = torch.empty(int(out_bytes * 1.15) + (256 << 20), dtype=torch.uint8, device="cuda")
-    del reserve
+    # scale tensors below 1 MiB come from the allocator's small pool (2 MiB segments): reserve those too
+    small = [n * k // 32 for n, k in shapes if n * k // 32 < (1 << 20)]
+    reserve_small = [torch.empty(sz, dtype=torch.uint8, device="cuda") for _ in range(hi - lo + 2) for sz in small]
+    del reserve, reserve_small
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_malloc0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(lo, hi):
         for m in srcs:
             kept.append(MXInferenceLinear.from_float(m, qc))
+    host_issue_s = time.perf_counter() - t0
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    n_malloc = torch.cuda.memory_stats().get("num_device_alloc", 0) - n_malloc0
     elems = (hi - lo) * sum(n * k for n, k in shapes)
     bpe = 2 + (0.5 if args.wdtype == "float4_e2m1" else 1.0) + 1 / 32
     t = torch.tensor([e0.elapsed_time(e1) * 1e-3, wall, float(elems)], device="cuda", dtype=torch.float64)
@@ -287,7 +293,7 @@ def run_quantize(args, world, rank):
     return {"mode": "quantize", "model": args.model, "layers": cfg["layers"], "world": world, "weights": args.wdtype,
             "weight_elements": int(t[2].item()), "gpu_s_max": round(float(tmax[0]), 4), "wall_s_max": round(float(tmax[1]), 4),
             "aggregate_GBps": round(float(t[2].item()) * bpe / float(tmax[0]) / 1e9, 1),
-            "linears_per_rank": (hi - lo) * len(shapes)}
+            "linears_per_rank": (hi - lo) * len(shapes), "host_issue_s_rank0": round(host_issue_s, 4), "cudaMalloc_calls_in_timed_region_rank0": n_malloc}
 
 
 def main():
