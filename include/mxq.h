@@ -168,6 +168,30 @@ MXQ_API int mxq_pack_operand(const void *codes, int elem, int64_t n_elements, vo
 MXQ_API int mxq_transcode_to_e4m3(const void *codes, int elem, int64_t n_elements, void *out_e4m3,
                           int device, void *stream);
 
+/*
+ * attention probabilities  <->  torchmx/layers/mx_llama_attention.py:214-239: the chain between the two MX matmuls of
+ * MXInferenceLlamaAttention (and its Qwen2 twin),
+ *     w = scores / sqrt(head_dim);  w = w + mask;  w = softmax(w, -1, dtype=float32).to(bfloat16);  to_mx(w, elem, 32)
+ * as ONE pass over the scores.  `scores` is the contiguous bf16 [batch, heads, q_len, kv_len] output of the Q.K^T matmul;
+ * every bf16 rounding of the chain is reproduced, the quantization is mxq_quantize's.
+ *   scaling     : the fp32 factor the chain multiplies by (CUDA evaluates `x / sqrt(d)` as x * (1.0f / sqrtf(d)))
+ *   mask        : NULL or an additive bf16 mask, element strides over (batch, head, query row) given, kv stride 1;
+ *                 stride 0 broadcasts
+ *   causal      : non-zero also hides kv index j > q + (kv_len - q_len) (what sdpa's is_causal does when no mask is given)
+ *   codes/scales: [rows, kv_len] (kv_len/2 for MXQ_ELEM_E2M1) / [rows, kv_len/32], rows = batch*heads*q_len
+ * kv_len must be a multiple of 32 and <= 32768; scores and codes 32-byte aligned; else MXQ_ERR_UNSUPPORTED_SHAPE.
+ */
+typedef struct {
+    const void *scores;
+    int64_t batch, heads, q_len, kv_len;
+    float scaling;
+    const void *mask; int64_t mask_stride_b, mask_stride_h, mask_stride_q;
+    int causal;
+    int elem /* mxq_elem_t */; unsigned flags /* MXQ_FLAG_* */;
+    void *codes; uint8_t *scales;
+} mxq_softmax_args_t;
+MXQ_API int mxq_softmax_quantize(const mxq_softmax_args_t *args, int device, void *stream);
+
 #define MXQ_OK 0
 #define MXQ_ERR_INVALID 1
 #define MXQ_ERR_UNSUPPORTED_SHAPE 2

@@ -28,7 +28,7 @@ SHAPES = {
 }
 
 
-def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: bool = True, llm_api: bool = False):
+def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: bool = True, llm_api: bool = False, mx_attention: bool = False):
     from transformers import LlamaConfig, LlamaForCausalLM
 
     import torchmx_b200  # noqa: F401
@@ -60,7 +60,10 @@ def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: boo
         if llm_api:  # attention / MLP blocks swapped for their MX versions (projection quantization only), then lm_head
             from torchmx_b200.config import QAttentionConfig
             from torchmx_b200.quant_api import quantize_llm_
-            quantize_llm_(model, QAttentionConfig(projection_config=qc), qc, fuse_rmsnorm=FUSE_NORM)
+            e = MXConfig(adt, 32)  # Q, K, V and the attention probabilities as MX operands too (reference :195-243)
+            qa = QAttentionConfig(projection_config=qc, query_config=e, key_config=e, value_config=e, attention_weights_config=e) if mx_attention \
+                else QAttentionConfig(projection_config=qc)
+            quantize_llm_(model, qa, qc, fuse_rmsnorm=FUSE_NORM)
         else:
             quantize_linear_(model, qc)
         e1.record()
@@ -111,14 +114,14 @@ def capture(fn):
 def run(args) -> dict:
     from transformers.cache_utils import StaticCache
 
-    model, cfg, info = build(args.model, args.layers, args.wdtype, args.adtype, quantize=not args.no_quant, llm_api=args.llm_api)
-    res = {"api": "none (bf16 HF)" if args.no_quant else ("quantize_llm_" if args.llm_api else "quantize_linear_"), "model": args.model, "layers": cfg.num_hidden_layers, "weights": args.wdtype, "activations": args.adtype, **info}
+    model, cfg, info = build(args.model, args.layers, args.wdtype, args.adtype, quantize=not args.no_quant, llm_api=args.llm_api, mx_attention=args.mx_attention)
+    res = {"api": "none (bf16 HF)" if args.no_quant else (("quantize_llm_ + MX attention" if args.mx_attention else "quantize_llm_") if args.llm_api else "quantize_linear_"), "model": args.model, "layers": cfg.num_hidden_layers, "weights": args.wdtype, "activations": args.adtype, **info}
     dev = "cuda"
 
     # ---- prefill: one prompt of `prefill` tokens, fresh static cache each run -------------------------------
     P = args.prefill
     ids = torch.randint(0, cfg.vocab_size, (1, P), device=dev)
-    cache = StaticCache(config=cfg, max_cache_len=P + 8)
+    cache = StaticCache(config=cfg, max_cache_len=-(-(P + 8) // 128) * 128)  # multiple of 128: the MX attention contractions need it
 
     def prefill():
         set_len(cache, 0)
@@ -141,7 +144,7 @@ def run(args) -> dict:
 
     # ---- decode: batch B, KV cache pre-filled with `ctx` tokens per sequence -----------------------------
     B, ctx, steps = args.batch, args.ctx, args.steps
-    cache = StaticCache(config=cfg, max_cache_len=ctx + steps + 8)
+    cache = StaticCache(config=cfg, max_cache_len=-(-(ctx + steps + 8) // 128) * 128)
     prompt = torch.randint(0, cfg.vocab_size, (B, ctx), device=dev)
     model(input_ids=prompt, past_key_values=cache, use_cache=True)
     tok = torch.randint(0, cfg.vocab_size, (B, 1), device=dev)
@@ -172,6 +175,8 @@ def run(args) -> dict:
     res["decode_weight_stream_floor_ms"] = codes_bytes / 6.5e12 * 1e3
     from torchmx_b200 import mx_gemm
     res["gemm_stats"] = dict(mx_gemm.stats)
+    from torchmx_b200 import attention_ops
+    res["attention_stats"] = dict(attention_ops.stats)
     res["max_mem_GB"] = torch.cuda.max_memory_allocated() / 1e9
     return res
 
@@ -189,6 +194,7 @@ if __name__ == "__main__":
     ap.add_argument("--adtype", default="float8_e4m3")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--llm-api", action="store_true", help="quantize_llm_ (MX attention / MLP blocks) instead of quantize_linear_")
+    ap.add_argument("--mx-attention", action="store_true", help="with --llm-api: quantize Q, K, V and the attention probabilities (MX bmm + fused softmax)")
     ap.add_argument("--no-quant", action="store_true", help="plain bf16 HF model (context line, not the product)")
     a = ap.parse_args()
     print(json.dumps(run(a)), flush=True)

@@ -15,7 +15,7 @@ FLAG_HW_EXACT = 1
 MAX_DIMS = 6
 
 EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_transcode_to_e4m3", "mxq_pack_operand",
-           "mxq_last_error", "mxq_version", "mxq_arch")
+           "mxq_softmax_quantize", "mxq_last_error", "mxq_version", "mxq_arch")
 
 
 class GemmArgs(ctypes.Structure):
@@ -30,6 +30,18 @@ class GemmArgs(ctypes.Structure):
         ("a_format", ctypes.c_int), ("b_format", ctypes.c_int),
         ("d_multicast", ctypes.c_void_p),
         ("x_bf16", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("x_quant_flags", ctypes.c_int),
+    ]
+
+
+class SoftmaxArgs(ctypes.Structure):
+    _fields_ = [
+        ("scores", ctypes.c_void_p),
+        ("batch", ctypes.c_int64), ("heads", ctypes.c_int64), ("q_len", ctypes.c_int64), ("kv_len", ctypes.c_int64),
+        ("scaling", ctypes.c_float),
+        ("mask", ctypes.c_void_p), ("mask_stride_b", ctypes.c_int64), ("mask_stride_h", ctypes.c_int64), ("mask_stride_q", ctypes.c_int64),
+        ("causal", ctypes.c_int),
+        ("elem", ctypes.c_int), ("flags", ctypes.c_uint),
+        ("codes", ctypes.c_void_p), ("scales", ctypes.c_void_p),
     ]
 
 
@@ -67,6 +79,8 @@ def lib() -> ctypes.CDLL:
         L.mxq_transcode_to_e4m3.argtypes = [vp, i32, i64, vp, i32, vp]
         L.mxq_pack_operand.restype = i32
         L.mxq_pack_operand.argtypes = [vp, i32, i64, vp, i32, vp]
+        L.mxq_softmax_quantize.restype = i32
+        L.mxq_softmax_quantize.argtypes = [ctypes.POINTER(SoftmaxArgs), i32, vp]
         if L.mxq_arch() != 1000:
             raise RuntimeError(f"torchmx_b200: libmxq.so was built for arch {L.mxq_arch()}, expected sm_100a")
         _lib = L

@@ -15,6 +15,7 @@ cudaError_t launch_dequantize_strided(const void*, const uint8_t*, int, const in
 cudaError_t launch_transcode(const void*, int, int64_t, void*, int, cudaStream_t);
 cudaError_t launch_pack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 int launch_gemm(const mxq_gemm_args_t*, int, cudaStream_t, char*, size_t);
+int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size_t);
 }  // namespace mxq
 
 namespace {
@@ -169,6 +170,19 @@ int mxq_gemm(const mxq_gemm_args_t* a, int device, void* stream) {
     char msg[400] = "";
     const int rc = mxq::launch_gemm(a, sm_count_of(scope.cur), (cudaStream_t)stream, msg, sizeof(msg));
     return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_gemm: %s", msg);
+}
+
+int mxq_softmax_quantize(const mxq_softmax_args_t* a, int device, void* stream) {
+    if (!a) return fail(MXQ_ERR_INVALID, "mxq_softmax_quantize: null args");
+    if (!valid_elem(a->elem)) return fail(MXQ_ERR_INVALID, "mxq_softmax_quantize: unknown element type %d", a->elem);
+    if (a->batch < 0 || a->heads < 0 || a->q_len < 0 || a->kv_len < 0) return fail(MXQ_ERR_INVALID, "mxq_softmax_quantize: negative extent");
+    if (a->batch == 0 || a->heads == 0 || a->q_len == 0 || a->kv_len == 0) return MXQ_OK;
+    if (!a->scores || !a->codes || !a->scales) return fail(MXQ_ERR_INVALID, "mxq_softmax_quantize: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_softmax_quantize: selecting device");
+    char msg[400] = "";
+    const int rc = mxq::launch_softmax_quantize(a, (cudaStream_t)stream, msg, sizeof(msg));
+    return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_softmax_quantize: %s", msg);
 }
 
 }  // extern "C"

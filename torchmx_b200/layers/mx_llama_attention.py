@@ -8,7 +8,8 @@ past_key_values, **kwargs) -> (attn_output, attn_weights)`), not the 4.44 intern
   exactly as the reference spells it out (:195-243): Q and K are quantized along head_dim, V along the key/value sequence
   (quantize the transpose, transpose back), scores = Q_mx @ K_mx^T * scaling (+ mask), softmax in fp32, P quantized along
   the key/value sequence, out = P_mx @ V_mx -- both contractions reach the tcgen05 block-scaled bmm when the blocked
-  extents are multiples of 128 (otherwise the dequantize path, like the reference);
+  extents are multiples of 128 (otherwise the dequantize path, like the reference), and everything between them is one
+  kernel (`attention_ops.softmax_to_mx`, K4a) when the key/value length is a multiple of 32;
 * without it the module keeps the model's configured attention function (sdpa / flash / eager) on the rotated bf16 Q, K, V.
 The KV cache stays in high precision (reference :186-187).
 """
@@ -19,6 +20,7 @@ from typing import Optional, Tuple
 import torch
 from torch import nn
 
+from .. import attention_ops
 from ..config import QAttentionConfig, QLinearConfig
 from ..mx_tensor import MXTensor
 from .mx_linear import MXInferenceLinear
@@ -86,13 +88,31 @@ class _MXAttentionMixin:
         q_mx = MXTensor.to_mx(query_states.contiguous(), qc.query_config.elem_dtype, qc.query_config.block_size)
         k_mx = MXTensor.to_mx(key_states.contiguous(), qc.key_config.elem_dtype, qc.key_config.block_size)
         v_mx = MXTensor.to_mx(value_states.transpose(2, 3).contiguous(), qc.value_config.elem_dtype, qc.value_config.block_size).transpose(2, 3)
-        attn_weights = torch.matmul(q_mx, k_mx.transpose(2, 3)) * scaling
-        if attention_mask is not None:
-            attn_weights = attn_weights + attention_mask[:, :, :, : key_states.shape[-2]]
-        attn_weights = nn.functional.softmax(attn_weights, dim=-1, dtype=torch.float32).to(dtype)
-        if self.training and getattr(self, "attention_dropout", 0.0):
-            attn_weights = nn.functional.dropout(attn_weights, p=self.attention_dropout, training=True)
-        p_mx = MXTensor.to_mx(attn_weights, qc.attention_weights_config.elem_dtype, qc.attention_weights_config.block_size)
+        scores = torch.matmul(q_mx, k_mx.transpose(2, 3))
+        q_len, kv_len = scores.shape[-2], scores.shape[-1]
+        mask, causal = None, False
+        if attention_mask is not None:  # no matter the length, we just slice it (reference :218-220)
+            mask = attention_mask[:, :, :, :kv_len]
+            if mask.dtype == torch.bool:  # the sdpa mask interface hands out "may attend" booleans instead of an additive mask
+                mask = torch.zeros_like(mask, dtype=dtype).masked_fill_(~mask, float("-inf"))
+        elif q_len > 1 and getattr(self, "is_causal", True):
+            causal = True  # mask creation was skipped because the attention function is expected to apply is_causal itself
+        dropout = self.training and getattr(self, "attention_dropout", 0.0)
+        pc = qc.attention_weights_config
+        # scale, mask, fp32 softmax, bf16 rounding and P quantization in one pass over the scores (K4a) ...
+        p_mx = None if dropout else attention_ops.softmax_to_mx(scores, scaling, mask, causal, pc.elem_dtype, pc.block_size)
+        if p_mx is None:  # ... or the chain as the reference spells it (:214-239)
+            attention_ops.stats["unfused_softmax"] += 1
+            attn_weights = scores * scaling
+            if mask is not None:
+                attn_weights = attn_weights + mask
+            if causal:
+                hidden = torch.ones(q_len, kv_len, dtype=torch.bool, device=scores.device).triu_(kv_len - q_len + 1)
+                attn_weights = attn_weights.masked_fill(hidden, float("-inf"))
+            attn_weights = nn.functional.softmax(attn_weights, dim=-1, dtype=torch.float32).to(dtype)
+            if dropout:
+                attn_weights = nn.functional.dropout(attn_weights, p=self.attention_dropout, training=True)
+            p_mx = MXTensor.to_mx(attn_weights, pc.elem_dtype, pc.block_size)
         attn_output = torch.matmul(p_mx, v_mx)
         return attn_output.transpose(1, 2).contiguous()
 
