@@ -163,6 +163,11 @@ MXQ_API int mxq_gemm(const mxq_gemm_args_t *args, int device, void *stream);
  * bits).  n_elements must be a multiple of 16. */
 MXQ_API int mxq_pack_operand(const void *codes, int elem, int64_t n_elements, void *out_packed, int device, void *stream);
 
+/* the inverse: packed operand stream -> reference-layout element codes (what MXTensor._data and a reference state_dict hold,
+ * torchmx/mx_tensor.py:495-520), so a weight can live in HBM / on disk ONLY in its dense 4 / 6-bit form (0.5 / 0.75 B per
+ * element instead of the reference's 0.5 / 1 B) and still be handed back to the reference bit-for-bit. */
+MXQ_API int mxq_unpack_operand(const void *packed, int elem, int64_t n_elements, void *out_codes, int device, void *stream);
+
 /* exact re-encoding of reference-layout element codes as E4M3 bytes (every e3m2 / e2m3 / e2m1
  * value is representable in e4m3): n elements in, n bytes out; MXQ_ELEM_E2M1 input is packed. */
 MXQ_API int mxq_transcode_to_e4m3(const void *codes, int elem, int64_t n_elements, void *out_e4m3,

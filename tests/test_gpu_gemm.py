@@ -308,3 +308,67 @@ def test_fused_activation_quantization_is_bit_identical(mx, rows, N, K, wdt, bia
     assert mx_gemm.stats.get("fused_act_quant", 0) == n0 + 1
     assert torch.equal(torch.nan_to_num(y_fused.float(), nan=12345.0), torch.nan_to_num(y_two.float(), nan=12345.0))
     assert torch.isnan(y_fused[0]).all() and torch.isnan(y_fused[-1]).all() and (rows < 3 or not torch.isnan(y_fused[1]).any())
+
+
+# ---- packed-only weights: PackedMXLinear / pack_linear_ / mxq_unpack_operand -----------------------------------
+@pytest.mark.parametrize("wdt", ["float6_e3m2", "float6_e2m3", "float4_e2m1", "float8_e4m3"])
+@pytest.mark.parametrize("rows", [8, 300])
+def test_packed_linear_is_bit_identical_and_round_trips(wdt, rows):
+    import io
+    import torchmx  # noqa: F401
+    from torchmx import mx_gemm
+    from torchmx.config import MXConfig, QLinearConfig
+    from torchmx.layers.mx_linear import MXInferenceLinear
+    from torchmx.layers.packed_linear import PackedMXLinear
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(512, 384, bias=True, device=DEV, dtype=torch.bfloat16)
+    qc = QLinearConfig(weights_config=MXConfig(wdt, 32), activations_config=MXConfig("float8_e4m3", 32))
+    ref = MXInferenceLinear.from_float(lin, qc)
+    x = torch.randn(rows, 512, device=DEV, dtype=torch.bfloat16)
+    want = ref(x)
+    codes, scales = ref.weight._data.clone(), ref.weight._scale_e8m0.clone()
+    packed = PackedMXLinear.from_mx_linear(ref, keep_source=True)
+    assert packed is not None
+    bits = {"float6_e3m2": 6, "float6_e2m3": 6, "float4_e2m1": 4, "float8_e4m3": 8}[wdt]
+    assert packed.weight_packed.shape == (384, 512 * bits // 8) and packed.weight_scale.shape == (384, 16)
+    n0 = mx_gemm.stats["tensor_core"]
+    got = packed(x)
+    assert mx_gemm.stats["tensor_core"] == n0 + 1
+    assert torch.equal(got, want)                      # same kernel, same operand bytes
+    assert torch.equal(packed(ref.prepare_input(x)), want)
+    # reference layout back, bit for bit (through the state_dict of the packed module)
+    buf = io.BytesIO()
+    torch.save(packed.state_dict(), buf)
+    buf.seek(0)
+    sd = torch.load(buf, weights_only=True)
+    assert set(sd) == {"weight_packed", "weight_scale", "bias"} and sd["weight_packed"].numel() == 384 * 512 * bits // 8
+    fresh = PackedMXLinear(512, 384, qc, packed.operand_format, bias=torch.nn.Parameter(torch.empty(384, device=DEV, dtype=torch.bfloat16)), device=DEV)
+    fresh.load_state_dict(sd)
+    back = fresh.to_mx_linear()
+    assert torch.equal(back.weight._data, codes) and torch.equal(back.weight._scale_e8m0, scales)
+    assert torch.equal(back(x), want)
+
+
+def test_pack_linear_on_a_model_and_what_it_leaves_alone():
+    import torchmx  # noqa: F401
+    from torchmx.config import MXConfig, QLinearConfig
+    from torchmx.layers.mx_linear import MXInferenceLinear
+    from torchmx.layers.packed_linear import PackedMXLinear
+    from torchmx.quant_api import pack_linear_, quantize_linear_, unpack_linear_
+    torch.manual_seed(2)
+    model = torch.nn.Sequential(torch.nn.Linear(256, 512, bias=False), torch.nn.GELU(), torch.nn.Linear(512, 96), torch.nn.Linear(96, 64)).to(DEV, torch.bfloat16)
+    quantize_linear_(model, QLinearConfig(weights_config=MXConfig("float6_e3m2", 32), activations_config=MXConfig("float8_e4m3", 32)))
+    x = torch.randn(40, 256, device=DEV, dtype=torch.bfloat16)
+    want = model(x)
+    sd_before = {k: (v._data.clone(), v._scale_e8m0.clone()) for k, v in model.state_dict().items() if k.endswith("weight")}
+    mem0 = sum(m.weight._data.numel() + m.weight._scale_e8m0.numel() for m in model if isinstance(m, MXInferenceLinear))
+    assert pack_linear_(model) == 2                                    # in_features 96 is not a multiple of 128: stays as it is
+    assert [type(m) for m in model if not isinstance(m, torch.nn.GELU)] == [PackedMXLinear, PackedMXLinear, MXInferenceLinear]
+    mem1 = sum(b.numel() for m in model if isinstance(m, PackedMXLinear) for b in m.buffers()) + model[3].weight._data.numel() + model[3].weight._scale_e8m0.numel()
+    assert mem1 < 0.78 * mem0
+    assert torch.equal(model(x), want)
+    assert unpack_linear_(model) == 2
+    for k, (codes, scales) in sd_before.items():
+        w = model.state_dict()[k]
+        assert torch.equal(w._data, codes) and torch.equal(w._scale_e8m0, scales)
+    assert torch.equal(model(x), want)

@@ -28,6 +28,9 @@ SHAPES = {
 }
 
 
+PACK = False
+
+
 def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: bool = True, llm_api: bool = False, mx_attention: bool = False):
     from transformers import LlamaConfig, LlamaForCausalLM
 
@@ -72,7 +75,12 @@ def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: boo
         info["quantize_gpu_ms"] = e0.elapsed_time(e1)
         bpe = 2 + (0.5 if wdt == "float4_e2m1" else 1) + 1 / 32
         info["quantize_GBps_gpu"] = w_elems * bpe / (info["quantize_gpu_ms"] * 1e-3) / 1e9
+    if quantize and PACK:  # reference storage layout dropped: the dense 4 / 6-bit operand stream is the only copy of each weight
+        from torchmx_b200.quant_api import pack_linear_
+        info["packed_linears"] = pack_linear_(model)
     torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    info["resident_after_quantize_GB"] = torch.cuda.memory_allocated() / 1e9
     return model, cfg, info
 
 
@@ -177,6 +185,7 @@ def run(args) -> dict:
     res["gemm_stats"] = dict(mx_gemm.stats)
     from torchmx_b200 import attention_ops
     res["attention_stats"] = dict(attention_ops.stats)
+    res["resident_after_run_GB"] = torch.cuda.memory_allocated() / 1e9
     res["max_mem_GB"] = torch.cuda.max_memory_allocated() / 1e9
     return res
 
@@ -196,5 +205,7 @@ if __name__ == "__main__":
     ap.add_argument("--llm-api", action="store_true", help="quantize_llm_ (MX attention / MLP blocks) instead of quantize_linear_")
     ap.add_argument("--mx-attention", action="store_true", help="with --llm-api: quantize Q, K, V and the attention probabilities (MX bmm + fused softmax)")
     ap.add_argument("--no-quant", action="store_true", help="plain bf16 HF model (context line, not the product)")
+    ap.add_argument("--pack", action="store_true", help="pack_linear_: weights held only as packed tensor-core operands")
     a = ap.parse_args()
+    PACK = a.pack
     print(json.dumps(run(a)), flush=True)

@@ -14,6 +14,7 @@ cudaError_t launch_dequantize_strided(const void*, const uint8_t*, int, const in
                                       void*, cudaStream_t);
 cudaError_t launch_transcode(const void*, int, int64_t, void*, int, cudaStream_t);
 cudaError_t launch_pack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
+cudaError_t launch_unpack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 int launch_gemm(const mxq_gemm_args_t*, int, cudaStream_t, char*, size_t);
 int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size_t);
 }  // namespace mxq
@@ -154,6 +155,17 @@ int mxq_pack_operand(const void* codes, int elem, int64_t n_elements, void* out,
     if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_pack_operand: selecting device");
     const cudaError_t e = mxq::launch_pack_operand(codes, elem, n_elements, out, sm_count_of(scope.cur), (cudaStream_t)stream);
     return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_pack_operand: launch");
+}
+
+int mxq_unpack_operand(const void* packed, int elem, int64_t n_elements, void* out, int device, void* stream) {
+    if (elem != MXQ_ELEM_E3M2 && elem != MXQ_ELEM_E2M3 && elem != MXQ_ELEM_E2M1) return fail(MXQ_ERR_INVALID, "mxq_unpack_operand: element type %d has no packed operand form", elem);
+    if (n_elements < 0 || n_elements % 16) return fail(MXQ_ERR_INVALID, "mxq_unpack_operand: element count must be a non-negative multiple of 16");
+    if (n_elements == 0) return MXQ_OK;
+    if (!packed || !out) return fail(MXQ_ERR_INVALID, "mxq_unpack_operand: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_unpack_operand: selecting device");
+    const cudaError_t e = mxq::launch_unpack_operand(packed, elem, n_elements, out, sm_count_of(scope.cur), (cudaStream_t)stream);
+    return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_unpack_operand: launch");
 }
 
 int mxq_gemm(const mxq_gemm_args_t* a, int device, void* stream) {

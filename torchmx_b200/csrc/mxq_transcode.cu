@@ -112,6 +112,35 @@ __global__ void __launch_bounds__(256) pack_fp6_kernel(const uint8_t* __restrict
     }
 }
 
+// fp6 inverse: 12 packed bytes -> 16 one-byte codes (bits [5:0]; bits [7:6] zero, as the reference quantizer writes them)
+__global__ void __launch_bounds__(256) unpack_fp6_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int64_t n_groups) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += stride) {
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(in + i * 12);
+        const uint32_t a = s[0], b = s[1], c = s[2];
+        const uint32_t t[4] = {a & 0xFFFFFFu, (a >> 24) | ((b & 0xFFFFu) << 8), (b >> 16) | ((c & 0xFFu) << 16), c >> 8};
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = (t[j] & 0x3F) | ((t[j] & 0xFC0) << 2) | ((t[j] & 0x3F000) << 4) | ((t[j] & 0xFC0000) << 6);
+        stg128_stream(out + i * 16, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+}
+
+cudaError_t launch_unpack_operand(const void* packed, int elem, int64_t n_elements, void* out, int sm_count, cudaStream_t stream) {
+    if (((uintptr_t)packed % 16) || ((uintptr_t)out % 16)) return cudaErrorMisalignedAddress;
+    const int64_t cap = (int64_t)sm_count * 32;
+    if (elem == MXQ_ELEM_E2M1) {  // the nibble swap is its own inverse
+        const int64_t n_bytes = n_elements / 2;
+        const int64_t want = (n_bytes / 16 + 255) / 256 + 1;
+        pack_fp4_kernel<<<(int)(want < cap ? want : cap), 256, 0, stream>>>((const uint8_t*)packed, (uint8_t*)out, n_bytes);
+    } else {
+        const int64_t n_groups = n_elements / 16;
+        const int64_t want = (n_groups + 255) / 256 + 1;
+        unpack_fp6_kernel<<<(int)(want < cap ? want : cap), 256, 0, stream>>>((const uint8_t*)packed, (uint8_t*)out, n_groups);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack_operand(const void* codes, int elem, int64_t n_elements, void* out, int sm_count, cudaStream_t stream) {
     if (((uintptr_t)codes % 16) || ((uintptr_t)out % 16)) return cudaErrorMisalignedAddress;
     const int64_t cap = (int64_t)sm_count * 32;

@@ -273,3 +273,62 @@ def linear_fused_act_quant(x: torch.Tensor, w: MXTensor, bias, hw_exact: bool) -
         stats["fused_allreduce"] += 1
         return out.view(tuple(x.shape[:-1]) + (N,))
     return out
+
+
+def pack_weight(w: MXTensor):
+    """MXTensor weight [N, K] (blocks along K) -> (operand tensor, MXQ_OPERAND_* format) in the form the tensor-core kernels
+    consume: the dense 4 / 6-bit stream for fp4 / fp6, the code bytes themselves for fp8.  None if the weight cannot run on
+    the tensor-core path at all (a packed-only layer has no dequantize path to fall back to)."""
+    if not _qualifies(w) or w._data.dim() != 2 or w._block_dim != 1 or w.shape[-1] % 128 != 0 or not w._data.is_contiguous():
+        return None
+    prev, packed = _USE_PACKED, None
+    set_packed_operands(True)
+    try:
+        packed = _operand_rows(w._data, w._elem_dtype, None)
+    finally:
+        set_packed_operands(prev)
+    return packed
+
+
+def unpack_weight(packed: torch.Tensor, fmt: int, elem: dtypes.DType) -> torch.Tensor:
+    """the inverse of `pack_weight`: reference-layout codes (MXTensor._data), bit-for-bit"""
+    if fmt in (FMT_E4M3_BYTES, FMT_E5M2_BYTES):
+        return packed.clone()
+    bits = _PACKED_BITS[fmt]
+    k = packed.shape[-1] * 8 // bits
+    out = torch.empty(tuple(packed.shape[:-1]) + (k // 2 if elem == dtypes.float4_e2m1 else k,), dtype=torch.uint8, device=packed.device)
+    rc = _C.lib().mxq_unpack_operand(packed.data_ptr(), dtypes.ELEM_ID[elem.name], packed.numel() * 8 // bits, out.data_ptr(),
+                                     packed.device.index, _stream_ptr(packed))
+    _C.check(rc, "mxq_unpack_operand")
+    return out
+
+
+def linear_packed_weight(x, b_e: torch.Tensor, sfb: torch.Tensor, b_fmt: int, bias, act_elem: dtypes.DType, hw_exact: bool) -> torch.Tensor:
+    """y = quantize_mx(x, act_elem, 32) @ W^T (+ bias) for a weight held only as its tensor-core operand (`pack_weight`).
+    x: bf16 [..., K] or an MXTensor already quantized with the layer's activation config.  Decode-sized bf16 activations
+    are quantized inside the GEMM; everything else goes K1 -> K3.  Raises if the launch is refused: there is no other path."""
+    N, K = b_e.shape[0], sfb.shape[-1] * 32
+    lead = tuple(x.shape[:-1])
+    assert x.shape[-1] == K, f"activation has {x.shape[-1]} features, the weight {K}"
+    if bias is not None:
+        assert bias.dtype == torch.bfloat16 and bias.dim() == 1 and bias.shape[0] == N and bias.is_contiguous()
+    rows = x.numel() // K if K else 0
+    out = torch.empty(lead + (N,), dtype=torch.bfloat16, device=b_e.device)
+    if rows == 0:
+        return out
+    if (not isinstance(x, MXTensor) and _FUSED_ACT and act_elem == dtypes.float8_e4m3 and rows <= FUSED_ACT_MAX_ROWS and x.is_contiguous()
+            and x.dtype == torch.bfloat16):
+        ok = _launch(None, None, b_e, sfb, bias, 1, rows, N, K, 0, 0, 0, 0, out, FMT_E4M3_BYTES, b_fmt, 0, x_hp=x.view(rows, K),
+                     x_flags=_C.FLAG_HW_EXACT if hw_exact else 0)
+        if ok:
+            stats["tensor_core"] += 1
+            stats["fused_act_quant"] = stats.get("fused_act_quant", 0) + 1
+            return out
+    x_mx = x if isinstance(x, MXTensor) else MXTensor.to_mx(x, act_elem, 32)
+    assert _qualifies(x_mx) and x_mx._block_dim == x_mx._data.dim() - 1 and x_mx._data.is_contiguous(), "activation cannot run on the tensor-core path"
+    a_codes, sfa = x_mx._data.reshape(rows, -1), x_mx._scale_e8m0.reshape(rows, -1)
+    a_e, a_fmt = _operand_rows(a_codes, x_mx._elem_dtype, None)
+    if not _launch(a_e, sfa, b_e, sfb, bias, 1, rows, N, K, 0, 0, 0, 0, out, a_fmt, b_fmt, 0):
+        raise RuntimeError(f"mxq_gemm refused [{rows}, {K}] x [{N}, {K}]^T for a packed-only weight: {_C.lib().mxq_last_error().decode()}")
+    stats["tensor_core"] += 1
+    return out

@@ -98,3 +98,38 @@ def quantize_llm_(model: torch.nn.Module, qattention_config: QAttentionConfig, q
     if fuse_rmsnorm:
         _swap_children(model, replacement_fn=lambda mod: FusedRMSNorm(mod.weight, mod.variance_epsilon),
                        filter_fn=lambda mod, fqn: type(mod).__name__ in ("LlamaRMSNorm", "Qwen2RMSNorm"))
+
+
+def pack_linear_(model: torch.nn.Module) -> int:
+    """Drop the reference storage layout of every `MXInferenceLinear` weight that can run on the tensor cores: the layer becomes a
+    `PackedMXLinear` whose only copy of the weight is the dense 4 / 6-bit operand stream (0.5 / 0.75 B per element + scales;
+    SURVEY §8f-3).  Same outputs bit for bit, smaller HBM footprint and `state_dict`.  Returns the number of layers packed;
+    layers that need the dequantize path (int8 elements, in_features % 128 != 0, meta weights) are left alone."""
+    from .layers.packed_linear import PackedMXLinear
+    n = 0
+
+    def replace(mod):
+        nonlocal n
+        new = PackedMXLinear.from_mx_linear(mod)
+        if new is None:
+            return mod
+        n += 1
+        return new
+
+    _swap_children(model, replacement_fn=replace, filter_fn=lambda mod, fqn: type(mod) is MXInferenceLinear)
+    return n
+
+
+def unpack_linear_(model: torch.nn.Module) -> int:
+    """The inverse of `pack_linear_`: every `PackedMXLinear` becomes an `MXInferenceLinear` again whose MXTensor weight (and
+    therefore `state_dict`) is bit-identical to the reference layout it was packed from."""
+    from .layers.packed_linear import PackedMXLinear
+    n = 0
+
+    def replace(mod):
+        nonlocal n
+        n += 1
+        return mod.to_mx_linear()
+
+    _swap_children(model, replacement_fn=replace, filter_fn=lambda mod, fqn: type(mod) is PackedMXLinear)
+    return n
