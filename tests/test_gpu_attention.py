@@ -16,27 +16,33 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _ordered_row_sum(e: torch.Tensor) -> torch.Tensor:
-    """fp32 sum over the last dim in the order K4a uses: 32 sequential adds per MX block, then either a sequential pass over
-    the row's blocks (<= 32 blocks) or a 5-step butterfly per warp followed by a sequential pass over the row's warps."""
+def _ordered_row_sum(e: torch.Tensor, masked: bool) -> torch.Tensor:
+    """fp32 sum over the last dim in the order K4a uses: 32 sequential adds per MX block, then over the row's blocks
+    * fewer than 8 blocks, or at most 32 without any mask: sequentially;
+    * 8 .. 256 blocks under a mask (causal or additive): a 3-step butterfly over each group of 8 consecutive blocks (one row's
+      lanes of a warp), then sequentially over the groups;
+    * otherwise: a 5-step butterfly over each group of 32 blocks (a warp), then sequentially over the groups."""
     kv = e.shape[-1]
     tpr = kv // 32
     eb = e.reshape(*e.shape[:-1], tpr, 32)
     s = torch.zeros_like(eb[..., 0])
     for i in range(32):
         s = s + eb[..., i]
-    if tpr <= 32:
+    if tpr < 8 or (not masked and tpr <= 32):
         acc = torch.zeros_like(s[..., 0])
         for j in range(tpr):
             acc = acc + s[..., j]
         return acc
-    wpr = (tpr + 31) // 32
-    v = torch.nn.functional.pad(s, (0, wpr * 32 - tpr)).reshape(*s.shape[:-1], wpr, 32)
-    for d in (16, 8, 4, 2, 1):
+    width = 8 if (masked and tpr <= 256) else 32
+    groups = (tpr + width - 1) // width
+    v = torch.nn.functional.pad(s, (0, groups * width - tpr)).reshape(*s.shape[:-1], groups, width)
+    d = width // 2
+    while d >= 1:
         v = v[..., :d] + v[..., d:2 * d]
+        d //= 2
     v = v[..., 0]
     acc = v[..., 0]
-    for j in range(1, wpr):
+    for j in range(1, groups):
         acc = acc + v[..., j]
     return acc
 
@@ -53,7 +59,7 @@ def _chain(scores, scaling, mask, causal, ordered: bool):
         return torch.softmax(w, dim=-1, dtype=torch.float32).to(torch.bfloat16)
     x = w.float()
     e = torch.exp(x - x.amax(-1, keepdim=True))
-    return (e / _ordered_row_sum(e).unsqueeze(-1)).to(torch.bfloat16)
+    return (e / _ordered_row_sum(e, causal or mask is not None).unsqueeze(-1)).to(torch.bfloat16)
 
 
 def _make(b, h, q, kv, mode, seed=0):
@@ -79,7 +85,8 @@ ELEMS = ["float8_e4m3", "float6_e3m2", "float6_e2m3", "float4_e2m1", "int8"]
 @pytest.mark.parametrize("shape,mode", [
     ((2, 3, 64, 32), "none"), ((1, 2, 40, 96), "causal"), ((2, 2, 17, 160), "mask"), ((1, 4, 128, 1024), "causal"),
     ((1, 2, 64, 1056), "mask_bcast"), ((2, 2, 256, 2048), "causal"), ((1, 1, 8, 4096), "mask_sliced"), ((1, 1, 3, 32768), "none"),
-    ((1, 2, 2048, 2048), "mask_bcast"),
+    ((1, 2, 2048, 2048), "mask_bcast"), ((1, 3, 70, 2176), "causal"), ((1, 1, 9, 8192), "mask"), ((1, 1, 5, 8224), "causal"),
+    ((2, 1, 33, 224), "causal"), ((1, 1, 2, 256), "none"), ((1, 2, 50, 1024), "none"), ((1, 1, 20, 2080), "none"), ((1, 1, 7, 512), "mask"),
 ])
 def test_softmax_to_mx_bit_exact_against_the_ordered_chain(elem, shape, mode):
     import torchmx  # noqa: F401

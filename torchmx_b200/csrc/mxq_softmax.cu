@@ -13,9 +13,9 @@
 // sum, i.e. the last ulp of the denominator, so a probability can land on the other side of a bf16 rounding boundary once in
 // ~1e4 elements.  The quantization itself is K1's arithmetic (mxq_quant_core.cuh), NaN rows included.
 //
-// Layout: one thread owns one 32-element MX block of a row (32 fp32 values in registers), a row is L/32 consecutive threads.
-// Rows shorter than 1024 elements share a warp (segmented shuffles), longer rows span whole warps of one CTA (shuffle +
-// shared-memory exchange).  L <= 32768.
+// Layout: one thread owns one 32-element MX block of a row (32 fp32 values in registers).  Rows of 8 .. 256 blocks (the
+// prefill sizes) are laid out 4 rows x 8 blocks per warp, so that causally hidden blocks fill whole warps; shorter rows share
+// a warp lane-segment-wise, longer ones span whole warps.  Row reductions: shuffles + one shared-memory exchange.  L <= 32768.
 #include "mxq_quant_core.cuh"
 
 #include <cmath>
@@ -29,6 +29,7 @@ struct SoftmaxParams {
     int64_t mask_sb, mask_sh, mask_sq;  // element strides of the mask over (batch, head, query row); kv stride is 1
     int64_t rows;
     int L, tpr;                         // row length, threads (= MX blocks) per row
+    int layout;                         // thread <-> (row, block) mapping: 0 = A, 1 = C, 2 = B (see the kernel)
     int heads, q_len;
     int causal, causal_offset;          // kv index j of query row q is visible iff j <= q + causal_offset
     int mask_vec;                       // mask rows are 16-byte aligned -> 128-bit loads
@@ -46,21 +47,32 @@ __device__ __forceinline__ float max_nan(float a, float b) {
 
 template <int ELEM, int MAXT>
 __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxParams p) {
-    __shared__ float red[32];
+    __shared__ float red[32 * 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t row;
     int t;
     bool live;
-    int seg_base = 0;       // first lane of this row's segment (rows that share a warp)
-    int warps_per_row = 1;  // rows that span warps
-    if (p.tpr <= 32) {
+    int seg_base = 0;       // layout A: first lane of this row's segment
+    int warps_per_row = 1;  // layouts B, C: warps that share a row
+    const int layout = p.layout;
+    if (layout == 0) {
+        // A (rows of at most 32 blocks): a row is tpr consecutive lanes, 32 / tpr rows per warp
         const int rpw = 32 / p.tpr;
         const int r = lane / p.tpr;
         t = lane - r * p.tpr;
         seg_base = r * p.tpr;
         row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * rpw + r;
         live = r < rpw && row < p.rows;
+    } else if (layout == 1) {
+        // C (masked rows of 8 .. 256 blocks): a warp holds 8 consecutive blocks of 4 consecutive rows, a row spans ceil(tpr / 8) warps.
+        // Blocks hidden by a causal mask are then (nearly) uniform across the warp, which skips their arithmetic as a whole.
+        warps_per_row = (p.tpr + 7) >> 3;
+        const int g = warp / warps_per_row;  // 4-row group within the CTA
+        t = (warp - g * warps_per_row) * 8 + (lane & 7);
+        row = ((int64_t)blockIdx.x * ((blockDim.x >> 5) / warps_per_row) + g) * 4 + (lane >> 3);
+        live = t < p.tpr && row < p.rows;
     } else {
+        // B (everything else): a row is ceil(tpr / 32) whole warps
         warps_per_row = (p.tpr + 31) >> 5;
         const int r = warp / warps_per_row;
         t = (warp - r * warps_per_row) * 32 + lane;
@@ -131,7 +143,7 @@ __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxPar
 #pragma unroll
     for (int i = 1; i < 32; ++i) m = max_nan(m, x[i]);
     auto row_reduce = [&](float v, bool is_max) -> float {
-        if (p.tpr <= 32) {
+        if (layout == 0) {
             float acc = is_max ? -INFINITY : 0.0f;
             for (int j = 0; j < p.tpr; ++j) {
                 const float o = __shfl_sync(0xFFFFFFFFu, v, (seg_base + j) & 31);
@@ -141,15 +153,17 @@ __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxPar
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
+            if (layout == 1 && d > 4) continue;  // C: the row's 8 lanes only
             const float o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
             v = is_max ? max_nan(v, o) : v + o;
         }
         __syncthreads();  // red[] may still be read from the previous reduction
-        if (lane == 0) red[warp] = v;
+        const int slot = layout == 1 ? (lane >> 3) : 0;  // C keeps one partial per row of the warp
+        if (layout == 1 ? (lane & 7) == 0 : lane == 0) red[warp * 4 + slot] = v;
         __syncthreads();
         const int w0 = (warp / warps_per_row) * warps_per_row;
-        float acc = red[w0];
-        for (int j = 1; j < warps_per_row; ++j) acc = is_max ? max_nan(acc, red[w0 + j]) : acc + red[w0 + j];
+        float acc = red[w0 * 4 + slot];
+        for (int j = 1; j < warps_per_row; ++j) acc = is_max ? max_nan(acc, red[(w0 + j) * 4 + slot]) : acc + red[(w0 + j) * 4 + slot];
         return acc;
     };
     const float row_max = row_reduce(m, true);
@@ -247,10 +261,19 @@ int launch_softmax_quantize(const mxq_softmax_args_t* a, cudaStream_t stream, ch
     p.codes = (uint8_t*)a->codes; p.scales = a->scales; p.flags = a->flags;
     int threads;
     int64_t rows_per_cta;
-    if (p.tpr <= 32) {
+    const bool masked = p.causal || p.mask;
+    if (p.tpr < 8 || (!masked && p.tpr <= 32)) {
+        p.layout = 0;
         threads = 256;
         rows_per_cta = (int64_t)(32 / p.tpr) * (threads / 32);
+    } else if (masked && p.tpr <= 256) {
+        p.layout = 1;  // measured on [32, 2048, 2048]: 6 % faster than B with a causal mask, 9 % slower without any mask
+        const int wpr = (p.tpr + 7) / 8;
+        const int groups = wpr >= 8 ? 1 : 8 / wpr;
+        threads = wpr * groups * 32;
+        rows_per_cta = 4 * groups;
     } else {
+        p.layout = 2;
         const int wpr = (p.tpr + 31) / 32;
         const int rpc = wpr >= 8 ? 1 : 8 / wpr;
         threads = wpr * rpc * 32;
