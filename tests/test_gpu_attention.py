@@ -206,3 +206,27 @@ def test_mx_attention_block_fused_softmax_and_implied_causal_mask():
         implied2 = qm(input_ids=ids2).logits
     assert torch.equal(implied[:, :96], implied2[:, :96])
     assert not torch.equal(implied[:, 96:], implied2[:, 96:])
+
+
+@pytest.mark.parametrize("elem", ["float8_e4m3", "float6_e3m2", "float4_e2m1"])
+def test_quantizing_kv_heads_before_repeating_them_is_bit_identical(elem):
+    """the reference repeats K / V to the query heads and then quantizes (mx_llama_attention.py:189-213); the block quantizes
+    the key/value heads once and repeats codes + scales"""
+    from transformers.models.llama.modeling_llama import repeat_kv
+    import torchmx  # noqa: F401
+    from torchmx import dtypes
+    from torchmx.layers.mx_llama_attention import _repeat_heads
+    from torchmx.mx_tensor import MXTensor
+    et = dtypes.STR_TO_ELEM_DTYPE[elem]
+    torch.manual_seed(4)
+    k = torch.randn(2, 2, 160, 128, device=DEV, dtype=torch.bfloat16)
+    v = torch.randn(2, 2, 160, 128, device=DEV, dtype=torch.bfloat16)
+    want_k = MXTensor.to_mx(repeat_kv(k, 4).contiguous(), et, 32)
+    got_k = _repeat_heads(MXTensor.to_mx(k.contiguous(), et, 32), 4)
+    want_v = MXTensor.to_mx(repeat_kv(v, 4).transpose(2, 3).contiguous(), et, 32).transpose(2, 3)
+    got_v = _repeat_heads(MXTensor.to_mx(v.transpose(2, 3).contiguous(), et, 32), 4).transpose(2, 3)
+    for got, want in ((got_k, want_k), (got_v, want_v)):
+        assert got.shape == want.shape and got._block_dim == want._block_dim
+        assert torch.equal(got._data, want._data) and torch.equal(got._scale_e8m0, want._scale_e8m0)
+    q = MXTensor.to_mx(torch.randn(2, 8, 128, 128, device=DEV, dtype=torch.bfloat16), dtypes.float8_e4m3, 32)
+    assert torch.equal(torch.matmul(q, got_k.transpose(2, 3)), torch.matmul(q, want_k.transpose(2, 3)))

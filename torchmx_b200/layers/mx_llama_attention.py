@@ -50,6 +50,33 @@ def _shell_like(cls, mod: nn.Module, skip=()) -> nn.Module:
     return new
 
 
+def _repeat_heads(t: MXTensor, n_rep: int) -> MXTensor:
+    """`repeat_kv` (transformers) on an MXTensor [batch, kv_heads, rows, cols]: each head n_rep times, codes and scales copied"""
+    if n_rep == 1:
+        return t
+
+    def rep(x):
+        b, h, r, c = x.shape
+        return x[:, :, None].expand(b, h, n_rep, r, c).reshape(b, h * n_rep, r, c)
+
+    return MXTensor(rep(t._scale_e8m0), rep(t._data), t._elem_dtype, t._block_size, t._orig_dtype, t._padding, t._block_dim)
+
+
+_mask_cache = (None, None)  # (weakref to the boolean mask tensor, its additive form): one conversion per forward, not per layer
+
+
+def _additive_mask(mask: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    global _mask_cache
+    import weakref
+    ref, add = _mask_cache
+    if ref is not None and ref[0]() is mask and ref[1] == mask._version and add.dtype == dtype and not torch.cuda.is_current_stream_capturing():
+        return add
+    add = torch.zeros_like(mask, dtype=dtype).masked_fill_(~mask, float("-inf"))
+    if not torch.cuda.is_current_stream_capturing():
+        _mask_cache = ((weakref.ref(mask), mask._version), add)
+    return add
+
+
 class _MXMLPMixin:
     @classmethod
     @torch.no_grad()
@@ -80,21 +107,23 @@ class _MXAttentionMixin:
 
     def _mx_attention(self, query_states, key_states, value_states, attention_mask, scaling: float) -> torch.Tensor:
         """reference :195-243; inputs [bs, heads, len, head_dim] after rotary / cache update -> [bs, q_len, heads, head_dim]"""
-        from transformers.models.llama.modeling_llama import repeat_kv
         qc = self.qconfig
-        key_states = repeat_kv(key_states, self.num_key_value_groups)
-        value_states = repeat_kv(value_states, self.num_key_value_groups)
         dtype = query_states.dtype
+        groups = self.num_key_value_groups
         q_mx = MXTensor.to_mx(query_states.contiguous(), qc.query_config.elem_dtype, qc.query_config.block_size)
-        k_mx = MXTensor.to_mx(key_states.contiguous(), qc.key_config.elem_dtype, qc.key_config.block_size)
-        v_mx = MXTensor.to_mx(value_states.transpose(2, 3).contiguous(), qc.value_config.elem_dtype, qc.value_config.block_size).transpose(2, 3)
+        # The reference repeats K and V to the number of query heads and then quantizes (:189-213).  Every MX block lives inside
+        # one head (K: along head_dim; V: along the sequence of one (head, channel) row), so quantizing the key/value heads once
+        # and repeating the CODES is bit-identical -- a quarter of the quantization work and of the bytes copied under 4-way GQA.
+        k_mx = _repeat_heads(MXTensor.to_mx(key_states.contiguous(), qc.key_config.elem_dtype, qc.key_config.block_size), groups)
+        v_mx = _repeat_heads(MXTensor.to_mx(value_states.transpose(2, 3).contiguous(), qc.value_config.elem_dtype, qc.value_config.block_size),
+                             groups).transpose(2, 3)
         scores = torch.matmul(q_mx, k_mx.transpose(2, 3))
         q_len, kv_len = scores.shape[-2], scores.shape[-1]
         mask, causal = None, False
         if attention_mask is not None:  # no matter the length, we just slice it (reference :218-220)
             mask = attention_mask[:, :, :, :kv_len]
             if mask.dtype == torch.bool:  # the sdpa mask interface hands out "may attend" booleans instead of an additive mask
-                mask = torch.zeros_like(mask, dtype=dtype).masked_fill_(~mask, float("-inf"))
+                mask = _additive_mask(attention_mask, dtype)[:, :, :, :kv_len]
         elif q_len > 1 and getattr(self, "is_causal", True):
             causal = True  # mask creation was skipped because the attention function is expected to apply is_causal itself
         dropout = self.training and getattr(self, "attention_dropout", 0.0)
