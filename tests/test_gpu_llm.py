@@ -88,3 +88,104 @@ def test_mx_attention_decode_with_cache(tiny_llama):
             steps.append(out.logits[:, -1])
     got = torch.stack(steps, 1)
     assert _sqnr(full[:, 31:39], got) > 25, _sqnr(full[:, 31:39], got)
+
+
+def test_quantize_llm_qwen2_with_projection_biases():
+    """Qwen2 (reference: layers/mx_qwen2_attention.py): q / k / v projections carry biases -> the bias epilogue of K3, plus the
+    MX attention contractions and the fused softmax; tensor-core path vs the dequantize path the reference executes"""
+    import copy
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    import torchmx  # noqa: F401
+    from torchmx import attention_ops, mx_gemm
+    from torchmx.config import MXConfig, QAttentionConfig, QLinearConfig
+    from torchmx.layers.mx_llama_attention import MXInferenceQwen2Attention, MXInferenceQwen2MLP
+    from torchmx.quant_api import quantize_llm_
+    cfg = Qwen2Config(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, vocab_size=512,
+                      max_position_embeddings=512, use_sliding_window=False)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(0)
+    model = Qwen2ForCausalLM(cfg).to(DEV, torch.bfloat16).eval()
+    for layer in model.model.layers:  # random-init biases are zero: make them matter
+        for n in ("q_proj", "k_proj", "v_proj"):
+            torch.nn.init.normal_(getattr(layer.self_attn, n).bias, std=0.5)
+    ids = torch.randint(0, cfg.vocab_size, (2, 128), device=DEV)
+    with torch.no_grad():
+        ref = model(input_ids=ids).logits
+    qm = copy.deepcopy(model)
+    lin = QLinearConfig(weights_config=MXConfig("float6_e3m2", 32), activations_config=MXConfig("float8_e4m3", 32))
+    e = MXConfig("float8_e4m3", 32)
+    quantize_llm_(qm, QAttentionConfig(projection_config=lin, query_config=e, key_config=e, value_config=e, attention_weights_config=e), lin)
+    layer = qm.model.layers[0]
+    assert type(layer.self_attn) is MXInferenceQwen2Attention and type(layer.mlp) is MXInferenceQwen2MLP
+    assert layer.self_attn.q_proj.bias is not None
+    before, soft0 = dict(mx_gemm.stats), attention_ops.stats["fused_softmax"]
+    with torch.no_grad():
+        out_tc = qm(input_ids=ids).logits
+    assert mx_gemm.stats["tensor_core"] - before["tensor_core"] == 19 and mx_gemm.stats["fallback"] == before["fallback"]
+    assert attention_ops.stats["fused_softmax"] == soft0 + 2
+    mx_gemm.set_enabled(False)
+    try:
+        with torch.no_grad():
+            out_deq = qm(input_ids=ids).logits
+    finally:
+        mx_gemm.set_enabled(True)
+    assert _sqnr(out_deq, out_tc) > 30, _sqnr(out_deq, out_tc)
+    assert _sqnr(ref, out_tc) > 12, _sqnr(ref, out_tc)
+
+
+def test_stacked_projections_match_separate_launches(tiny_llama):
+    """q/k/v and gate/up stacked into one launch each for decode-sized activations: same storage (no second copy, state_dict
+    unchanged), outputs within accumulation noise of the separate launches (the split-K factor of the weight-streaming kernel
+    depends on the number of output tiles); prefill keeps one launch per projection and is bit-identical"""
+    import copy
+    import torchmx  # noqa: F401
+    from torchmx.config import MXConfig, QAttentionConfig, QLinearConfig
+    from torchmx.layers import mx_llama_attention as mla
+    from torchmx.quant_api import quantize_llm_
+    model, cfg = tiny_llama
+    lin = QLinearConfig(weights_config=MXConfig("float6_e3m2", 32), activations_config=MXConfig("float8_e4m3", 32))
+    built = {}
+    for fuse in (True, False):
+        prev, mla.FUSE_PROJECTIONS = mla.FUSE_PROJECTIONS, fuse
+        try:
+            qm = copy.deepcopy(model)
+            quantize_llm_(qm, QAttentionConfig(projection_config=lin), lin)
+        finally:
+            mla.FUSE_PROJECTIONS = prev
+        built[fuse] = qm
+    fused, plain = built[True], built[False]
+    att, mlp = fused.model.layers[0].self_attn, fused.model.layers[0].mlp
+    assert att.__dict__["_qkv"] is not None and mlp.__dict__["_gate_up"] is not None and plain.model.layers[0].self_attn.__dict__["_qkv"] is None
+    assert att.k_proj.weight._data.data_ptr() == att.__dict__["_qkv"].weight._data[att.q_proj.out_features:].data_ptr()  # aliases, not copies
+    sd_f, sd_p = fused.state_dict(), plain.state_dict()
+    assert list(sd_f) == list(sd_p)
+    for k in sd_f:
+        a, b = sd_f[k], sd_p[k]
+        if hasattr(a, "_data"):
+            assert torch.equal(a._data, b._data) and torch.equal(a._scale_e8m0, b._scale_e8m0), k
+    ids = torch.randint(0, cfg.vocab_size, (2, 128), device=DEV)
+    from torchmx import mx_gemm
+    n0 = mx_gemm.stats["tensor_core"]
+    with torch.no_grad():
+        out_f = fused(input_ids=ids).logits
+    n1 = mx_gemm.stats["tensor_core"]
+    with torch.no_grad():
+        out_p = plain(input_ids=ids).logits
+    assert n1 - n0 == 2 * 7 + 1 and mx_gemm.stats["tensor_core"] - n1 == 2 * 7 + 1   # 256 tokens: one launch per projection
+    assert torch.equal(out_f, out_p)
+    ids8 = ids[:, :4]
+    n0 = mx_gemm.stats["tensor_core"]
+    with torch.no_grad():
+        d_f = fused(input_ids=ids8).logits
+    n1 = mx_gemm.stats["tensor_core"]
+    with torch.no_grad():
+        d_p = plain(input_ids=ids8).logits
+    assert n1 - n0 == 2 * 4 + 1 and mx_gemm.stats["tensor_core"] - n1 == 2 * 7 + 1   # 8 tokens: q/k/v and gate/up stacked
+    assert _sqnr(d_p, d_f) > 40, _sqnr(d_p, d_f)
+    # a layer whose weight is replaced afterwards must not keep using the stale stacked copy
+    att.k_proj.weight = torch.nn.Parameter(plain.model.layers[1].self_attn.k_proj.weight, requires_grad=False)
+    plain.model.layers[0].self_attn.k_proj.weight = att.k_proj.weight
+    with torch.no_grad():
+        a, b = fused(input_ids=ids8).logits, plain(input_ids=ids8).logits
+    assert _sqnr(b, a) > 40, _sqnr(b, a)  # (a stale stacked k_proj would be a different weight matrix altogether)
+    assert _sqnr(d_f, a) < 30             # ... and the swap did change the output
