@@ -73,8 +73,15 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("M,N,K,ea,eb,bias,batch,spread", CASES)
-def test_tensor_core_matmul(mx, M, N, K, ea, eb, bias, batch, spread):
+# shapes whose 256x256 pair tiles would under-fill the GPU are dispatched to 128x128 tiles; "pair" switches that rule off so the
+# CTA-pair kernel keeps its small-shape coverage (ragged edges, bias, batches)
+TILE_RULES = [(*c, rule) for c in CASES for rule in (("auto", "pair") if c[0] > 128 and c[1] > 128 else ("auto",))]
+
+
+@pytest.mark.parametrize("M,N,K,ea,eb,bias,batch,spread,rule", TILE_RULES)
+def test_tensor_core_matmul(mx, monkeypatch, M, N, K, ea, eb, bias, batch, spread, rule):
+    if rule == "pair":
+        monkeypatch.setenv("MXQ_GEMM_NARROW", "-1")
     from torchmx import dtypes
     from torchmx.mx_tensor import MXTensor
     from torchmx_b200 import mx_gemm

@@ -718,7 +718,12 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
     }
     const int force_narrow = getenv("MXQ_GEMM_NARROW") ? atoi(getenv("MXQ_GEMM_NARROW")) : 0;  // developer knobs, re-read per call
     const int cfg = getenv("MXQ_GEMM_CFG") ? atoi(getenv("MXQ_GEMM_CFG")) : 0;  // developer knob: <BLOCK_N><STAGES>, 2<STAGES> = CTA pair
-    const bool wide = a->N > 128 && !force_narrow;
+    // Under-filled grids: when the 256x256 pair tiles would occupy at most a quarter of the SM pairs, 128x128 tiles spread the
+    // same work over 4x as many SMs (measured, K = 4096: 2048x1024 16.8 -> 15.1 us, 1024x1024 16.6 -> 14.5, 512x4096 17.1 -> 15.2).
+    // MXQ_GEMM_NARROW=-1 switches the rule off.
+    const int64_t pair_tiles = ((a->M + 255) / 256) * ((a->N + 255) / 256) * a->batch;
+    const bool underfilled = force_narrow >= 0 && a->M > 128 && a->N > 128 && pair_tiles * 4 <= sm_count && a->d_multicast == nullptr;
+    const bool wide = a->N > 128 && force_narrow <= 0 && !underfilled;
     CUtensorMap ma, mb;
     const bool use_pair = wide && a->M > 128 && sm_count >= 2 && (cfg == 0 || cfg / 10 == 2 || a->d_multicast != nullptr);
     if (use_pair) {
