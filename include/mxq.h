@@ -197,6 +197,18 @@ typedef struct {
 } mxq_softmax_args_t;
 MXQ_API int mxq_softmax_quantize(const mxq_softmax_args_t *args, int device, void *stream);
 
+/*
+ * SwiGLU gating + quantization  <->  the MLP block of the reference (torchmx/layers/mx_llama_attention.py:19-59 around
+ * transformers' `down_proj(act_fn(gate_proj(x)) * up_proj(x))`) followed by the activation quantization on entry to down_proj
+ * (torchmx/layers/mx_linear.py:63-66): codes, scales = quantize_mx(bf16(bf16(silu(gate)) * up), elem, 32) in one pass,
+ * bit-identical to aten silu + aten mul + mxq_quantize.
+ *   gate / up : bf16 [rows, cols], row strides ld_gate / ld_up in elements (>= cols, multiples of 16), 32-byte aligned bases;
+ *               they may be column slices of one stacked gate+up projection output
+ *   codes     : [rows, cols] (cols/2 for MXQ_ELEM_E2M1), scales: [rows, cols/32]; cols % 32 == 0
+ */
+MXQ_API int mxq_silu_mul_quantize(const void *gate, const void *up, int64_t rows, int64_t cols, int64_t ld_gate, int64_t ld_up,
+                          int elem /* mxq_elem_t */, unsigned flags /* MXQ_FLAG_* */, void *codes, uint8_t *scales, int device, void *stream);
+
 #define MXQ_OK 0
 #define MXQ_ERR_INVALID 1
 #define MXQ_ERR_UNSUPPORTED_SHAPE 2

@@ -230,3 +230,46 @@ def test_quantizing_kv_heads_before_repeating_them_is_bit_identical(elem):
         assert torch.equal(got._data, want._data) and torch.equal(got._scale_e8m0, want._scale_e8m0)
     q = MXTensor.to_mx(torch.randn(2, 8, 128, 128, device=DEV, dtype=torch.bfloat16), dtypes.float8_e4m3, 32)
     assert torch.equal(torch.matmul(q, got_k.transpose(2, 3)), torch.matmul(q, want_k.transpose(2, 3)))
+
+
+# ---- K1b: SwiGLU gating + quantization (mxq_silu_mul_quantize) ---------------------------------------------------------------
+@pytest.mark.parametrize("elem", ELEMS)
+@pytest.mark.parametrize("shape", [(1, 64), (3, 7, 96), (300, 1024), (2, 128, 14336)])
+def test_silu_mul_to_mx_is_bit_identical_to_the_chain(elem, shape):
+    import torchmx  # noqa: F401
+    from torchmx import dtypes, mlp_ops
+    from torchmx.mx_tensor import MXTensor
+    et = dtypes.STR_TO_ELEM_DTYPE[elem]
+    g = torch.Generator(device=DEV).manual_seed(11)
+    gate = (torch.randn(*shape, device=DEV, generator=g) * 4).to(torch.bfloat16)
+    up = (torch.randn(*shape, device=DEV, generator=g) * 2).to(torch.bfloat16)
+    gate.view(-1)[:8] = torch.tensor([0.0, -0.0, 88.0, -88.0, -120.0, 3e38, -3e38, 1e-30], device=DEV).to(torch.bfloat16)
+    got = mlp_ops.silu_mul_to_mx(gate, up, et, 32)
+    want = MXTensor.to_mx(torch.nn.functional.silu(gate) * up, et, 32)
+    assert got is not None and got.shape == want.shape
+    assert torch.equal(got._scale_e8m0, want._scale_e8m0) and torch.equal(got._data, want._data)
+
+
+def test_silu_mul_to_mx_on_column_slices_nan_blocks_and_refusals():
+    import torchmx  # noqa: F401
+    from torchmx import dtypes, mlp_ops
+    from torchmx import env_variables as env
+    from torchmx.mx_tensor import MXTensor
+    torch.manual_seed(12)
+    both = torch.randn(2, 40, 2 * 1024, device=DEV).to(torch.bfloat16)  # a stacked gate+up projection output
+    gate, up = both.split([1024, 1024], dim=-1)
+    gate[0, 3, 40] = float("nan")
+    up[1, 5, 100] = float("inf")
+    for hw_exact in ("False", "True"):
+        prev, env.MX_EXACT_QUANTIZATION = env.MX_EXACT_QUANTIZATION, hw_exact
+        try:
+            got = mlp_ops.silu_mul_to_mx(gate, up, dtypes.float8_e4m3, 32)
+            want = MXTensor.to_mx(torch.nn.functional.silu(gate) * up, dtypes.float8_e4m3, 32)
+        finally:
+            env.MX_EXACT_QUANTIZATION = prev
+        assert torch.equal(got._scale_e8m0, want._scale_e8m0) and torch.equal(got._data, want._data)
+        assert got._scale_e8m0[0, 3, 1] == 255 and got._scale_e8m0[1, 5, 3] == 255
+    assert mlp_ops.silu_mul_to_mx(gate[..., :48], up[..., :48], dtypes.float8_e4m3, 32) is None          # cols % 32
+    assert mlp_ops.silu_mul_to_mx(gate.float(), up.float(), dtypes.float8_e4m3, 32) is None              # dtype
+    assert mlp_ops.silu_mul_to_mx(gate[..., 8:72], up[..., 8:72], dtypes.float8_e4m3, 32) is None         # rows not 32-byte aligned
+    assert mlp_ops.silu_mul_to_mx(gate.transpose(0, 1), up.transpose(0, 1), dtypes.float8_e4m3, 32) is None  # no single row stride

@@ -8,7 +8,7 @@ import sys
 
 import torchmx_b200 as _impl
 
-_ALIASES = ("dtypes", "env_variables", "config", "utils", "mx_tensor", "ops", "mx_gemm", "attention_ops", "quant_api", "layers", "layers.mx_linear", "layers.packed_linear", "layers.mx_llama_attention", "layers.tp_linear")
+_ALIASES = ("dtypes", "env_variables", "config", "utils", "mx_tensor", "ops", "mx_gemm", "attention_ops", "mlp_ops", "quant_api", "layers", "layers.mx_linear", "layers.packed_linear", "layers.mx_llama_attention", "layers.tp_linear")
 for _name in _ALIASES:
     try:
         sys.modules[f"{__name__}.{_name}"] = importlib.import_module(f"torchmx_b200.{_name}")

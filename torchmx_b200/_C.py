@@ -15,7 +15,7 @@ FLAG_HW_EXACT = 1
 MAX_DIMS = 6
 
 EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
-           "mxq_softmax_quantize", "mxq_last_error", "mxq_version", "mxq_arch")
+           "mxq_softmax_quantize", "mxq_silu_mul_quantize", "mxq_last_error", "mxq_version", "mxq_arch")
 
 
 class GemmArgs(ctypes.Structure):
@@ -81,6 +81,8 @@ def lib() -> ctypes.CDLL:
         L.mxq_pack_operand.argtypes = [vp, i32, i64, vp, i32, vp]
         L.mxq_unpack_operand.restype = i32
         L.mxq_unpack_operand.argtypes = [vp, i32, i64, vp, i32, vp]
+        L.mxq_silu_mul_quantize.restype = i32
+        L.mxq_silu_mul_quantize.argtypes = [vp, vp, i64, i64, i64, i64, i32, u32, vp, vp, i32, vp]
         L.mxq_softmax_quantize.restype = i32
         L.mxq_softmax_quantize.argtypes = [ctypes.POINTER(SoftmaxArgs), i32, vp]
         if L.mxq_arch() != 1000:

@@ -16,6 +16,7 @@ cudaError_t launch_transcode(const void*, int, int64_t, void*, int, cudaStream_t
 cudaError_t launch_pack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 cudaError_t launch_unpack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 int launch_gemm(const mxq_gemm_args_t*, int, cudaStream_t, char*, size_t);
+cudaError_t launch_silu_mul_quantize(const void*, const void*, int64_t, int64_t, int64_t, int64_t, int, unsigned, void*, uint8_t*, int, cudaStream_t);
 int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size_t);
 }  // namespace mxq
 
@@ -182,6 +183,20 @@ int mxq_gemm(const mxq_gemm_args_t* a, int device, void* stream) {
     char msg[400] = "";
     const int rc = mxq::launch_gemm(a, sm_count_of(scope.cur), (cudaStream_t)stream, msg, sizeof(msg));
     return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_gemm: %s", msg);
+}
+
+int mxq_silu_mul_quantize(const void* gate, const void* up, int64_t rows, int64_t cols, int64_t ld_gate, int64_t ld_up, int elem, unsigned flags,
+                          void* codes, uint8_t* scales, int device, void* stream) {
+    if (!valid_elem(elem)) return fail(MXQ_ERR_INVALID, "mxq_silu_mul_quantize: unknown element type %d", elem);
+    if (rows < 0 || cols < 0) return fail(MXQ_ERR_INVALID, "mxq_silu_mul_quantize: negative extent");
+    if (rows == 0 || cols == 0) return MXQ_OK;
+    if (!gate || !up || !codes || !scales) return fail(MXQ_ERR_INVALID, "mxq_silu_mul_quantize: null pointer");
+    if (cols % 32 || ld_gate < cols || ld_up < cols || (ld_gate % 16) || (ld_up % 16) || ((uintptr_t)gate % 32) || ((uintptr_t)up % 32) || ((uintptr_t)codes % 32))
+        return fail(MXQ_ERR_UNSUPPORTED_SHAPE, "mxq_silu_mul_quantize: needs cols %% 32 == 0 and 32-byte aligned rows (base pointers, row strides %% 16 elements)");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_silu_mul_quantize: selecting device");
+    const cudaError_t e = mxq::launch_silu_mul_quantize(gate, up, rows, cols, ld_gate, ld_up, elem, flags, codes, scales, sm_count_of(scope.cur), (cudaStream_t)stream);
+    return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_silu_mul_quantize: launch");
 }
 
 int mxq_softmax_quantize(const mxq_softmax_args_t* a, int device, void* stream) {

@@ -21,7 +21,7 @@ from typing import Optional, Tuple
 import torch
 from torch import nn
 
-from .. import attention_ops
+from .. import attention_ops, mlp_ops
 from ..config import QAttentionConfig, QLinearConfig
 from ..mx_tensor import MXTensor
 from .mx_linear import MXInferenceLinear
@@ -93,10 +93,15 @@ STACKED_MAX_ROWS = 128  # measured on Llama-8B: decode 10.1 -> 9.8 ms/step stack
 #                         one launch per projection
 
 
-def _fused_still_valid(fused: Optional[MXInferenceLinear], mods, x: torch.Tensor) -> bool:
+# gate/up feed K1b, which reads the two column slices in place: no strided follow-up kernels, so the MLP stacks at every size
+# (Llama-8B prefill 27.0 -> 26.4 ms)
+MLP_STACKED_MAX_ROWS = int(os.environ.get("MXQ_MLP_STACKED_MAX_ROWS", 1 << 30))
+
+
+def _fused_still_valid(fused: Optional[MXInferenceLinear], mods, x: torch.Tensor, max_rows: int = 0) -> bool:
     """the stacked layer is used for decode-sized activations, and only while the source layers still alias it (a later
     .to(device) / weight swap re-materialises them separately)"""
-    if fused is None or fused.weight._data.device != x.device or x.numel() > STACKED_MAX_ROWS * x.shape[-1]:
+    if fused is None or fused.weight._data.device != x.device or x.numel() > (max_rows or STACKED_MAX_ROWS) * x.shape[-1]:
         return False
     row = 0
     base, es = fused.weight._data.data_ptr(), fused.weight._data.stride(0)
@@ -146,13 +151,24 @@ class _MXMLPMixin:
         object.__setattr__(new, "_gate_up", _fuse_linears([new.gate_proj, new.up_proj]) if FUSE_PROJECTIONS else None)
         return new
 
+    def _gated(self, gate, up):
+        """act_fn(gate) * up, handed to down_proj -- for SiLU as the already quantized MXTensor (K1b: gating + quantization in one
+        launch, bit-identical to silu, mul and K1), otherwise as the bf16 product"""
+        if type(self.act_fn).__name__ in ("SiLU", "SiLUActivation") and isinstance(self.down_proj, MXInferenceLinear):
+            ac = self.down_proj.qconfig.activations_config
+            h = mlp_ops.silu_mul_to_mx(gate, up, ac.elem_dtype, ac.block_size)
+            if h is not None:
+                return h
+        return self.act_fn(gate) * up
+
     def forward(self, x):
         fused = self.__dict__.get("_gate_up")
-        if _fused_still_valid(fused, (self.gate_proj, self.up_proj), x):
+        if _fused_still_valid(fused, (self.gate_proj, self.up_proj), x, MLP_STACKED_MAX_ROWS):
             gate, up = fused(x).split(fused._split, dim=-1)  # one launch for both projections
-            return self.down_proj(self.act_fn(gate) * up)
-        x_in = self.gate_proj.prepare_input(x)  # gate and up read the same activation: quantize it once
-        return self.down_proj(self.act_fn(self.gate_proj(x_in)) * self.up_proj(x_in))
+        else:
+            x_in = self.gate_proj.prepare_input(x)  # gate and up read the same activation: quantize it once
+            gate, up = self.gate_proj(x_in), self.up_proj(x_in)
+        return self.down_proj(self._gated(gate, up))
 
 
 class _MXAttentionMixin:
