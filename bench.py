@@ -236,6 +236,23 @@ def mx_matmul_extras(dev):
     w_bytes = 14336 * 4096 * (1 + 1 / 32) + 32 * 4096 * (1 + 1 / 32) + 32 * 14336 * 2
     out["linear_32x14336x4096_decode"] = {"us": round(us_med, 1), "us_best": round(us_min, 1), "GB/s": round(w_bytes / us_med / 1e3, 1),
                                           "bound": "hbm (weight codes + scales read once)"}
+    del X, W
+    # (4) the chain between the two attention matmuls as one kernel (K4a): scale + causal rule + softmax + to_mx(P, e4m3)
+    from torchmx_b200 import attention_ops, mlp_ops
+    scores = (torch.randn(1, 32, 2048, 2048, device=dev, generator=gen) * 11).to(torch.bfloat16)
+    us_min, us_med = timed(lambda: attention_ops.softmax_to_mx(scores, 128 ** -0.5, None, True, dtypes.float8_e4m3, BLOCK))
+    n_el = 32 * 2048 * 2048
+    out["softmax_to_mx_1x32x2048x2048_causal"] = {"us": round(us_med, 1), "us_best": round(us_min, 1),
+                                                  "GB/s_all_blocks": round(n_el * (3 + 1 / 32) / us_med / 1e3, 1),
+                                                  "GB/s_moved": round(n_el * (1 + 1 + 1 / 32) / us_med / 1e3, 1),
+                                                  "bound": "instruction issue (exact expf / divide per visible element), see DESIGN.md K4a"}
+    del scores
+    # (5) SwiGLU gating + quantization of down_proj's input (K1b) on a 2048-token Llama-3-8B MLP activation
+    gate_up = torch.randn(2048, 2 * 14336, device=dev, dtype=torch.bfloat16, generator=gen)
+    g_, u_ = gate_up.split([14336, 14336], dim=-1)
+    us_min, us_med = timed(lambda: mlp_ops.silu_mul_to_mx(g_, u_, dtypes.float8_e4m3, BLOCK))
+    out["silu_mul_to_mx_2048x14336"] = {"us": round(us_med, 1), "us_best": round(us_min, 1),
+                                        "GB/s": round(2048 * 14336 * (5 + 1 / 32) / us_med / 1e3, 1), "bound": "hbm (2 + 2 + 1 + 1/32 B per element)"}
     out["tensor_core_calls"] = mx_gemm.stats["tensor_core"] - before["tensor_core"]
     out["fallback_calls"] = mx_gemm.stats["fallback"] - before["fallback"]
     return out

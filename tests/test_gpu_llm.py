@@ -54,8 +54,8 @@ def test_quantize_llm_swaps_blocks_and_matches_the_dequantize_path(tiny_llama, q
     with torch.no_grad():
         out_tc = qm(input_ids=ids).logits
     n_mm = mx_gemm.stats["tensor_core"] - before["tensor_core"]
-    # 2 layers x (4 projections + 3 MLP linears) + lm_head, plus 2 attention contractions per layer when Q/K/V are quantized
-    assert n_mm == 15 + (4 if qkv else 0) and mx_gemm.stats["fallback"] == before["fallback"]
+    # 2 layers x (4 projections + stacked gate/up + down) + lm_head, plus 2 attention contractions per layer when Q/K/V are quantized
+    assert n_mm == 13 + (4 if qkv else 0) and mx_gemm.stats["fallback"] == before["fallback"]
     mx_gemm.set_enabled(False)
     try:
         with torch.no_grad():
@@ -121,7 +121,7 @@ def test_quantize_llm_qwen2_with_projection_biases():
     before, soft0 = dict(mx_gemm.stats), attention_ops.stats["fused_softmax"]
     with torch.no_grad():
         out_tc = qm(input_ids=ids).logits
-    assert mx_gemm.stats["tensor_core"] - before["tensor_core"] == 19 and mx_gemm.stats["fallback"] == before["fallback"]
+    assert mx_gemm.stats["tensor_core"] - before["tensor_core"] == 17 and mx_gemm.stats["fallback"] == before["fallback"]
     assert attention_ops.stats["fused_softmax"] == soft0 + 2
     mx_gemm.set_enabled(False)
     try:
