@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
                                                               const Params p) {
     using L = SmemLayout<BLOCK_N, STAGES>;
     constexpr int SF_COLS_A = 4, SF_COLS_B = BLOCK_N / 32;
-    constexpr int TMEM_COLS = (BLOCK_N + SF_COLS_A + SF_COLS_B) <= 256 ? 256 : 512;
+    // two scale-factor buffers in TMEM: the tcgen05.cp of K block k+1 must not wait for the MMAs of K block k to finish
+    // reading theirs (measured on 1024 x 1024 x 8192, one tile per CTA: 296 -> 241 ns per K block)
+    constexpr int SF_BUF = SF_COLS_A + SF_COLS_B;
+    constexpr int TMEM_COLS = (BLOCK_N + 2 * SF_BUF) <= 256 ? 256 : 512;
     constexpr uint32_t TM_SFA = BLOCK_N, TM_SFB = BLOCK_N + SF_COLS_A;
 
     extern __shared__ uint8_t smem_raw[];
@@ -109,28 +112,29 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_kernel(const __grid_const
     } else if (warp == 1) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N) | p.idesc_fmt;
-        uint32_t stage = 0, phase = 0, acc_phase = 0;
+        uint32_t stage = 0, phase = 0, acc_phase = 0, sf_sel = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             mbar_wait(tmem_empty, acc_phase ^ 1);
             tc_fence_after();
-            for (int kb = 0; kb < k_blocks; ++kb) {
+            for (int kb = 0; kb < k_blocks; ++kb, sf_sel ^= 1) {
                 mbar_wait(&full[stage], phase);
                 mbar_wait(&sf_full[stage], phase);
                 tc_fence_after();
                 if (elect_one()) {
+                    const uint32_t tm_sfa = tmem_base + TM_SFA + sf_sel * SF_BUF, tm_sfb = tmem_base + TM_SFB + sf_sel * SF_BUF;
                     const uint32_t a_addr = smem_u32(smem + L::OFF_A + stage * L::A_STAGE);
                     const uint32_t b_addr = smem_u32(smem + L::OFF_B + stage * L::B_STAGE);
                     const uint32_t sfa_addr = smem_u32(smem + L::OFF_SFA + stage * L::SFA_STAGE);
                     const uint32_t sfb_addr = smem_u32(smem + L::OFF_SFB + stage * L::SFB_STAGE);
-                    tc_copy_sf(tmem_base + TM_SFA, smem_desc(sfa_addr, 128, kLayoutNone));
+                    tc_copy_sf(tm_sfa, smem_desc(sfa_addr, 128, kLayoutNone));
 #pragma unroll
-                    for (int i = 0; i < BLOCK_N / 128; ++i) tc_copy_sf(tmem_base + TM_SFB + 4 * i, smem_desc(sfb_addr + 512 * i, 128, kLayoutNone));
+                    for (int i = 0; i < BLOCK_N / 128; ++i) tc_copy_sf(tm_sfb + 4 * i, smem_desc(sfb_addr + 512 * i, 128, kLayoutNone));
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // K-major SW128 tile: 8-row groups are 1024 B apart; advancing K inside the swizzle row = +32 B
                         const uint64_t da = smem_desc(a_addr + k * UMMA_K, 1024, kLayoutSw128);
                         const uint64_t db = smem_desc(b_addr + k * UMMA_K, 1024, kLayoutSw128);
-                        tc_mma_mx(tmem_base, da, db, idesc_with_sf(idesc, k, k), (kb | k) != 0, tmem_base + TM_SFA, tmem_base + TM_SFB);
+                        tc_mma_mx(tmem_base, da, db, idesc_with_sf(idesc, k, k), (kb | k) != 0, tm_sfa, tm_sfb);
                     }
                     tc_commit(&empty[stage]);
                     if (kb == k_blocks - 1) tc_commit(tmem_full);
@@ -719,7 +723,7 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
     const int force_narrow = getenv("MXQ_GEMM_NARROW") ? atoi(getenv("MXQ_GEMM_NARROW")) : 0;  // developer knobs, re-read per call
     const int cfg = getenv("MXQ_GEMM_CFG") ? atoi(getenv("MXQ_GEMM_CFG")) : 0;  // developer knob: <BLOCK_N><STAGES>, 2<STAGES> = CTA pair
     // Under-filled grids: when the 256x256 pair tiles would occupy at most a quarter of the SM pairs, 128x128 tiles spread the
-    // same work over 4x as many SMs (measured, K = 4096: 2048x1024 16.8 -> 15.1 us, 1024x1024 16.6 -> 14.5, 512x4096 17.1 -> 15.2).
+    // same work over 4x as many SMs (measured, K = 4096, before / after: 2048x1024 16.8 -> 13.9 us, 1024x1024 16.6 -> 12.8, 512x4096 17.1 -> 13.7).
     // MXQ_GEMM_NARROW=-1 switches the rule off.
     const int64_t pair_tiles = ((a->M + 255) / 256) * ((a->N + 255) / 256) * a->batch;
     const bool underfilled = force_narrow >= 0 && a->M > 128 && a->N > 128 && pair_tiles * 4 <= sm_count && a->d_multicast == nullptr;
