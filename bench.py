@@ -253,6 +253,33 @@ def mx_matmul_extras(dev):
     us_min, us_med = timed(lambda: mlp_ops.silu_mul_to_mx(g_, u_, dtypes.float8_e4m3, BLOCK))
     out["silu_mul_to_mx_2048x14336"] = {"us": round(us_med, 1), "us_best": round(us_min, 1),
                                         "GB/s": round(2048 * 14336 * (5 + 1 / 32) / us_med / 1e3, 1), "bound": "hbm (2 + 2 + 1 + 1/32 B per element)"}
+    del gate_up, g_, u_
+    # (6) SURVEY 8(d) config 2 side conditions: the quantize / dequantize times must not depend on the value distribution
+    # (plain N(0,1); per-block exponents spread over 2^+-40; every bf16 bit pattern incl. NaN / Inf / subnormals), plus the
+    # fp32 dequantize target and the float8_e5m2 extension element type.  16384 x 16384, CUDA-graph replay of 4 launches.
+    R = C = 16384
+    n_el = R * C
+    dist = {}
+    x0 = torch.randn(R, C, device=dev, dtype=torch.bfloat16, generator=gen)
+    variants = {"normal": lambda: x0,
+                "wide_2^+-40_per_block": lambda: (x0.view(R, C // 32, 32) * torch.exp2(torch.randint(-40, 41, (R, C // 32, 1), device=dev, generator=gen).float()).to(torch.bfloat16)).view(R, C),
+                "all_bf16_bit_patterns": lambda: torch.arange(n_el, device=dev, dtype=torch.int32).bitwise_and_(0xFFFF).to(torch.int16).view(torch.bfloat16).view(R, C)}
+    for name, make in variants.items():
+        x = make().contiguous()
+        _, q_us = timed(lambda: MXTensor.to_mx(x, dtypes.float8_e4m3, BLOCK), n=4, rounds=3)
+        m = MXTensor.to_mx(x, dtypes.float8_e4m3, BLOCK)
+        _, d_us = timed(lambda: m.to_dtype(torch.bfloat16), n=4, rounds=3)
+        dist[name] = {"to_mx_e4m3_us": round(q_us, 1), "to_dtype_bf16_us": round(d_us, 1), "GB/s": [round(n_el * (3 + 1 / 32) / q_us / 1e3, 1), round(n_el * (3 + 1 / 32) / d_us / 1e3, 1)]}
+        del x, m
+    out["value_distribution_independence_16384x16384"] = dist
+    m8, m4 = MXTensor.to_mx(x0, dtypes.float8_e4m3, BLOCK), MXTensor.to_mx(x0, dtypes.float4_e2m1, BLOCK)
+    _, us8 = timed(lambda: m8.to_dtype(torch.float32), n=4, rounds=3)
+    _, us4 = timed(lambda: m4.to_dtype(torch.float32), n=4, rounds=3)
+    out["to_dtype_fp32_16384x16384"] = {"float8_e4m3": {"us": round(us8, 1), "GB/s": round(n_el * (5 + 1 / 32) / us8 / 1e3, 1)},
+                                        "float4_e2m1": {"us": round(us4, 1), "GB/s": round(n_el * (4.5 + 1 / 32) / us4 / 1e3, 1)}}
+    del m8, m4
+    _, us5 = timed(lambda: MXTensor.to_mx(x0, dtypes.float8_e5m2, BLOCK), n=4, rounds=3)
+    out["to_mx_float8_e5m2_extension_16384x16384"] = {"us": round(us5, 1), "GB/s": round(n_el * (3 + 1 / 32) / us5 / 1e3, 1), "parity": "unpinned (element type absent from the reference)"}
     out["tensor_core_calls"] = mx_gemm.stats["tensor_core"] - before["tensor_core"]
     out["fallback_calls"] = mx_gemm.stats["fallback"] - before["fallback"]
     return out
