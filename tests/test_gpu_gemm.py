@@ -66,6 +66,11 @@ CASES = [
     (128, 7168, 1024, "float8_e4m3", "float6_e3m2", False, 0, 0),
     (5, 2048, 7168, "float8_e4m3", "float6_e3m2", True, 0, 0),
     (8, 640, 384, "float8_e4m3", "float8_e4m3", False, 0, 0),
+    # small grids with a long K loop (M > 128): 128 x 128 tiles of the single-CTA kernel (under-filled pair grid)
+    (300, 384, 4096, "float8_e4m3", "float6_e3m2", True, 0, 6),
+    (257, 129, 2048, "float8_e4m3", "float4_e2m1", True, 0, 0),
+    (1024, 1024, 4096, "float8_e4m3", "float6_e3m2", False, 0, 10),
+    (640, 200, 8192, "float6_e2m3", "float8_e5m2", False, 0, 0),
     # float8_e5m2 (labelled extension element type) as a native one-byte operand, all three kernels
     (300, 520, 640, "float8_e5m2", "float6_e3m2", True, 0, 10),
     (48, 1000, 512, "float8_e4m3", "float8_e5m2", False, 0, 0),
