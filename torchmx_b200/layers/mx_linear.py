@@ -71,6 +71,14 @@ class MXInferenceLinear(torch.nn.Linear):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         ac = self.qconfig.activations_config
         bias = self.bias
+        if torch.compiler.is_compiling():
+            # under torch.compile the layer is what the reference's is (mx_linear.py:61-95): quantize, then the aten.linear
+            # override on two MXTensors -- ops the tracer knows (custom ops with fake kernels); the direct launches below
+            # are host code it cannot see through
+            if not isinstance(self.weight, MXTensor) and bias is not None:
+                bias = bias.to(torch.bfloat16)
+            x_mx = x if isinstance(x, MXTensor) else MXTensor.to_mx(x, ac.elem_dtype, ac.block_size)
+            return F.linear(x_mx, self._weight_mx(), bias)
         if isinstance(x, MXTensor):  # already quantized by the owning block (prepare_input)
             assert x._elem_dtype == ac.elem_dtype and x._block_size == ac.block_size, "activation was quantized with another config"
             if not isinstance(self.weight, MXTensor) and bias is not None:

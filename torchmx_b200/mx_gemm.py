@@ -115,7 +115,9 @@ def _rows_k(t: MXTensor, k_dim_from_end: int):
 
 
 def _qualifies(t: MXTensor) -> bool:
-    return (isinstance(t, MXTensor) and (t._elem_dtype in dtypes.SUPPORTED_FP_ELEM_DTYPES or t._elem_dtype == dtypes.float8_e5m2) and t._block_size == 32 and t._padding == 0
+    # (plain inner tensors only: while torch.compile / AOT autograd trace through the subclass the inner tensors are fake or
+    # functional wrappers without storage -- the override then takes the dequantize path, whose custom op has a fake kernel)
+    return (isinstance(t, MXTensor) and type(t._data) is torch.Tensor and type(t._scale_e8m0) is torch.Tensor and (t._elem_dtype in dtypes.SUPPORTED_FP_ELEM_DTYPES or t._elem_dtype == dtypes.float8_e5m2) and t._block_size == 32 and t._padding == 0
             and t._data.is_cuda and t._orig_dtype == torch.bfloat16)
 
 
@@ -143,7 +145,7 @@ def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs
 
 def try_tensor_core(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back, count_fallback: bool = True) -> Optional[torch.Tensor]:
     out = None
-    if not _DISABLED and _qualifies(a) and _qualifies(b):
+    if not _DISABLED and not torch.compiler.is_compiling() and _qualifies(a) and _qualifies(b):
         out = _dispatch(aten_op, a, b, extra_front, extra_back)
     if out is not None:
         stats["tensor_core"] += 1
@@ -240,7 +242,7 @@ def linear_fused_act_quant(x: torch.Tensor, w: MXTensor, bias, hw_exact: bool) -
     with the quantization done inside the weight-streaming kernel (bit-identical to the two-launch path).  Returns None when
     the operands do not qualify; the caller then quantizes with K1 and goes through `try_tensor_core`."""
     global _fused_out
-    if _DISABLED or not _FUSED_ACT or type(x) is not torch.Tensor or not x.is_cuda or x.dtype != torch.bfloat16 or not _qualifies(w):
+    if _DISABLED or not _FUSED_ACT or torch.compiler.is_compiling() or type(x) is not torch.Tensor or not x.is_cuda or x.dtype != torch.bfloat16 or not _qualifies(w):
         return None
     K = x.shape[-1]
     if w._data.dim() != 2 or w._block_dim != 1 or K % 128 != 0 or w.shape[-1] != K or not x.is_contiguous():

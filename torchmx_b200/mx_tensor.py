@@ -301,7 +301,7 @@ class MXTensor(torch.Tensor):
     # --- user API -----------------------------------------------------------------------------
     def to_dtype(self, target_dtype: torch.dtype) -> torch.Tensor:
         """Dequantize to `target_dtype` (bfloat16 or float32); reference: mx_tensor.py:456-472."""
-        if not torch.is_grad_enabled() and self._data.is_cuda and not torch.compiler.is_compiling():
+        if not torch.is_grad_enabled() and type(self._data) is torch.Tensor and self._data.is_cuda and not torch.compiler.is_compiling():
             return FromMXConstrFunc.forward(None, self, target_dtype, _op=_dequantize_mx_impl)  # inference fast path, see to_mx
         return FromMXConstrFunc.apply(self, target_dtype)
 
@@ -322,7 +322,7 @@ class MXTensor(torch.Tensor):
 
     def __repr__(self):
         s = f"MXTensor: _elem_dtype: {self._elem_dtype}, _scale_e8m0: {self._scale_e8m0}, _data: {self._data}"
-        if self._data.is_cuda:
+        if type(self._data) is torch.Tensor and self._data.is_cuda:  # (not while tracing: fake / functional inner tensors)
             s += f", d_hp: {self.to_dtype(self._orig_dtype)}"
         if self._padding > 0:
             s += f", padding: {self._padding}"
