@@ -384,3 +384,75 @@ def test_pack_linear_on_a_model_and_what_it_leaves_alone():
         w = model.state_dict()[k]
         assert torch.equal(w._data, codes) and torch.equal(w._scale_e8m0, scales)
     assert torch.equal(model(x), want)
+
+
+# ---- special values (reference: tests/layers/test_mx_linear.py:117-175, tests/test_mx_tensor.py:102-160, :243-263) --------------
+@pytest.mark.parametrize("M,N,K,rule", [(4, 384, 256, "auto"), (64, 1000, 1024, "auto"), (200, 300, 256, "auto"), (300, 520, 384, "pair"),
+                                        (300, 520, 384, "auto")])
+@pytest.mark.parametrize("bias", [False, True])
+def test_nan_and_inf_blocks_poison_the_same_outputs_as_the_dequantize_path(mx, monkeypatch, M, N, K, rule, bias):
+    """an Inf / NaN anywhere in a 32-block gives that block the NaN scale (255); the reference then dequantizes the whole block to
+    NaN and every output that contracts over it is NaN.  The block-scaled MMA must agree (E8M0 0xFF is NaN in hardware too)."""
+    if rule == "pair":
+        monkeypatch.setenv("MXQ_GEMM_NARROW", "-1")
+    from torchmx import dtypes, mx_gemm
+    from torchmx.mx_tensor import MXTensor
+    g = torch.Generator(device=DEV).manual_seed(5)
+    a = torch.randn(M, K, device=DEV, dtype=torch.bfloat16, generator=g)
+    w = torch.randn(N, K, device=DEV, dtype=torch.bfloat16, generator=g)
+    a[1, 3] = float("inf")
+    a[2, K - 1] = float("-inf")
+    a[3, 40] = float("nan")
+    w[5, 70] = float("nan")
+    w[N - 1, 0] = float("inf")
+    b = torch.randn(N, device=DEV, dtype=torch.bfloat16, generator=g) if bias else None
+    A, W = MXTensor.to_mx(a, dtypes.float8_e4m3, 32), MXTensor.to_mx(w, dtypes.float6_e3m2, 32)
+    n0 = mx_gemm.stats["tensor_core"]
+    out = torch.nn.functional.linear(A, W, b)
+    assert mx_gemm.stats["tensor_core"] == n0 + 1
+    mx_gemm.set_enabled(False)
+    try:
+        ref = torch.nn.functional.linear(A, W, b)
+    finally:
+        mx_gemm.set_enabled(True)
+    want_nan = torch.zeros(M, N, dtype=torch.bool, device=DEV)
+    want_nan[1:4] = True
+    want_nan[:, 5] = True
+    want_nan[:, N - 1] = True
+    assert torch.equal(torch.isnan(ref), want_nan)
+    assert torch.equal(torch.isnan(out), want_nan)
+    ok = ~want_nan
+    assert (out[ok].float() - ref[ok].float()).abs().max().item() <= 2.0 ** -6 * ref[ok].float().abs().max().item()
+
+
+@pytest.mark.parametrize("elem", ["float8_e4m3", "float6_e3m2", "float6_e2m3", "float4_e2m1", "int8"])
+@pytest.mark.parametrize("hp_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("padding", [0, 3])
+def test_cast_autograd_is_a_pass_through(mx, elem, hp_dtype, padding):
+    """reference tests/test_mx_tensor.py:243-263: to_mx / to_dtype are identity in the backward pass"""
+    from torchmx import dtypes
+    from torchmx.mx_tensor import MXTensor
+    et = dtypes.STR_TO_ELEM_DTYPE[elem]
+    x = torch.arange(8 + padding, device=DEV, dtype=torch.bfloat16).requires_grad_()
+    grad = torch.arange(8 + padding, device=DEV, dtype=torch.bfloat16) * 0.5
+    x_dq = MXTensor.to_mx(x, et, 8).to_dtype(hp_dtype)
+    if et == dtypes.float4_e2m1 and padding > 0:
+        with pytest.raises(ValueError):
+            x_dq.backward(gradient=grad)
+    else:
+        x_dq.backward(gradient=grad)
+        assert torch.equal(grad, x.grad)
+
+
+@pytest.mark.parametrize("elem,floor", [("float8_e4m3", 19.0), ("int8", 38.0), ("float6_e3m2", 14.0), ("float6_e2m3", 14.0), ("float4_e2m1", 14.0)])
+@pytest.mark.parametrize("shape,block", [((128, 128), 32), ((4, 6, 64), 16), ((2, 2, 8, 96), 8), ((1024,), 32), ((3, 70), 7)])
+def test_round_trip_sqnr_floors(mx, elem, floor, shape, block):
+    """reference tests/test_mx_tensor.py:59-100: SQNR of to_mx -> to_dtype per element type"""
+    from torchmx import dtypes
+    from torchmx.mx_tensor import MXTensor
+    x = torch.randn(*shape, device=DEV, dtype=torch.bfloat16)
+    y = MXTensor.to_mx(x, dtypes.STR_TO_ELEM_DTYPE[elem], block).to_dtype(torch.bfloat16)
+    sqnr = float(20 * torch.log10(x.float().norm() / (x.float() - y.float()).norm()))
+    assert sqnr >= floor, sqnr
+    z = MXTensor.to_mx(torch.zeros_like(x), dtypes.STR_TO_ELEM_DTYPE[elem], block).to_dtype(torch.bfloat16)
+    assert torch.equal(z, torch.zeros_like(x))
