@@ -129,7 +129,7 @@ def run(args) -> dict:
     # ---- prefill: one prompt of `prefill` tokens, fresh static cache each run -------------------------------
     P = args.prefill
     ids = torch.randint(0, cfg.vocab_size, (1, P), device=dev)
-    cache = StaticCache(config=cfg, max_cache_len=-(-(P + 8) // 128) * 128)  # multiple of 128: the MX attention contractions need it
+    cache = StaticCache(config=cfg, max_cache_len=-(-(P + 8) // 128) * 128 if args.mx_attention else P + 8)  # MX attention contractions need a multiple of 128
 
     def prefill():
         set_len(cache, 0)
@@ -152,7 +152,7 @@ def run(args) -> dict:
 
     # ---- decode: batch B, KV cache pre-filled with `ctx` tokens per sequence -----------------------------
     B, ctx, steps = args.batch, args.ctx, args.steps
-    cache = StaticCache(config=cfg, max_cache_len=-(-(ctx + steps + 8) // 128) * 128)
+    cache = StaticCache(config=cfg, max_cache_len=-(-(ctx + steps + 8) // 128) * 128 if args.mx_attention else ctx + steps + 8)
     prompt = torch.randint(0, cfg.vocab_size, (B, ctx), device=dev)
     model(input_ids=prompt, past_key_values=cache, use_cache=True)
     tok = torch.randint(0, cfg.vocab_size, (B, 1), device=dev)
