@@ -131,6 +131,24 @@ def test_quantize_llm_qwen2_with_projection_biases():
         mx_gemm.set_enabled(True)
     assert _sqnr(out_deq, out_tc) > 30, _sqnr(out_deq, out_tc)
     assert _sqnr(ref, out_tc) > 12, _sqnr(ref, out_tc)
+    # decode-sized input: q/k/v (with their biases) and gate/up run as one stacked launch each; same result as separate launches
+    from torchmx.layers import mx_llama_attention as mla
+    att = layer.self_attn
+    assert att.__dict__["_qkv"] is not None and att.__dict__["_qkv"].bias is not None
+    assert att.k_proj.bias.data_ptr() == att.__dict__["_qkv"].bias[att.q_proj.out_features:].data_ptr()
+    ids8 = ids[:, :4]
+    n0 = mx_gemm.stats["tensor_core"]
+    with torch.no_grad():
+        stacked = qm(input_ids=ids8).logits
+    # per layer qkv, o, gate_up, down + the Q.K^T bmm (P.V contracts over 4 padded positions: dequantize path), then lm_head
+    assert mx_gemm.stats["tensor_core"] - n0 == 2 * 4 + 2 + 1
+    prev, mla.STACKED_MAX_ROWS, mla.MLP_STACKED_MAX_ROWS = (mla.STACKED_MAX_ROWS, mla.MLP_STACKED_MAX_ROWS), -1, -1
+    try:
+        with torch.no_grad():
+            separate = qm(input_ids=ids8).logits
+    finally:
+        mla.STACKED_MAX_ROWS, mla.MLP_STACKED_MAX_ROWS = prev
+    assert _sqnr(separate, stacked) > 35, _sqnr(separate, stacked)
 
 
 def test_stacked_projections_match_separate_launches(tiny_llama):

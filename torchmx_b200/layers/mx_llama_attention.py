@@ -78,11 +78,15 @@ def _fuse_linears(mods) -> Optional[MXInferenceLinear]:
     if mods[0].bias is None:
         fused.register_parameter("bias", None)
     else:
+        if any(m.bias.dtype != torch.bfloat16 or m.bias.device != codes.device for m in mods):
+            return None
         fused.bias = nn.Parameter(torch.cat([m.bias.data for m in mods], 0), requires_grad=False)
     row = 0
-    for m, w in zip(mods, ws):  # re-point the source layers at their slice of the stacked storage
+    for m, w in zip(mods, ws):  # re-point the source layers at their slice of the stacked storage (weights and biases alike)
         n = w.shape[0]
         m.weight = nn.Parameter(MXTensor(scales[row:row + n], codes[row:row + n], w._elem_dtype, w._block_size, w._orig_dtype), requires_grad=False)
+        if fused.bias is not None:
+            m.bias = nn.Parameter(fused.bias.data[row:row + n], requires_grad=False)
         row += n
     fused._split = [w.shape[0] for w in ws]
     return fused
@@ -108,6 +112,8 @@ def _fused_still_valid(fused: Optional[MXInferenceLinear], mods, x: torch.Tensor
     for m, n in zip(mods, fused._split):
         w = m.weight
         if not isinstance(w, MXTensor) or w._data.data_ptr() != base + row * es or w.shape[0] != n:
+            return False
+        if (m.bias is None) != (fused.bias is None) or (m.bias is not None and m.bias.data_ptr() != fused.bias.data_ptr() + row * fused.bias.element_size()):
             return False
         row += n
     return True
