@@ -62,7 +62,7 @@ def set_packed_operands(flag: bool) -> None:
     _USE_PACKED = bool(flag)
 
 
-def _operand_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[MXTensor]):
+def _operand_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[MXTensor], packed: Optional[bool] = None):
     """codes: [..., rows, Kb] reference-layout element codes with unit stride along Kb -> (uint8 operand tensor, format).
 
     float8_e4m3 passes through untouched (a view).  fp4 / fp6 codes become the packed 4 / 6-bit streams the sm_100a TMA
@@ -75,7 +75,7 @@ def _operand_rows(codes: torch.Tensor, elem: dtypes.DType, cache_on: Optional[MX
         return codes, FMT_E4M3_BYTES
     if elem == dtypes.float8_e5m2:  # labelled extension element type: one byte per element, native MMA format
         return codes, FMT_E5M2_BYTES
-    fmt = _PACKED_FORMAT[elem.name] if _USE_PACKED else FMT_E4M3_BYTES
+    fmt = _PACKED_FORMAT[elem.name] if (_USE_PACKED if packed is None else packed) else FMT_E4M3_BYTES
     key = None
     if cache_on is not None:
         key = (codes.data_ptr(), tuple(codes.shape), tuple(codes.stride()), cache_on._data._version, fmt)
@@ -283,13 +283,7 @@ def pack_weight(w: MXTensor):
     the tensor-core path at all (a packed-only layer has no dequantize path to fall back to)."""
     if not _qualifies(w) or w._data.dim() != 2 or w._block_dim != 1 or w.shape[-1] % 128 != 0 or not w._data.is_contiguous():
         return None
-    prev, packed = _USE_PACKED, None
-    set_packed_operands(True)
-    try:
-        packed = _operand_rows(w._data, w._elem_dtype, None)
-    finally:
-        set_packed_operands(prev)
-    return packed
+    return _operand_rows(w._data, w._elem_dtype, None, packed=True)
 
 
 def unpack_weight(packed: torch.Tensor, fmt: int, elem: dtypes.DType) -> torch.Tensor:
