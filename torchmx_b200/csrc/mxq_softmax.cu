@@ -44,6 +44,11 @@ __device__ __forceinline__ float max_nan(float a, float b) {
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
+__device__ __forceinline__ float max_nan3(float a, float b, float c) {  // FMNMX3.NAN: one issue slot for two comparisons
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
 
 template <int ELEM, int MAXT>
 __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxParams p) {
@@ -131,17 +136,18 @@ __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxPar
             for (int i = 0; i < 32; ++i)
                 if (i >= vis) x[i] = -INFINITY;
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = -INFINITY;
     }
 
     // ---- row max ---------------------------------------------------------------------------------------------------
     // NaN-propagating max: a NaN score makes row_max NaN, every exp(x - NaN) NaN and the whole row NaN -- the same outcome
     // as the unfused softmax (whose max drops NaNs but whose sum picks them up).
-    float m = x[0];
+    float m = -INFINITY;  // a block the query row cannot see at all (vis == 0) never touches x[]
+    if (vis > 0) {
+        m = x[0];
 #pragma unroll
-    for (int i = 1; i < 32; ++i) m = max_nan(m, x[i]);
+        for (int i = 1; i < 31; i += 2) m = max_nan3(m, x[i], x[i + 1]);
+        m = max_nan(m, x[31]);
+    }
     auto row_reduce = [&](float v, bool is_max) -> float {
         if (layout == 0) {
             float acc = is_max ? -INFINITY : 0.0f;
