@@ -142,11 +142,17 @@ __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxPar
     // NaN-propagating max: a NaN score makes row_max NaN, every exp(x - NaN) NaN and the whole row NaN -- the same outcome
     // as the unfused softmax (whose max drops NaNs but whose sum picks them up).
     float m = -INFINITY;  // a block the query row cannot see at all (vis == 0) never touches x[]
+    float lo = INFINITY;  // smallest entry: tells below whether any exp() can be denormal-ish without a per-element test
     if (vis > 0) {
         m = x[0];
+        lo = x[0];
 #pragma unroll
-        for (int i = 1; i < 31; i += 2) m = max_nan3(m, x[i], x[i + 1]);
+        for (int i = 1; i < 31; i += 2) {
+            m = max_nan3(m, x[i], x[i + 1]);
+            lo = fminf(lo, fminf(x[i], x[i + 1]));
+        }
         m = max_nan(m, x[31]);
+        lo = fminf(lo, x[31]);
     }
     auto row_reduce = [&](float v, bool is_max) -> float {
         if (layout == 0) {
@@ -211,9 +217,13 @@ __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxPar
     // the guard becomes "0 < e < 2^-80 or an unusual denominator", in which case the block takes the plain divide.
     uint32_t w[16];
     const bool plain_b = row_sum >= 1.0f && row_sum <= 65536.0f;  // sum of <= 32768 terms in [0,1] with exp(0) = 1 among them
+    // 0 < e < 2^-80 anywhere?  Not if the smallest entry is within 55 of the row max (e >= exp(-55) > 2^-80); only blocks with
+    // very small (or masked) entries pay for the per-element test.
     uint32_t tiny = 0;
+    if (!(lo - row_max >= -55.0f)) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) tiny |= (uint32_t)((__float_as_uint(x[i]) - 1u) < 0x17800000u - 1u);  // 0 < e < 2^-80
+        for (int i = 0; i < 32; ++i) tiny |= (uint32_t)((__float_as_uint(x[i]) - 1u) < 0x17800000u - 1u);
+    }
     if (plain_b && !tiny) {
         float r0;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(row_sum));
