@@ -450,6 +450,7 @@ def test_round_trip_sqnr_floors(mx, elem, floor, shape, block):
     """reference tests/test_mx_tensor.py:59-100: SQNR of to_mx -> to_dtype per element type"""
     from torchmx import dtypes
     from torchmx.mx_tensor import MXTensor
+    torch.manual_seed(1234)
     x = torch.randn(*shape, device=DEV, dtype=torch.bfloat16)
     y = MXTensor.to_mx(x, dtypes.STR_TO_ELEM_DTYPE[elem], block).to_dtype(torch.bfloat16)
     sqnr = float(20 * torch.log10(x.float().norm() / (x.float() - y.float()).norm()))
