@@ -6,8 +6,6 @@ kernel, or the dequantize path when the operands do not qualify).
 """
 from __future__ import annotations
 
-import os
-
 import torch
 import torch.nn.functional as F
 
