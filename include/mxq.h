@@ -140,7 +140,23 @@ typedef struct {
      * the separate quantize launch disappears.  x_quant_flags = MXQ_FLAG_* of mxq_quantize.  Decode shapes only
      * (M <= 64, batch == 1); otherwise MXQ_ERR_UNSUPPORTED_SHAPE and the caller quantizes first. */
     const void *x_bf16; int64_t ldx; int x_quant_flags;
+    /* MXQ_GEMM_* bits below (0 = defaults) */
+    unsigned flags;
+    /* decode kernel only: number of K splits per 128-row weight tile (a cluster of that many CTAs, <= 8); 0 = chosen by the
+     * library.  Exposed so that tests can pin every split count; results are bit-reproducible per value. */
+    int split_k;
 } mxq_gemm_args_t;
+/* The B operand (b_codes, sfb) is long-lived: nothing enqueued earlier on `stream` (or still running on the device) writes it.
+ * True for a layer's pre-quantized weight and its cached operand shadow (torchmx/layers/mx_linear.py:21-59), false for
+ * F.linear(to_mx(x), to_mx(w)) or a weight quantized on the fly (:68-92).  Only with this bit set may the decode kernel, which
+ * is launched with programmatic stream serialization, request weight tiles before the preceding kernel has finished. */
+#define MXQ_GEMM_B_STATIC 1u
+/* keep the 256x256 CTA-pair tiles even when they would under-fill the GPU (the library otherwise prefers 128x128 tiles there) */
+#define MXQ_GEMM_WIDE_TILES 2u
+/* launch without programmatic stream serialization */
+#define MXQ_GEMM_NO_PDL 4u
+/* fp4 x fp4 (both operands MXQ_OPERAND_E2M1_PACKED): stay on kind::mxf8f6f4 instead of the double-rate kind::mxf4 kernel */
+#define MXQ_GEMM_NO_MXF4 8u
 MXQ_API int mxq_gemm(const mxq_gemm_args_t *args, int device, void *stream);
 
 /* Operand storage formats of mxq_gemm.  The packed formats are what the sm_100a TMA unit expands on the fly

@@ -85,11 +85,10 @@ TILE_RULES = [(*c, rule) for c in CASES for rule in (("auto", "pair") if c[0] > 
 
 @pytest.mark.parametrize("M,N,K,ea,eb,bias,batch,spread,rule", TILE_RULES)
 def test_tensor_core_matmul(mx, monkeypatch, M, N, K, ea, eb, bias, batch, spread, rule):
-    if rule == "pair":
-        monkeypatch.setenv("MXQ_GEMM_NARROW", "-1")
     from torchmx import dtypes
     from torchmx.mx_tensor import MXTensor
     from torchmx_b200 import mx_gemm
+    monkeypatch.setitem(mx_gemm.overrides, "wide_tiles", rule == "pair")  # mxq_gemm_args_t.flags: MXQ_GEMM_WIDE_TILES
     g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
     sa, sb = ((batch, M, K), (batch, N, K)) if batch else ((M, K), (N, K))
     a = torch.randn(*sa, device=DEV, dtype=torch.bfloat16, generator=g)
@@ -158,7 +157,8 @@ def test_skinny_split_k_is_deterministic_and_consistent(mx, monkeypatch, splits)
     bit-identical, and every split count stays within the matmul tolerance."""
     from torchmx import dtypes
     from torchmx.mx_tensor import MXTensor
-    monkeypatch.setenv("MXQ_SKINNY_SPLITS", splits)
+    from torchmx_b200 import mx_gemm
+    monkeypatch.setitem(mx_gemm.overrides, "split_k", int(splits))  # mxq_gemm_args_t.split_k
     g = torch.Generator(device=DEV).manual_seed(11)
     x = torch.randn(32, 4096, device=DEV, dtype=torch.bfloat16, generator=g)
     w = torch.randn(1536, 4096, device=DEV, dtype=torch.bfloat16, generator=g)
@@ -393,10 +393,9 @@ def test_pack_linear_on_a_model_and_what_it_leaves_alone():
 def test_nan_and_inf_blocks_poison_the_same_outputs_as_the_dequantize_path(mx, monkeypatch, M, N, K, rule, bias):
     """an Inf / NaN anywhere in a 32-block gives that block the NaN scale (255); the reference then dequantizes the whole block to
     NaN and every output that contracts over it is NaN.  The block-scaled MMA must agree (E8M0 0xFF is NaN in hardware too)."""
-    if rule == "pair":
-        monkeypatch.setenv("MXQ_GEMM_NARROW", "-1")
     from torchmx import dtypes, mx_gemm
     from torchmx.mx_tensor import MXTensor
+    monkeypatch.setitem(mx_gemm.overrides, "wide_tiles", rule == "pair")
     g = torch.Generator(device=DEV).manual_seed(5)
     a = torch.randn(M, K, device=DEV, dtype=torch.bfloat16, generator=g)
     w = torch.randn(N, K, device=DEV, dtype=torch.bfloat16, generator=g)

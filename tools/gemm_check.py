@@ -58,17 +58,14 @@ ok &= check(77, 300, 256, "float4_e2m1", "float4_e2m1", batch=3)
 ok &= check(1024, 4096, 4096, "float8_e4m3", "float6_e3m2", scale_spread=4)
 # decode-sized activations: the skinny weight-streaming kernel (K3c), every token-tile width, auto and forced K splits
 for forced in ("", "1", "2", "8"):
-    if forced:
-        os.environ["MXQ_SKINNY_SPLITS"] = forced
-    else:
-        os.environ.pop("MXQ_SKINNY_SPLITS", None)
-    print(f"-- skinny, MXQ_SKINNY_SPLITS={forced or 'auto'}")
+    mx_gemm.overrides["split_k"] = int(forced or 0)
+    print(f"-- skinny, split_k={forced or 'auto'}")
     ok &= check(32, 4096, 4096, "float8_e4m3", "float6_e3m2", bias=True, scale_spread=6)
     ok &= check(17, 1000, 1024, "float8_e4m3", "float4_e2m1")
     ok &= check(64, 1024, 4096, "float8_e4m3", "float6_e3m2", bias=True)
     ok &= check(100, 384, 2048, "float6_e2m3", "float6_e3m2", scale_spread=12)
     ok &= check(128, 14336, 4096, "float8_e4m3", "float6_e3m2")
-os.environ.pop("MXQ_SKINNY_SPLITS", None)
+mx_gemm.overrides["split_k"] = 0
 ok &= check(32, 128256, 4096, "float8_e4m3", "float6_e3m2")
 ok &= check(5, 4096, 14336, "float8_e4m3", "float6_e3m2", bias=True)
 print("ALL OK" if ok else "FAILURES")

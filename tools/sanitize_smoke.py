@@ -27,7 +27,7 @@ with torch.no_grad():
             y = torch.bmm(A, B.transpose(1, 2)) if batch else torch.nn.functional.linear(A, B, b)
     mx_gemm.set_packed_operands(True)
     for s in ("1", "2", "4"):
-        os.environ["MXQ_SKINNY_SPLITS"] = s
+        mx_gemm.overrides["split_k"] = int(s)
         A = MXTensor.to_mx(torch.randn(8, 2048, device=dev, dtype=torch.bfloat16), dtypes.float8_e4m3, 32)
         B = MXTensor.to_mx(torch.randn(200, 2048, device=dev, dtype=torch.bfloat16), dtypes.float6_e3m2, 32)
         torch.nn.functional.linear(A, B)

@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmxq.so")
 OK, ERR_INVALID, ERR_UNSUPPORTED_SHAPE, ERR_CUDA = 0, 1, 2, 3
 HP_BF16, HP_F32 = 0, 1
 FLAG_HW_EXACT = 1
+GEMM_B_STATIC, GEMM_WIDE_TILES, GEMM_NO_PDL, GEMM_NO_MXF4 = 1, 2, 4, 8
+ABI_VERSION = 2
 MAX_DIMS = 6
 
 EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
@@ -30,6 +32,7 @@ class GemmArgs(ctypes.Structure):
         ("a_format", ctypes.c_int), ("b_format", ctypes.c_int),
         ("d_multicast", ctypes.c_void_p),
         ("x_bf16", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("x_quant_flags", ctypes.c_int),
+        ("flags", ctypes.c_uint), ("split_k", ctypes.c_int),
     ]
 
 
@@ -85,6 +88,8 @@ def lib() -> ctypes.CDLL:
         L.mxq_silu_mul_quantize.argtypes = [vp, vp, i64, i64, i64, i64, i32, u32, vp, vp, i32, vp]
         L.mxq_softmax_quantize.restype = i32
         L.mxq_softmax_quantize.argtypes = [ctypes.POINTER(SoftmaxArgs), i32, vp]
+        if L.mxq_version() != ABI_VERSION:
+            raise RuntimeError(f"torchmx_b200: libmxq.so has ABI v{L.mxq_version()}, this package needs v{ABI_VERSION}: rebuild with `python -m torchmx_b200.build --force`")
         if L.mxq_arch() != 1000:
             raise RuntimeError(f"torchmx_b200: libmxq.so was built for arch {L.mxq_arch()}, expected sm_100a")
         _lib = L

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libmxq.so")
-SOURCES = ["mxq_api.cu", "mxq_quantize.cu", "mxq_dequantize.cu", "mxq_transcode.cu", "mxq_gemm.cu", "mxq_gemm_skinny.cu", "mxq_softmax.cu", "mxq_act_quant.cu"]
+SOURCES = ["mxq_api.cu", "mxq_quantize.cu", "mxq_dequantize.cu", "mxq_transcode.cu", "mxq_tmap.cu", "mxq_gemm.cu", "mxq_gemm_skinny.cu", "mxq_softmax.cu", "mxq_act_quant.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -23,6 +23,10 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     # NO --use_fast_math / -ftz: fp32 subnormals carry real values at the ends of the E8M0 range.
 ]
+
+
+if os.environ.get("MXQ_DEV") == "1":  # developer build: the clock64 trace / tile-configuration hooks of the K3 kernels (tools/gemm_trace.py)
+    NVCC_FLAGS.append("-DMXQ_DEV")
 
 
 def _nvcc() -> str:

@@ -15,7 +15,7 @@ cudaError_t launch_dequantize_strided(const void*, const uint8_t*, int, const in
 cudaError_t launch_transcode(const void*, int, int64_t, void*, int, cudaStream_t);
 cudaError_t launch_pack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 cudaError_t launch_unpack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
-int launch_gemm(const mxq_gemm_args_t*, int, cudaStream_t, char*, size_t);
+int launch_gemm(const mxq_gemm_args_t*, int, int, cudaStream_t, char*, size_t);
 cudaError_t launch_silu_mul_quantize(const void*, const void*, int64_t, int64_t, int64_t, int64_t, int, unsigned, void*, uint8_t*, int, cudaStream_t);
 int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size_t);
 }  // namespace mxq
@@ -79,7 +79,7 @@ int waves_override() { static int v = env_int("MXQ_WAVES"); return v > 0 ? v : 0
 extern "C" {
 
 const char* mxq_last_error(void) { return g_err; }
-int mxq_version(void) { return 1; }
+int mxq_version(void) { return 2; }
 int mxq_arch(void) { return 1000; }
 
 int mxq_quantize(const void* src, int src_dtype, int64_t n_blocks, int block_size, int elem, unsigned flags, void* codes, uint8_t* scales,
@@ -181,7 +181,7 @@ int mxq_gemm(const mxq_gemm_args_t* a, int device, void* stream) {
     DeviceScope scope(device);
     if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_gemm: selecting device");
     char msg[400] = "";
-    const int rc = mxq::launch_gemm(a, sm_count_of(scope.cur), (cudaStream_t)stream, msg, sizeof(msg));
+    const int rc = mxq::launch_gemm(a, sm_count_of(scope.cur), scope.cur, (cudaStream_t)stream, msg, sizeof(msg));
     return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_gemm: %s", msg);
 }
 

@@ -263,7 +263,7 @@ struct Smem {
     static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
-template <int STAGES, int EW, int NBUF>
+template <int STAGES, int EW, int NBUF, bool MXF4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
     mx_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_d,
                         const Params p, const int group_m, const int tma_store) {
@@ -284,7 +284,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-    const int k_blocks = p.K / BLOCK_K;
+    const int k_blocks = p.K / BLOCK_K;  // 128-element K blocks = one 32-bit scale word per row
+    // operand stages: one 128-byte swizzle row per matrix row = 128 one-byte (or expanded 6 / 4-bit) elements, or, for the
+    // dense 4-bit streams of kind::mxf4, 256 elements = two K blocks
+    constexpr int KBS = MXF4 ? 2 : 1;
+    const int k_stages = k_blocks / KBS;
     const int tiles_per_batch = p.m_blocks * p.n_blocks;
     const int num_tiles = tiles_per_batch * p.batch;
 
@@ -312,11 +316,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
     cluster_sync_all();  // the peer's barriers must be initialised before anything is posted on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    if (p.trace != nullptr && leader && threadIdx.x == 128) {
+    MXQ_DEV_ONLY(if (p.trace != nullptr && leader && threadIdx.x == 128) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[640 + pair_id] = (long long)t;
-    }
+    })
 
     // grouped rasterisation: group_m row-blocks x all column-blocks at a time, row-block fastest, so one wave of
     // pairs touches ~group_m A panels and ~num_pairs/group_m B panels (both stay in L2) instead of every A panel
@@ -339,7 +343,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
             for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
                 int b, mb, nb;
                 tile_coords(tile, b, mb, nb);
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                for (int kb = 0; kb < k_stages; ++kb) {  // (coordinates: elements, or bytes of the dense 4-bit stream)
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (p.tx_a + p.tx_b));
                     const uint32_t full_leader = mapa_shared(smem_u32(&full[stage]), 0);
@@ -361,36 +365,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
             const uint32_t a_lo0 = smem_u32(smem + L::OFF_A) >> 4, b_lo0 = smem_u32(smem + L::OFF_B) >> 4;
             const uint32_t sfa_lo0 = smem_u32(smem + L::OFF_SFA) >> 4, sfb_lo0 = smem_u32(smem + L::OFF_SFB) >> 4;
             uint32_t stage = 0, phase = 0, sfs = 0, sf_phase = 0, sf_j = 0, acc_phase = 0, slot = 0, sf_sel = 0;
-            const bool tracing = p.trace != nullptr && pair_id == 0 && lane == 0;
-            int tile_iter = 0;
-            for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tile_iter) {
-                if (tracing) p.trace[tile_iter * 8 + 0] = clock64();
+            MXQ_DEV_ONLY(const bool tracing = p.trace != nullptr && pair_id == 0 && lane == 0; int tile_iter = 0;)
+            for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+                MXQ_DEV_ONLY(if (tracing) p.trace[tile_iter * 8 + 0] = clock64();)
                 mbar_wait(tmem_empty, acc_phase ^ 1);
                 tc_fence_after();
-                if (tracing) p.trace[tile_iter * 8 + 1] = clock64();
+                MXQ_DEV_ONLY(if (tracing) p.trace[tile_iter * 8 + 1] = clock64();)
                 const uint32_t tmem_d = tmem_base + (slot ? ACC_SLOT1 : 0u);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    if (tracing && tile_iter == 2 && kb < 64) p.trace[256 + kb * 4 + 0] = clock64();
+                for (int kb = 0; kb < k_stages; ++kb) {
                     if (sf_j == 0) mbar_wait(&sf_full[sfs], sf_phase);
-                    if (tracing && tile_iter == 2 && kb < 64) p.trace[256 + kb * 4 + 1] = clock64();
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    if (tracing && tile_iter == 2 && kb < 64) p.trace[256 + kb * 4 + 2] = clock64();
-                    if (tracing && kb == 0) p.trace[tile_iter * 8 + 2] = clock64();
-                    const bool last = kb == k_blocks - 1;
-                    const bool sf_done = sf_j == SF_KB - 1 || last;
+                    MXQ_DEV_ONLY(if (tracing && kb == 0) p.trace[tile_iter * 8 + 2] = clock64();)
+                    const bool last = kb == k_stages - 1;
+                    const bool sf_done = sf_j + KBS >= SF_KB || last;
                     if (elect_one()) {
                         const uint32_t a_lo = a_lo0 + stage * (L::A_STAGE >> 4), b_lo = b_lo0 + stage * (L::B_STAGE >> 4);
-                        const uint32_t sfa_lo = sfa_lo0 + sfs * (L::SFA_STAGE >> 4) + sf_j * (L::SFA_KB >> 4);
-                        const uint32_t sfb_lo = sfb_lo0 + sfs * (L::SFB_STAGE >> 4) + sf_j * (L::SFB_KB >> 4);
-                        const uint32_t tm_sfa = tmem_base + TM_SF + sf_sel * SF_BUF_COLS, tm_sfb = tm_sfa + 4;
-                        tc_copy_sf_pair(tm_sfa, HI_SF | sfa_lo);
-                        tc_copy_sf_pair(tm_sfb, HI_SF | sfb_lo);
-                        tc_copy_sf_pair(tm_sfb + 4, HI_SF | (sfb_lo + (512 >> 4)));
+                        const uint32_t tm_sf = tmem_base + TM_SF + sf_sel * (KBS * SF_BUF_COLS);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)  // advancing K inside the 128B swizzle row = +32 B
-                            tc_mma_mx_pair(tmem_d, HI_OPERAND | (a_lo + k * (UMMA_K >> 4)), HI_OPERAND | (b_lo + k * (UMMA_K >> 4)),
-                                           idesc_with_sf(idesc, k, k), (kb | k) != 0, tm_sfa, tm_sfb);
+                        for (int j = 0; j < KBS; ++j) {  // scale words of the stage's K block(s): SFA 4 columns, SFB 8 columns each
+                            const uint32_t sfa_lo = sfa_lo0 + sfs * (L::SFA_STAGE >> 4) + (sf_j + j) * (L::SFA_KB >> 4);
+                            const uint32_t sfb_lo = sfb_lo0 + sfs * (L::SFB_STAGE >> 4) + (sf_j + j) * (L::SFB_KB >> 4);
+                            const uint32_t tm_sfa = tm_sf + j * SF_BUF_COLS, tm_sfb = tm_sfa + 4;
+                            tc_copy_sf_pair(tm_sfa, HI_SF | sfa_lo);
+                            tc_copy_sf_pair(tm_sfb, HI_SF | sfb_lo);
+                            tc_copy_sf_pair(tm_sfb + 4, HI_SF | (sfb_lo + (512 >> 4)));
+                        }
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {  // advancing K inside the 128B swizzle row = +32 B
+                            if constexpr (MXF4) {
+                                // 64 elements per instruction: K block k / 2 of the stage, scale bytes {0,1} or {2,3} of its word
+                                const uint32_t tm_sfa = tm_sf + (k >> 1) * SF_BUF_COLS;
+                                tc_mma_mxf4_pair(tmem_d, HI_OPERAND | (a_lo + k * (UMMA_K >> 4)), HI_OPERAND | (b_lo + k * (UMMA_K >> 4)),
+                                                 idesc_with_sf(idesc, (k & 1) * 2, (k & 1) * 2), (kb | k) != 0, tm_sfa, tm_sfa + 4);
+                            } else {
+                                tc_mma_mx_pair(tmem_d, HI_OPERAND | (a_lo + k * (UMMA_K >> 4)), HI_OPERAND | (b_lo + k * (UMMA_K >> 4)),
+                                               idesc_with_sf(idesc, k, k), (kb | k) != 0, tm_sf, tm_sf + 4);
+                            }
+                        }
                         tc_commit_pair(&empty[stage]);
                         if (sf_done) tc_commit_pair(&sf_empty[sfs]);
                         if (last) tc_commit_pair(tmem_full);
@@ -400,12 +412,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
                         sf_j = 0;
                         if (++sfs == SF_STAGES) { sfs = 0; sf_phase ^= 1; }
                     } else {
-                        ++sf_j;
+                        sf_j += KBS;
                     }
                     sf_sel ^= 1;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (tracing) p.trace[tile_iter * 8 + 3] = clock64();
+                MXQ_DEV_ONLY(if (tracing) p.trace[tile_iter * 8 + 3] = clock64(); ++tile_iter;)
                 acc_phase ^= 1;
                 slot ^= 1;
             }
@@ -434,14 +446,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
         const int quad = warp & 3;
         const uint32_t tmem_empty_leader = mapa_shared(smem_u32(tmem_empty), 0);
         uint32_t acc_phase = 0, slot = 0;
-        const bool tracing = p.trace != nullptr && pair_id == 0 && leader && warp == 4 && lane == 0;
-        int tile_iter = 0;
-        for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tile_iter) {
+        MXQ_DEV_ONLY(const bool tracing = p.trace != nullptr && pair_id == 0 && leader && warp == 4 && lane == 0; int tile_iter = -1;)
+        for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
             int b, mb, nb;
             tile_coords(tile, b, mb, nb);
             mbar_wait(tmem_full, acc_phase);
             tc_fence_after();
-            if (tracing) p.trace[tile_iter * 8 + 4] = clock64();
+            MXQ_DEV_ONLY(++tile_iter; if (tracing) p.trace[tile_iter * 8 + 4] = clock64();)
             const int row = mb * TILE_M + (int)rank * 128 + quad * 32 + lane;
             uint16_t* drow = p.d + (int64_t)b * p.d_batch + (int64_t)row * p.ldd;
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (slot ? ACC_SLOT1 : 0u);
@@ -476,7 +487,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
-                        if (tracing) p.trace[tile_iter * 8 + 5] = clock64();
+                        MXQ_DEV_ONLY(if (tracing) p.trace[tile_iter * 8 + 5] = clock64();)
                     }
                     const int col0 = nb * TILE_N + g * 64;
                     uint8_t* buf = ebuf + (NBUF == 2 ? (h & 1) : h) * 4096;  // NBUF == 4 goes with four groups per warp and tile
@@ -533,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
                         tma_store_commit();
                     }
                 }
-                if (tracing) p.trace[tile_iter * 8 + 6] = clock64();
+                MXQ_DEV_ONLY(if (tracing) p.trace[tile_iter * 8 + 6] = clock64();)
                 acc_phase ^= 1;
                 slot ^= 1;
                 continue;
@@ -541,7 +552,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
             const int first = slot ? 0 : 6;  // the two 32-column chunks inside [192,256) of TMEM come first
             auto store_chunk = [&](const uint32_t (&v)[32], int c) {
                 const int col0 = nb * TILE_N + c * 32;
-                if (row < p.M && col0 < p.N && !(p.dbg & 1)) {
+                if (row < p.M && col0 < p.N MXQ_DEV_ONLY(&& !(p.dbg & 1))) {
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -576,7 +587,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
-                if (tracing) p.trace[tile_iter * 8 + 5] = clock64();
+                MXQ_DEV_ONLY(if (tracing) p.trace[tile_iter * 8 + 5] = clock64();)
                 store_chunk(v0, first);
                 store_chunk(v1, first + 1);
             }
@@ -588,17 +599,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
                 tmem_ld_wait();
                 store_chunk(v, c);
             }
-            if (tracing) p.trace[tile_iter * 8 + 6] = clock64();
+            MXQ_DEV_ONLY(if (tracing) p.trace[tile_iter * 8 + 6] = clock64();)
             acc_phase ^= 1;
             slot ^= 1;
         }
     }
 
-    if (p.trace != nullptr && leader && threadIdx.x == 128) {  // epilogue warp 4 of every leader: when did this pair finish (ns)
+    MXQ_DEV_ONLY(if (p.trace != nullptr && leader && threadIdx.x == 128) {  // epilogue warp 4 of every leader: when did this pair finish (ns)
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[512 + pair_id] = (long long)t;
-    }
+    })
     if (tma_store && warp >= 4 && lane == 0) tma_store_wait<0>();  // this thread's bulk stores have left shared memory and are performed
     __syncwarp();  // single-lane roles (producer, MMA issuer) rejoin their warp before the aligned cluster barrier
     tc_fence_before();
@@ -608,27 +619,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
 }  // namespace pair
 
 // ---- host side ------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES>
-static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t stream, char* msg,
-                      size_t msg_len) {
-    using L = SmemLayout<BLOCK_N, STAGES>;
-    {   // per device / context attribute: set on every launch (a few hundred ns)
-        const cudaError_t e = cudaFuncSetAttribute(mx_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
-        if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
-    }
-    Params p;
+static void fill_params(Params& p, const mxq_gemm_args_t* a, int tile_m, int tile_n) {
     p.sfa = a->sfa; p.sfb = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
     p.d_mc = nullptr;
     p.ld_sfa = a->ld_sfa; p.ld_sfb = a->ld_sfb; p.sfa_batch = a->sfa_batch_stride; p.sfb_batch = a->sfb_batch_stride;
     p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
-    p.trace = nullptr;
-    p.dbg = 0;
     p.idesc_fmt = idesc_formats(a->a_format, a->b_format);
     p.tx_a = 128 * BLOCK_K * operand_bits(a->a_format) / 8;
     p.tx_b = 128 * BLOCK_K * operand_bits(a->b_format) / 8;
-    p.m_blocks = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
-    p.n_blocks = (int)((a->N + BLOCK_N - 1) / BLOCK_N);
+    p.m_blocks = (int)((a->M + tile_m - 1) / tile_m);
+    p.n_blocks = (int)((a->N + tile_n - 1) / tile_n);
+    MXQ_DEV_ONLY(p.trace = nullptr; p.dbg = 0;)
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, int device, cudaStream_t stream, char* msg,
+                      size_t msg_len) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    {
+        const cudaError_t e = ensure_smem_attr((const void*)mx_gemm_kernel<BLOCK_N, STAGES>, L::DYN_BYTES, device);
+        if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    }
+    Params p;
+    fill_params(p, a, BLOCK_M, BLOCK_N);
     const int64_t tiles = (int64_t)p.m_blocks * p.n_blocks * p.batch;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     mx_gemm_kernel<BLOCK_N, STAGES><<<grid, kThreads, L::DYN_BYTES, stream>>>(ma, mb, p);
@@ -638,35 +652,32 @@ static int launch_cfg(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUt
 }
 
 
-template <int STAGES, int EW, int NBUF>
-static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t stream, char* msg,
+template <int STAGES, int EW, int NBUF, bool MXF4>
+static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, int device, cudaStream_t stream, char* msg,
                        size_t msg_len) {
     using L = pair::Smem<STAGES, EW, NBUF>;
     {
-        const cudaError_t e = cudaFuncSetAttribute(pair::mx_gemm_pair_kernel<STAGES, EW, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+        const cudaError_t e = ensure_smem_attr((const void*)pair::mx_gemm_pair_kernel<STAGES, EW, NBUF, MXF4>, L::DYN_BYTES, device);
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     }
     Params p;
-    p.sfa = a->sfa; p.sfb = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
+    fill_params(p, a, pair::TILE_M, pair::TILE_N);
     p.d_mc = (uint16_t*)a->d_multicast;
-    p.ld_sfa = a->ld_sfa; p.ld_sfb = a->ld_sfb; p.sfa_batch = a->sfa_batch_stride; p.sfb_batch = a->sfb_batch_stride;
-    p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
-    p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.batch = (int)a->batch;
-    p.idesc_fmt = idesc_formats(a->a_format, a->b_format);
-    p.tx_a = 128 * BLOCK_K * operand_bits(a->a_format) / 8;
-    p.tx_b = 128 * BLOCK_K * operand_bits(a->b_format) / 8;
-    p.dbg = getenv("MXQ_GEMM_DBG") ? atoi(getenv("MXQ_GEMM_DBG")) : 0;
-    p.trace = getenv("MXQ_GEMM_TRACE") ? reinterpret_cast<long long*>(strtoull(getenv("MXQ_GEMM_TRACE"), nullptr, 0)) : nullptr;
-    p.m_blocks = (int)((a->M + pair::TILE_M - 1) / pair::TILE_M);
-    p.n_blocks = (int)((a->N + pair::TILE_N - 1) / pair::TILE_N);
+    if (MXF4) {  // dense 4-bit streams: a stage is 128 rows x 128 bytes (256 elements) of each operand
+        p.idesc_fmt = kIdescMxf4Formats;
+        p.tx_a = p.tx_b = 128 * 128;
+    }
+    MXQ_DEV_ONLY(p.dbg = dev_env("MXQ_GEMM_DBG");
+                 p.trace = getenv("MXQ_GEMM_TRACE") ? reinterpret_cast<long long*>(strtoull(getenv("MXQ_GEMM_TRACE"), nullptr, 0)) : nullptr;)
     const int64_t tiles = (int64_t)p.m_blocks * p.n_blocks * p.batch;
     const int max_pairs = sm_count / 2;
     const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
-    const int group_m_env = getenv("MXQ_GEMM_GM") ? atoi(getenv("MXQ_GEMM_GM")) : 0;
-    const int group_m = group_m_env > 0 ? group_m_env : 8;
+    int group_m = 8;
+    MXQ_DEV_ONLY(if (dev_env("MXQ_GEMM_GM") > 0) group_m = dev_env("MXQ_GEMM_GM");)
     // coalesced TMA-store epilogue needs a 16-byte aligned D with a 16-byte multiple row pitch; otherwise direct stores
     CUtensorMap md;
-    int tma_store = ((uintptr_t)a->d % 16 == 0) && (a->ldd % 8 == 0) && (a->d_batch_stride % 8 == 0) && !(p.dbg & 2);
+    int tma_store = ((uintptr_t)a->d % 16 == 0) && (a->ldd % 8 == 0) && (a->d_batch_stride % 8 == 0);
+    MXQ_DEV_ONLY(if (p.dbg & 2) tma_store = 0;)
     if (a->d_multicast != nullptr) {  // fused all-reduce epilogue: staging path without the tensor map
         if (((uintptr_t)a->d_multicast % 16) || (a->ldd % 8) || (a->N % 8) || a->batch != 1) {
             snprintf(msg, msg_len, "d_multicast needs a 16-byte aligned buffer, N %% 8 == 0, ldd %% 8 == 0 and batch == 1");
@@ -674,20 +685,20 @@ static int launch_pair(const mxq_gemm_args_t* a, const CUtensorMap& ma, const CU
         }
         tma_store = 1;
         md = ma;
-    } else if (tma_store && !make_d_map(&md, a->d, a->N, a->M, a->batch, a->ldd, a->d_batch_stride)) tma_store = 0;
+    } else if (tma_store && !cached_d_map(&md, a->d, a->N, a->M, a->batch, a->ldd, a->d_batch_stride, device)) tma_store = 0;
     if (!tma_store) md = ma;  // unused placeholder
     if (EW == 8 && !tma_store) return MXQ_ERR_UNSUPPORTED_SHAPE;  // the eight-warp epilogue exists for the staged path only (caller retries with EW = 4)
-    pair::mx_gemm_pair_kernel<STAGES, EW, NBUF><<<2 * pairs, 128 + 32 * EW, L::DYN_BYTES, stream>>>(ma, mb, md, p, group_m, tma_store);
+    pair::mx_gemm_pair_kernel<STAGES, EW, NBUF, MXF4><<<2 * pairs, 128 + 32 * EW, L::DYN_BYTES, stream>>>(ma, mb, md, p, group_m, tma_store);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (pair): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;
 }
 
-int launch_gemm_skinny(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, char* msg, size_t msg_len);  // mxq_gemm_skinny.cu
+int launch_gemm_skinny(const mxq_gemm_args_t* a, int sm_count, int device, cudaStream_t stream, char* msg, size_t msg_len);  // mxq_gemm_skinny.cu
 
 }  // namespace gemm
 
-int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, char* msg, size_t msg_len) {
+int launch_gemm(const mxq_gemm_args_t* a, int sm_count, int device, cudaStream_t stream, char* msg, size_t msg_len) {
     using namespace gemm;
     if (a->K <= 0 || a->K % BLOCK_K) { snprintf(msg, msg_len, "K=%lld is not a positive multiple of %d", (long long)a->K, BLOCK_K); return MXQ_ERR_UNSUPPORTED_SHAPE; }
     if ((a->lda % 16) || (a->ldb % 16) || ((uintptr_t)a->a_codes % 16) || ((uintptr_t)a->b_codes % 16) || (a->a_batch_stride % 16) || (a->b_batch_stride % 16)) {
@@ -708,8 +719,10 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
     if (a->M > 0x7FFFFFFF || a->N > 0x7FFFFFFF || a->K > 0x7FFFFFFF || a->batch > 0x7FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
-    if (a->M <= 128 && a->batch == 1 && !getenv("MXQ_NO_SKINNY")) {  // decode-sized activations: weight-streaming kernel (K3c)
-        const int rc = launch_gemm_skinny(a, sm_count, stream, msg, msg_len);
+    bool skinny_ok = a->M <= 128 && a->batch == 1;
+    MXQ_DEV_ONLY(if (dev_env("MXQ_NO_SKINNY")) skinny_ok = false;)
+    if (skinny_ok) {  // decode-sized activations: weight-streaming kernel (K3c)
+        const int rc = launch_gemm_skinny(a, sm_count, device, stream, msg, msg_len);
         if (rc != MXQ_ERR_UNSUPPORTED_SHAPE) return rc;
     }
     if (a->x_bf16 != nullptr) {
@@ -720,47 +733,44 @@ int launch_gemm(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, cha
         snprintf(msg, msg_len, "d_multicast (fused all-reduce) is implemented by the CTA-pair and skinny kernels only");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
-    const int force_narrow = getenv("MXQ_GEMM_NARROW") ? atoi(getenv("MXQ_GEMM_NARROW")) : 0;  // developer knobs, re-read per call
-    const int cfg = getenv("MXQ_GEMM_CFG") ? atoi(getenv("MXQ_GEMM_CFG")) : 0;  // developer knob: <BLOCK_N><STAGES>, 2<STAGES> = CTA pair
+    int cfg = 0;  // developer builds: <BLOCK_N><STAGES>, 2<STAGES> = CTA pair
+    MXQ_DEV_ONLY(cfg = dev_env("MXQ_GEMM_CFG");)
     // Under-filled grids: when the 256x256 pair tiles would occupy at most a quarter of the SM pairs, 128x128 tiles spread the
     // same work over 4x as many SMs (measured, K = 4096, before / after: 2048x1024 16.8 -> 13.9 us, 1024x1024 16.6 -> 12.8, 512x4096 17.1 -> 13.7).
-    // MXQ_GEMM_NARROW=-1 switches the rule off.
+    // MXQ_GEMM_WIDE_TILES switches the rule off; a fused all-reduce epilogue exists in the pair kernel only.
     const int64_t pair_tiles = ((a->M + 255) / 256) * ((a->N + 255) / 256) * a->batch;
-    const bool underfilled = force_narrow >= 0 && a->M > 128 && a->N > 128 && pair_tiles * 4 <= sm_count && a->d_multicast == nullptr;
-    const bool wide = a->N > 128 && force_narrow <= 0 && !underfilled;
+    const bool underfilled = !(a->flags & MXQ_GEMM_WIDE_TILES) && a->M > 128 && a->N > 128 && pair_tiles * 4 <= sm_count && a->d_multicast == nullptr;
+    const bool wide = a->N > 128 && !underfilled;
     CUtensorMap ma, mb;
     const bool use_pair = wide && a->M > 128 && sm_count >= 2 && (cfg == 0 || cfg / 10 == 2 || a->d_multicast != nullptr);
     if (use_pair) {
-        if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, 128, a->a_format) ||
-            !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, 128, a->b_format)) {
+        // fp4 x fp4: kind::mxf4 reads the dense 4-bit streams (no 16-byte slot expansion) -> plain byte maps over K / 2 bytes per row
+        const bool mxf4 = a->a_format == MXQ_OPERAND_E2M1_PACKED && a->b_format == MXQ_OPERAND_E2M1_PACKED && a->K % 256 == 0 && !(a->flags & MXQ_GEMM_NO_MXF4);
+        const int64_t k_a = mxf4 ? a->K / 2 : a->K, k_b = mxf4 ? a->K / 2 : a->K;
+        const int fmt_a = mxf4 ? MXQ_OPERAND_E4M3_BYTES : a->a_format, fmt_b = mxf4 ? MXQ_OPERAND_E4M3_BYTES : a->b_format;
+        if (!cached_operand_map(&ma, a->a_codes, k_a, a->M, a->batch, a->lda, a->a_batch_stride, 128, fmt_a, device) ||
+            !cached_operand_map(&mb, a->b_codes, k_b, a->N, a->batch, a->ldb, a->b_batch_stride, 128, fmt_b, device)) {
             snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
             return MXQ_ERR_UNSUPPORTED_SHAPE;
         }
-        if (cfg == 24) return launch_pair<4, 4, 2>(a, ma, mb, sm_count, stream, msg, msg_len);
-        // short K loops are bound by the epilogue (a 64 KB output tile per CTA for a few hundred MMA cycles): eight
-        // epilogue warps and a shallower operand ring; long K loops hide the epilogue and want the deeper ring
-        const int ew8 = getenv("MXQ_GEMM_EW8") ? atoi(getenv("MXQ_GEMM_EW8")) : 0;  // small-K variant (3 stages): 0 = 4 epilogue warps x 2 buffers (best once the bias code was un-predicated), 1 = 8 warps, 2 = 4 warps x 4 buffers
-        const int ew8_max_kb = getenv("MXQ_GEMM_EW8_KB") ? atoi(getenv("MXQ_GEMM_EW8_KB")) : 2;  // measured: helps at K = 128 (Q@K^T: 85 -> 79 us), hurts at K = 1024
-        if (a->K / BLOCK_K <= ew8_max_kb && cfg != 25) {
-            const int rc = ew8 == 1 ? launch_pair<3, 8, 2>(a, ma, mb, sm_count, stream, msg, msg_len)
-                           : (ew8 == 2 ? launch_pair<3, 4, 4>(a, ma, mb, sm_count, stream, msg, msg_len) : launch_pair<3, 4, 2>(a, ma, mb, sm_count, stream, msg, msg_len));
+        if (mxf4) return launch_pair<5, 4, 2, true>(a, ma, mb, sm_count, device, stream, msg, msg_len);
+        MXQ_DEV_ONLY(if (cfg == 24) return launch_pair<4, 4, 2, false>(a, ma, mb, sm_count, device, stream, msg, msg_len);)
+        // short K loops are bound by the epilogue (a 64 KB output tile per CTA for a few hundred MMA cycles): a shallower operand
+        // ring; long K loops hide the epilogue and want the deeper ring.  (Eight epilogue warps / four staging buffers per warp
+        // were measured and dropped once the bias code was un-predicated.)
+        if (a->K / BLOCK_K <= 2 && cfg != 25) {
+            const int rc = launch_pair<3, 4, 2, false>(a, ma, mb, sm_count, device, stream, msg, msg_len);
             if (rc != MXQ_ERR_UNSUPPORTED_SHAPE) return rc;
         }
-        return launch_pair<5, 4, 2>(a, ma, mb, sm_count, stream, msg, msg_len);
+        return launch_pair<5, 4, 2, false>(a, ma, mb, sm_count, device, stream, msg, msg_len);
     }
-    if (!make_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M, a->a_format) ||
-        !make_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128, a->b_format)) {
+    if (!cached_operand_map(&ma, a->a_codes, a->K, a->M, a->batch, a->lda, a->a_batch_stride, BLOCK_M, a->a_format, device) ||
+        !cached_operand_map(&mb, a->b_codes, a->K, a->N, a->batch, a->ldb, a->b_batch_stride, wide ? 256 : 128, a->b_format, device)) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
-    if (wide) {
-        if (cfg == 2563) return launch_cfg<256, 3>(a, ma, mb, sm_count, stream, msg, msg_len);
-        if (cfg == 2562) return launch_cfg<256, 2>(a, ma, mb, sm_count, stream, msg, msg_len);
-        return launch_cfg<256, 4>(a, ma, mb, sm_count, stream, msg, msg_len);
-    }
-    if (cfg == 1284) return launch_cfg<128, 4>(a, ma, mb, sm_count, stream, msg, msg_len);
-    if (cfg == 1283) return launch_cfg<128, 3>(a, ma, mb, sm_count, stream, msg, msg_len);
-    return launch_cfg<128, 6>(a, ma, mb, sm_count, stream, msg, msg_len);
+    if (wide) return launch_cfg<256, 4>(a, ma, mb, sm_count, device, stream, msg, msg_len);
+    return launch_cfg<128, 6>(a, ma, mb, sm_count, device, stream, msg, msg_len);
 }
 
 }  // namespace mxq

@@ -30,10 +30,10 @@ struct Params {
     const uint16_t* x_hp; int64_t ldx; int x_flags;  // fused mode: bf16 activation, quantized to e4m3 / block 32 in the kernel
     int64_t ld_sfx, ld_sfw, ldd;
     int M, N, K, splits;
-    int w_tiled;  // W codes are the tile-major shadow ([N/128][K/128][128][128 B])
     uint32_t idesc_fmt, tx_w, tx_x;  // element formats of the descriptor; bytes a W / X box posts on the mbarrier
     int pdl;      // launched with programmatic stream serialization: X / its scales may only be read after griddepcontrol.wait
-    int pf_dist;  // L2 prefetch distance of the W stream, in K blocks
+    int w_static; // ... and W / its scales too, unless the caller vouches that no earlier kernel writes them (MXQ_GEMM_B_STATIC)
+    int pf_dist;  // L2 prefetch distance of the W stream, in K blocks (developer builds; 0 = off)
     int sf_tma;   // scales are 16-byte aligned with a 16-byte multiple row pitch: fetch them with TMA (deep prefetch)
 };
 
@@ -129,10 +129,12 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
         // ================= TMA producer =================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
-            // Programmatic dependent launch: this grid may be running before the kernel that produces the activation has
-            // finished.  The weights do not depend on it, so the first ring of W tiles is requested right away; everything
-            // that reads X (and, transitively, every write of D) comes after pdl_wait().
-            const int n_pre = p.pdl ? min(k_blocks, STAGES) : 0;
+            // Programmatic dependent launch: this grid may be running before the preceding kernels of the stream have
+            // finished.  A layer's pre-quantized weight does not depend on them (the caller says so: w_static), so the first
+            // ring of W tiles is requested right away; everything that reads X (and, transitively, every write of D) comes
+            // after pdl_wait().  Without that promise -- F.linear(to_mx(x), to_mx(w)): the quantize kernel that is still
+            // writing W lets its dependents start early -- nothing is read before the wait.
+            const int n_pre = (p.pdl && p.w_static) ? min(k_blocks, STAGES) : 0;
             const bool xq = p.x_hp != nullptr;
             const uint32_t tx = p.tx_w + (xq ? 0u : p.tx_x);
             for (int i = 0; i < n_pre; ++i) {
@@ -153,10 +155,7 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
                 if (kb + pf_dist < kb1) tma_prefetch_l2_3d(&map_w, (kb + pf_dist) * BLOCK_K, n0, 0);
                 mbar_wait(&empty[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full[stage], tx);
-                if (p.w_tiled)
-                    tma_load_4d(&map_w, &full[stage], smem + L::OFF_W + stage * L::W_STAGE, 0, 0, kb, tile);
-                else
-                    tma_load_3d(&map_w, &full[stage], smem + L::OFF_W + stage * L::W_STAGE, kb * BLOCK_K, n0, 0);
+                tma_load_3d(&map_w, &full[stage], smem + L::OFF_W + stage * L::W_STAGE, kb * BLOCK_K, n0, 0);
                 if (!xq) tma_load_3d(&map_x, &full[stage], smem + L::OFF_X + stage * L::X_STAGE, kb * BLOCK_K, 0, 0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -209,8 +208,8 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
         };
         if (warp == 3 && p.x_hp != nullptr) {
             // fused mode: the token scales are produced by the quantizer (epilogue) warps
-        } else if (warp == 3 && p.pdl) {
-            pdl_wait();  // the token scales are written by the preceding quantize kernel
+        } else if (p.pdl && (warp == 3 || !p.w_static)) {
+            pdl_wait();  // the token scales (and, unless static, the weight scales) are written by a preceding kernel
         }
         if (warp == 3 && p.x_hp != nullptr) {
         } else if (p.sf_tma) {
@@ -356,14 +355,13 @@ __global__ void __launch_bounds__(kThreads) mx_gemm_skinny_kernel(const __grid_c
 }
 
 template <int N_TOK, int STAGES, int RAW_W>
-static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, char* msg, size_t msg_len) {
+static int launch(const mxq_gemm_args_t* a, int splits, int device, cudaStream_t stream, char* msg, size_t msg_len) {
     using L = Smem<N_TOK, STAGES, RAW_W>;
     CUtensorMap mw, mx;
-    const int fake_tiled = getenv("MXQ_SKINNY_FAKE_TILED") ? atoi(getenv("MXQ_SKINNY_FAKE_TILED")) : 0;  // timing experiment only (wrong results)
-    const bool w_ok = fake_tiled ? make_tiled_operand_map(&mw, a->b_codes, a->K, a->N / 128 * 128, 1) : make_operand_map(&mw, a->b_codes, a->K, a->N, 1, a->ldb, 0, TILE_W, a->b_format);
+    const bool w_ok = cached_operand_map(&mw, a->b_codes, a->K, a->N, 1, a->ldb, 0, TILE_W, a->b_format, device);
     const bool xq = a->x_bf16 != nullptr;
     if (xq) mx = mw;  // unused placeholders in fused-quantization mode
-    if (!w_ok || (!xq && !make_operand_map(&mx, a->a_codes, a->K, a->M, 1, a->lda, 0, N_TOK, a->a_format))) {
+    if (!w_ok || (!xq && !cached_operand_map(&mx, a->a_codes, a->K, a->M, 1, a->lda, 0, N_TOK, a->a_format, device))) {
         snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed (driver entry point missing or invalid strides)");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
@@ -371,10 +369,11 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
     CUtensorMap msw = mw, msx = mx;
     const int k_blocks_total = (int)(a->K / BLOCK_K);
     int sf_tma = (xq || (((uintptr_t)a->sfa % 16 == 0) && (a->ld_sfa % 16 == 0))) && ((uintptr_t)a->sfb % 16 == 0) && (a->ld_sfb % 16 == 0) &&
-                 (k_blocks_total % (splits * SF_KB) == 0) && !getenv("MXQ_SKINNY_NO_SFTMA");
-    if (sf_tma && (!make_scale_map(&msw, a->sfb, a->K / 32, a->N, a->ld_sfb) || (!xq && !make_scale_map(&msx, a->sfa, a->K / 32, a->M, a->ld_sfa)))) sf_tma = 0;
+                 (k_blocks_total % (splits * SF_KB) == 0);
+    MXQ_DEV_ONLY(if (dev_env("MXQ_SKINNY_NO_SFTMA")) sf_tma = 0;)
+    if (sf_tma && (!cached_scale_map(&msw, a->sfb, a->K / 32, a->N, a->ld_sfb, device) || (!xq && !cached_scale_map(&msx, a->sfa, a->K / 32, a->M, a->ld_sfa, device)))) sf_tma = 0;
     auto kernel = mx_gemm_skinny_kernel<N_TOK, STAGES, RAW_W>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+    cudaError_t e = ensure_smem_attr((const void*)kernel, L::DYN_BYTES, device);
     if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     Params p;
     p.sfx = a->sfa; p.sfw = a->sfb; p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
@@ -382,14 +381,15 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
     p.x_hp = (const uint16_t*)a->x_bf16; p.ldx = a->ldx; p.x_flags = a->x_quant_flags;
     p.ld_sfx = a->ld_sfa; p.ld_sfw = a->ld_sfb; p.ldd = a->ldd;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K; p.splits = splits;
-    p.w_tiled = fake_tiled;
     // the weights are the MMA A operand here, the tokens the B operand
     p.idesc_fmt = idesc_formats(a->b_format, xq ? MXQ_OPERAND_E4M3_BYTES : a->a_format);
     p.tx_w = TILE_W * BLOCK_K * operand_bits(a->b_format) / 8;
     p.tx_x = N_TOK * BLOCK_K * operand_bits(a->a_format) / 8;
     p.sf_tma = sf_tma;
-    p.pdl = getenv("MXQ_PDL") ? atoi(getenv("MXQ_PDL")) : 1;
-    p.pf_dist = getenv("MXQ_SKINNY_PF") ? atoi(getenv("MXQ_SKINNY_PF")) : 0;  // measured: no gain on B200 (0 = off)
+    p.pdl = (a->flags & MXQ_GEMM_NO_PDL) ? 0 : 1;
+    p.w_static = (a->flags & MXQ_GEMM_B_STATIC) ? 1 : 0;
+    p.pf_dist = 0;  // measured: no gain on B200
+    MXQ_DEV_ONLY(p.pf_dist = dev_env("MXQ_SKINNY_PF");)
     const int n_tiles = (int)((a->N + TILE_W - 1) / TILE_W);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_tiles * splits), 1, 1);
@@ -413,7 +413,7 @@ static int launch(const mxq_gemm_args_t* a, int splits, cudaStream_t stream, cha
 }  // namespace skinny
 
 // M <= 128, batch == 1.  Returns MXQ_ERR_UNSUPPORTED_SHAPE when the caller should use the general kernels.
-int launch_gemm_skinny(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stream, char* msg, size_t msg_len) {
+int launch_gemm_skinny(const mxq_gemm_args_t* a, int sm_count, int device, cudaStream_t stream, char* msg, size_t msg_len) {
     using namespace skinny;
     if (a->batch != 1 || a->M > 128 || a->K % BLOCK_K) return MXQ_ERR_UNSUPPORTED_SHAPE;
     if (a->x_bf16 != nullptr && (a->M > 64 || ((uintptr_t)a->x_bf16 % 16) || (a->ldx % 8))) {
@@ -429,17 +429,19 @@ int launch_gemm_skinny(const mxq_gemm_args_t* a, int sm_count, cudaStream_t stre
     // split K across a cluster until about one CTA per SM is streaming; keep >= 4 K blocks per CTA and 4-K-block aligned
     // split points (the scale-factor loaders read 16 bytes = 4 K blocks per row)
     int splits = 1;
-    const int forced = getenv("MXQ_SKINNY_SPLITS") ? atoi(getenv("MXQ_SKINNY_SPLITS")) : 0;
-    if (forced > 0) {
-        splits = forced;
+    if (a->split_k > 0) {
+        if (a->split_k > 8) {
+            snprintf(msg, msg_len, "split_k=%d exceeds the portable cluster size 8", a->split_k);
+            return MXQ_ERR_INVALID;
+        }
+        splits = a->split_k < k_blocks ? a->split_k : k_blocks;
     } else {
         while (splits < 8 && n_tiles * splits * 2 <= sm_count && k_blocks % (splits * 2 * 4) == 0 && k_blocks / (splits * 2) >= 4) splits *= 2;
     }
-    if (splits > k_blocks) splits = k_blocks;
     const bool deep = (int64_t)n_tiles * splits <= sm_count;  // one CTA per SM: spend the shared memory on a deeper ring
-    if (a->M <= 32) return deep ? launch<32, 8, 8>(a, splits, stream, msg, msg_len) : launch<32, 4, 4>(a, splits, stream, msg, msg_len);
-    if (a->M <= 64) return deep ? launch<64, 7, 8>(a, splits, stream, msg, msg_len) : launch<64, 4, 4>(a, splits, stream, msg, msg_len);
-    return deep ? launch<128, 6, 4>(a, splits, stream, msg, msg_len) : launch<128, 4, 4>(a, splits, stream, msg, msg_len);
+    if (a->M <= 32) return deep ? launch<32, 8, 8>(a, splits, device, stream, msg, msg_len) : launch<32, 4, 4>(a, splits, device, stream, msg, msg_len);
+    if (a->M <= 64) return deep ? launch<64, 7, 8>(a, splits, device, stream, msg, msg_len) : launch<64, 4, 4>(a, splits, device, stream, msg, msg_len);
+    return deep ? launch<128, 6, 4>(a, splits, device, stream, msg, msg_len) : launch<128, 4, 4>(a, splits, device, stream, msg, msg_len);
 }
 
 }  // namespace gemm

@@ -200,6 +200,18 @@ __device__ __forceinline__ void tc_mma_mx_pair(uint32_t tmem_d, uint64_t desc_a,
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
         : "memory");
 }
+// fp4 x fp4 at twice the rate: kind::mxf4, K = 64 per instruction, operands are the DENSE 4-bit streams (128 bytes of a 128B
+// swizzle row = 256 elements), one E8M0 scale per 32 elements = two scale bytes per row and instruction (scale_vec::2X): the
+// scale-factor id in the descriptor selects byte pair 0 or 2 of the row's 32-bit scale word in TMEM
+__device__ __forceinline__ void tc_mma_mxf4_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                                 uint32_t tmem_sfa, uint32_t tmem_sfb) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
 // arrive on the barrier at the same shared-memory offset in both CTAs of the pair once all prior MMAs retire
 __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -228,6 +240,7 @@ __host__ __device__ constexpr int operand_bits(int operand_format) {
     return operand_format == MXQ_OPERAND_E2M1_PACKED ? 4 : ((operand_format == MXQ_OPERAND_E4M3_BYTES || operand_format == MXQ_OPERAND_E5M2_BYTES) ? 8 : 6);
 }
 __host__ __device__ constexpr uint32_t idesc_formats(int a_format, int b_format) { return (umma_format(a_format) << 7) | (umma_format(b_format) << 10); }
+constexpr uint32_t kIdescMxf4Formats = (1u << 7) | (1u << 10);  // kind::mxf4: E2M1 = 1 for both operands
 __device__ __forceinline__ uint32_t idesc_with_sf(uint32_t idesc, uint32_t sfa_id, uint32_t sfb_id) {
     return idesc | (sfb_id << 4) | (sfa_id << 29);
 }
@@ -239,9 +252,16 @@ struct Params {
     int M, N, K, batch, m_blocks, n_blocks;
     uint32_t idesc_fmt;  // element-format bits of the instruction descriptor (idesc_formats)
     uint32_t tx_a, tx_b; // bytes one 128-row x 128-element box of A / B posts on the mbarrier (packed formats count packed bytes)
-    int dbg;           // developer hook (MXQ_GEMM_DBG): bit0 = epilogue skips the global stores
-    long long* trace;  // developer hook (MXQ_GEMM_TRACE=<device pointer>): clock64 stamps of pair 0's leader, 8 slots per tile
+#ifdef MXQ_DEV  // developer builds only (python -m torchmx_b200.build with MXQ_DEV=1): never in the shipped library
+    int dbg;           // MXQ_GEMM_DBG: bit0 = epilogue skips the global stores
+    long long* trace;  // MXQ_GEMM_TRACE=<device pointer>: clock64 stamps of pair 0's leader, 8 slots per tile
+#endif
 };
+#ifdef MXQ_DEV
+#define MXQ_DEV_ONLY(...) __VA_ARGS__
+#else
+#define MXQ_DEV_ONLY(...)
+#endif
 
 
 // ---- scale-factor loader (one warp, one output tile) ---------------------------------------------------
@@ -413,75 +433,27 @@ __device__ __forceinline__ void sf_tma_tile4(const CUtensorMap* map_sf, int byte
     }
 }
 
-// ---- host side: tensor maps -------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static inline EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
-}
+// ---- host side: tensor maps (mxq_tmap.cu) ---------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a pure function of (base, extents, strides, box, type): the encoded 128-byte descriptors are kept in a
+// small process-wide table keyed by exactly those arguments, so a layer's weight (and the handful of activation / output
+// addresses the caching allocator cycles through) is encoded once, not on every launch.  Thread-safe.
 
 // [batch][rows][K elements], K contiguous, box = 128 elements x box_rows, 128B swizzle, OOB rows read as zero.  The shared
-// memory image is always 128 bytes per row and K block: one byte per element for E4M3 bytes, and for the packed 4 / 6-bit
+// memory image is always 128 bytes per row and K block: one byte per element for E4M3 / E5M2 bytes, and for the packed 4 / 6-bit
 // formats the TMA unit expands every 16 elements (8 / 12 bytes) to a 16-byte slot -- the layout kind::mxf8f6f4 reads.
-static inline bool make_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows, int64_t batch, int64_t ld, int64_t batch_stride,
-                             int box_rows, int operand_format = MXQ_OPERAND_E4M3_BYTES) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    const CUtensorMapDataType dt = (operand_format == MXQ_OPERAND_E4M3_BYTES || operand_format == MXQ_OPERAND_E5M2_BYTES) ? CU_TENSOR_MAP_DATA_TYPE_UINT8
-                                   : (operand_format == MXQ_OPERAND_E2M1_PACKED ? CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B : CU_TENSOR_MAP_DATA_TYPE_16U6_ALIGN16B);
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)ld, (cuuint64_t)(batch > 1 ? batch_stride : ld * rows)};
-    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    return fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// weight shadow in tile-major layout: [rows/128][K/128][128 rows][128 B]; a box is one contiguous 16 KB tile
-static inline bool make_tiled_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows_padded, int box_tiles) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    const cuuint64_t kb = (cuuint64_t)(K / 128);
-    cuuint64_t dims[4] = {128, 128, kb, (cuuint64_t)(rows_padded / 128)};
-    cuuint64_t strides[3] = {128, 16384, 16384 * kb};
-    cuuint32_t box[4] = {128, 128, 1, (cuuint32_t)box_tiles};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
+bool cached_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows, int64_t batch, int64_t ld, int64_t batch_stride, int box_rows,
+                        int operand_format, int device);
 // E8M0 scales [rows][K/32 bytes] row-major: box = 16 bytes (4 K blocks) x 128 rows, rows / bytes past the edge read as zero
-static inline bool make_scale_map(CUtensorMap* map, const void* base, int64_t scale_bytes_per_row, int64_t rows, int64_t ld) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)scale_bytes_per_row, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld};
-    cuuint32_t box[2] = {16, 128};
-    cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
+bool cached_scale_map(CUtensorMap* map, const void* base, int64_t scale_bytes_per_row, int64_t rows, int64_t ld, int device);
 // D: [batch][M][N] bf16, box = 64 columns x 32 rows, 128B swizzle (one epilogue warp's staging buffer)
-static inline bool make_d_map(CUtensorMap* map, void* base, int64_t N, int64_t M, int64_t batch, int64_t ldd, int64_t batch_stride) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)ldd * 2, (cuuint64_t)(batch > 1 ? batch_stride : ldd * M) * 2};
-    cuuint32_t box[3] = {64, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
+bool cached_d_map(CUtensorMap* map, void* base, int64_t N, int64_t M, int64_t batch, int64_t ldd, int64_t batch_stride, int device);
+// The dynamic shared-memory opt-in is a per-(kernel, device) attribute: set the first time a kernel is launched on a device,
+// not on every call.
+cudaError_t ensure_smem_attr(const void* kernel, int bytes, int device);
+#ifdef MXQ_DEV
+// developer builds: integer value of an environment variable (0 when unset), re-read on every call
+static inline int dev_env(const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; }
+#endif
 
 }  // namespace gemm
 }  // namespace mxq

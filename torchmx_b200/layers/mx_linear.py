@@ -36,6 +36,7 @@ class MXInferenceLinear(torch.nn.Linear):
         if w.device.type != "meta":
             wc = qconfig.weights_config
             new.weight = torch.nn.Parameter(MXTensor.to_mx(w, wc.elem_dtype, wc.block_size), requires_grad=False)
+            mx_gemm.mark_static(new.weight)
         else:
             new.weight = torch.nn.Parameter(torch.empty(mod.out_features, mod.in_features, device="meta", dtype=w.dtype), requires_grad=False)
         if mod.bias is None:
@@ -66,7 +67,9 @@ class MXInferenceLinear(torch.nn.Linear):
         return MXTensor.to_mx(x, ac.elem_dtype, ac.block_size)
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, _fused=None) -> torch.Tensor:
+        """`_fused` (mx_gemm.FusedOutput, internal): set by RowParallelMXLinear -- the launch may add its result into that
+        symmetric buffer instead of returning a local tensor."""
         ac = self.qconfig.activations_config
         bias = self.bias
         if torch.compiler.is_compiling():
@@ -82,20 +85,20 @@ class MXInferenceLinear(torch.nn.Linear):
             if not isinstance(self.weight, MXTensor) and bias is not None:
                 bias = bias.to(torch.bfloat16)
             w_mx = self._weight_mx()
-            out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x, w_mx, (), (bias,), count_fallback=False)
+            out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x, w_mx, (), (bias,), count_fallback=False, fused=_fused)
             return out if out is not None else F.linear(x, w_mx, bias)
         if not isinstance(self.weight, MXTensor) and bias is not None:
             bias = bias.to(torch.bfloat16)
         w_mx = self._weight_mx()
         if ac.elem_dtype_name == "float8_e4m3" and ac.block_size == 32:
             # decode-sized activations: quantization fused into the weight-streaming GEMM (one launch, no code round trip)
-            out = mx_gemm.linear_fused_act_quant(x, w_mx, bias, env.MX_EXACT_QUANTIZATION == "True")
+            out = mx_gemm.linear_fused_act_quant(x, w_mx, bias, env.MX_EXACT_QUANTIZATION == "True", fused=_fused)
             if out is not None:
                 return out
         x_mx = MXTensor.to_mx(x, ac.elem_dtype, ac.block_size)
         # F.linear(x_mx, w_mx, bias) reaches the same kernel through the dispatcher (aten.t + aten.mm / addmm on MXTensor
         # views, ~50 us of host time per layer); hand the operands to the tensor-core path directly when they qualify
-        out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x_mx, w_mx, (), (bias,), count_fallback=False)
+        out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x_mx, w_mx, (), (bias,), count_fallback=False, fused=_fused)
         if out is not None:
             return out
         return F.linear(x_mx, w_mx, bias)

@@ -21,7 +21,7 @@ from typing import Optional, Tuple
 import torch
 from torch import nn
 
-from .. import attention_ops, mlp_ops
+from .. import attention_ops, mlp_ops, mx_gemm
 from ..config import QAttentionConfig, QLinearConfig
 from ..mx_tensor import MXTensor
 from .mx_linear import MXInferenceLinear
@@ -87,7 +87,9 @@ def _fuse_linears(mods) -> Optional[MXInferenceLinear]:
         m.weight = nn.Parameter(MXTensor(scales[row:row + n], codes[row:row + n], w._elem_dtype, w._block_size, w._orig_dtype), requires_grad=False)
         if fused.bias is not None:
             m.bias = nn.Parameter(fused.bias.data[row:row + n], requires_grad=False)
+        mx_gemm.mark_static(m.weight)
         row += n
+    mx_gemm.mark_static(fused.weight)
     fused._split = [w.shape[0] for w in ws]
     return fused
 
@@ -102,21 +104,64 @@ STACKED_MAX_ROWS = 128  # measured on Llama-8B: decode 10.1 -> 9.8 ms/step stack
 MLP_STACKED_MAX_ROWS = int(os.environ.get("MXQ_MLP_STACKED_MAX_ROWS", 1 << 30))
 
 
-def _fused_still_valid(fused: Optional[MXInferenceLinear], mods, x: torch.Tensor, max_rows: int = 0) -> bool:
+def _weight_rows(m):
+    """(device, address of row 0, row pitch in bytes, rows) of a layer's resident weight codes: the reference-layout codes of
+    an MXInferenceLinear or the packed operand stream of a PackedMXLinear; None for anything else"""
+    from .packed_linear import PackedMXLinear
+    if type(m) is MXInferenceLinear and isinstance(getattr(m, "weight", None), MXTensor):
+        d = m.weight._data
+    elif type(m) is PackedMXLinear:
+        d = m.weight_packed
+    else:
+        return None
+    return d.device, d.data_ptr(), d.stride(0) * d.element_size(), d.shape[0]
+
+
+def _fused_still_valid(fused, mods, x: torch.Tensor, max_rows: int = 0) -> bool:
     """the stacked layer is used for decode-sized activations, and only while the source layers still alias it (a later
     .to(device) / weight swap re-materialises them separately)"""
-    if fused is None or fused.weight._data.device != x.device or x.numel() > (max_rows or STACKED_MAX_ROWS) * x.shape[-1]:
+    if fused is None:
+        return False
+    fw = _weight_rows(fused)
+    if fw is None or fw[0] != x.device or x.numel() > (max_rows or STACKED_MAX_ROWS) * x.shape[-1]:
         return False
     row = 0
-    base, es = fused.weight._data.data_ptr(), fused.weight._data.stride(0)
     for m, n in zip(mods, fused._split):
-        w = m.weight
-        if not isinstance(w, MXTensor) or w._data.data_ptr() != base + row * es or w.shape[0] != n:
+        w = _weight_rows(m)  # (same class as the stacked layer: both reference layout, or both packed by pack_linear_)
+        if w is None or type(m) is not type(fused) or w[1] != fw[1] + row * fw[2] or w[3] != n:
             return False
         if (m.bias is None) != (fused.bias is None) or (m.bias is not None and m.bias.data_ptr() != fused.bias.data_ptr() + row * fused.bias.element_size()):
             return False
         row += n
     return True
+
+
+def pack_stacked_(block: nn.Module) -> int:
+    """`pack_linear_` support: a block that owns a stacked projection (`_qkv` / `_gate_up`) gets the STACKED weight packed once
+    and its per-projection layers replaced by PackedMXLinear views of row slices of that stream, so the dense 4 / 6-bit form is
+    the only resident copy (no reference-layout codes left behind in the stacked layer).  Returns the number of layers packed."""
+    from .packed_linear import PackedMXLinear
+    n = 0
+    for attr, names in (("_qkv", ("q_proj", "k_proj", "v_proj")), ("_gate_up", ("gate_proj", "up_proj"))):
+        fused = block.__dict__.get(attr)
+        if fused is None or type(fused) is not MXInferenceLinear or not all(hasattr(block, k) for k in names):
+            continue
+        mods = [getattr(block, k) for k in names]
+        if not all(type(m) is MXInferenceLinear for m in mods) or not _fused_still_valid(fused, mods, fused.weight._data.new_empty(0, fused.in_features)):
+            continue
+        packed = PackedMXLinear.from_mx_linear(fused)
+        if packed is None:
+            continue
+        packed._split = list(fused._split)
+        row = 0
+        for k, m, rows in zip(names, mods, packed._split):
+            view = PackedMXLinear.view_of(packed, row, rows, None if m.bias is None else m.bias)
+            m._parameters.pop("weight", None)
+            setattr(block, k, view)
+            row += rows
+            n += 1
+        object.__setattr__(block, attr, packed)
+    return n
 
 
 def _repeat_heads(t: MXTensor, n_rep: int) -> MXTensor:
@@ -140,7 +185,10 @@ def _additive_mask(mask: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     ref, add = _mask_cache
     if ref is not None and ref[0]() is mask and ref[1] == mask._version and add.dtype == dtype and not torch.cuda.is_current_stream_capturing():
         return add
-    add = torch.zeros_like(mask, dtype=dtype).masked_fill_(~mask, float("-inf"))
+    # finfo.min, not -inf (what transformers' eager mask and the reference's 4.44 causal mask use): a query row that may attend
+    # to nothing -- left padding under the sdpa mask interface -- then softmaxes to a uniform row instead of NaN, and NaN would
+    # spread to every token of the batch through the next layer's K / V
+    add = torch.zeros_like(mask, dtype=dtype).masked_fill_(~mask, torch.finfo(dtype).min)
     if not torch.cuda.is_current_stream_capturing():
         _mask_cache = ((weakref.ref(mask), mask._version), add)
     return add

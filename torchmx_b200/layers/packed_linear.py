@@ -60,6 +60,24 @@ class PackedMXLinear(torch.nn.Module):
         if not keep_source:
             w.__dict__.pop(mx_gemm._SHADOW_ATTR, None)
             lin._parameters.pop("weight", None)
+        mx_gemm.mark_static(new)
+        return new
+
+    @classmethod
+    @torch.no_grad()
+    def view_of(cls, stacked: "PackedMXLinear", row0: int, rows: int, bias=None) -> "PackedMXLinear":
+        """a layer over rows [row0, row0 + rows) of `stacked`'s operand stream and scales (aliases, nothing is copied): the
+        per-projection face of a stacked q/k/v or gate/up weight"""
+        new = cls.__new__(cls)
+        torch.nn.Module.__init__(new)
+        new.in_features, new.out_features, new.qconfig, new.operand_format = stacked.in_features, rows, stacked.qconfig, stacked.operand_format
+        new.register_buffer("weight_packed", stacked.weight_packed[row0:row0 + rows])
+        new.register_buffer("weight_scale", stacked.weight_scale[row0:row0 + rows])
+        if bias is None:
+            new.register_parameter("bias", None)
+        else:
+            new.bias = bias
+        mx_gemm.mark_static(new)
         return new
 
     @torch.no_grad()
@@ -91,4 +109,4 @@ class PackedMXLinear(torch.nn.Module):
         if isinstance(x, MXTensor):
             assert x._elem_dtype == ac.elem_dtype and x._block_size == ac.block_size, "activation was quantized with another config"
         return mx_gemm.linear_packed_weight(x, self.weight_packed, self.weight_scale, self.operand_format, self.bias, ac.elem_dtype,
-                                            env.MX_EXACT_QUANTIZATION == "True")
+                                            env.MX_EXACT_QUANTIZATION == "True", owner=self)

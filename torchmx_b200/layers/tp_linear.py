@@ -144,10 +144,10 @@ class RowParallelMXLinear(MXInferenceLinear):
             from .. import mx_gemm
             rows = x.numel() // x.shape[-1]
             view, hdl = pool.next(rows)
-            mx_gemm.set_fused_output(view, hdl.multicast_ptr)
-            y = super().forward(x)
-            if mx_gemm.take_fused_output() is None:  # the GEMM took the buffer: its epilogue already reduced across ranks
-                hdl.barrier(channel=0)               # every rank's adds have landed everywhere
+            target = mx_gemm.FusedOutput(view, hdl.multicast_ptr)
+            y = super().forward(x, _fused=target)
+            if target.taken:             # the GEMM took the buffer: its epilogue already reduced across ranks
+                hdl.barrier(channel=0)   # every rank's adds have landed everywhere
                 return y
             # the operands did not qualify for the fused epilogue: y is a plain local partial
         else:

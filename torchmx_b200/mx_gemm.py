@@ -26,22 +26,51 @@ _SHADOW_ATTR = "_mxq_e4m3_shadow"
 
 stats = {"tensor_core": 0, "fallback": 0, "transcode": 0, "fused_allreduce": 0}
 
-# Set by RowParallelMXLinear (fused all-reduce mode) around its F.linear call: (output view of a symmetric buffer, multicast
-# address of that view).  The next tensor-core launch writes nothing locally: it adds its partial into every rank's buffer
-# through the multicast address (mxq_gemm_args_t.d_multicast) and clears the slot, which tells the layer it was taken.
-_fused_out = None
+class FusedOutput:
+    """Target of a fused GEMM + all-reduce launch, handed EXPLICITLY from RowParallelMXLinear.forward down to the launch (no
+    module-level state: layers are driven from arbitrary threads, torchmx/examples/quantized_llama_chat.py:123-129): `view` is
+    the [rows, features] output view of a symmetric buffer, `multicast_ptr` the NVLink multicast address of that view.  A
+    tensor-core launch that can honour it writes nothing locally -- its epilogue adds the partial into every rank's buffer
+    (mxq_gemm_args_t.d_multicast) -- and sets `taken`; otherwise `taken` stays False and the layer all-reduces with NCCL."""
+    __slots__ = ("view", "multicast_ptr", "taken")
+
+    def __init__(self, view, multicast_ptr: int):
+        self.view, self.multicast_ptr, self.taken = view, multicast_ptr, False
 
 
-def set_fused_output(out_view, multicast_ptr: int) -> None:
-    global _fused_out
-    _fused_out = (out_view, multicast_ptr)
+# Dispatch overrides for tests (every value maps to a documented field of mxq_gemm_args_t, include/mxq.h): keep the CTA-pair
+# tiles on small grids, pin the decode kernel's K split count, keep fp4 x fp4 on kind::mxf8f6f4, launch without PDL.
+overrides = {"wide_tiles": False, "split_k": 0, "no_mxf4": False, "no_pdl": False}
 
 
-def take_fused_output():
-    """-> the pending (view, ptr) if no launch consumed it (the layer then falls back to NCCL), else None"""
-    global _fused_out
-    pending, _fused_out = _fused_out, None
-    return pending
+def _flags(static_b: bool) -> int:
+    return ((_C.GEMM_B_STATIC if static_b else 0) | (_C.GEMM_WIDE_TILES if overrides["wide_tiles"] else 0)
+            | (_C.GEMM_NO_MXF4 if overrides["no_mxf4"] else 0) | (_C.GEMM_NO_PDL if overrides["no_pdl"] else 0))
+
+
+def mark_static(w) -> None:
+    """Declare an MXTensor long-lived (a layer's pre-quantized weight): nothing enqueued from now on writes its codes / scales,
+    so -- once the kernels that produced them have finished -- the decode kernel may prefetch them before its predecessor in
+    the stream is done (MXQ_GEMM_B_STATIC).  A CUDA event recorded here tells `_static_b` when that is the case.  `w` is an
+    MXTensor (the mark goes on the long-lived tensor its views come from) or any object that owns operand buffers (a module)."""
+    dev = w._data.device if isinstance(w, MXTensor) else next(iter(w.buffers())).device
+    w = getattr(w, "_mxq_origin", w)
+    if dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        w.__dict__["_mxq_static"] = ev
+
+
+def _static_b(b_origin) -> bool:
+    st = b_origin.__dict__.get("_mxq_static")
+    if st is None:
+        return False
+    if st is True:
+        return True
+    if torch.cuda.is_current_stream_capturing() or not st.query():  # producers still in flight: this launch waits for them
+        return False
+    b_origin.__dict__["_mxq_static"] = True
+    return True
 
 
 def set_enabled(flag: bool) -> None:
@@ -122,9 +151,10 @@ def _qualifies(t: MXTensor) -> bool:
 
 
 def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs, sfb_bs, out, a_fmt=FMT_E4M3_BYTES, b_fmt=FMT_E4M3_BYTES,
-            d_multicast: int = 0, x_hp: Optional[torch.Tensor] = None, x_flags: int = 0) -> bool:
+            d_multicast: int = 0, x_hp: Optional[torch.Tensor] = None, x_flags: int = 0, static_b: bool = False) -> bool:
     g = _C.GemmArgs()
     g.a_format, g.b_format = a_fmt, b_fmt
+    g.flags, g.split_k = _flags(static_b), overrides["split_k"]
     g.d_multicast = d_multicast or None
     if x_hp is not None:  # fused activation quantization: the kernel reads the bf16 activation itself
         g.x_bf16, g.ldx, g.x_quant_flags = x_hp.data_ptr(), x_hp.stride(-2), x_flags
@@ -143,10 +173,11 @@ def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs
     return True
 
 
-def try_tensor_core(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back, count_fallback: bool = True) -> Optional[torch.Tensor]:
+def try_tensor_core(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back, count_fallback: bool = True,
+                    fused: Optional[FusedOutput] = None) -> Optional[torch.Tensor]:
     out = None
     if not _DISABLED and not torch.compiler.is_compiling() and _qualifies(a) and _qualifies(b):
-        out = _dispatch(aten_op, a, b, extra_front, extra_back)
+        out = _dispatch(aten_op, a, b, extra_front, extra_back, fused)
     if out is not None:
         stats["tensor_core"] += 1
     elif count_fallback:
@@ -154,7 +185,7 @@ def try_tensor_core(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back, 
     return out
 
 
-def _dispatch(aten_op, a, b, extra_front, extra_back):
+def _dispatch(aten_op, a, b, extra_front, extra_back, fused: Optional[FusedOutput] = None):
     bias = None
     if aten_op is aten.linear.default:
         bias = extra_back[0] if extra_back else None
@@ -206,10 +237,8 @@ def _dispatch(aten_op, a, b, extra_front, extra_back):
     b_e, b_fmt = _operand_rows(b_codes, b._elem_dtype, b_origin if not batched else None)
     if a_e.stride(-1) != 1 or b_e.stride(-1) != 1:
         return None
-    global _fused_out
-    fused = _fused_out
-    if fused is not None and not batched and fused[0].shape == (M, N) and fused[0].is_contiguous():
-        out, d_mc = fused[0], fused[1]
+    if fused is not None and not batched and fused.view.shape == (M, N) and fused.view.is_contiguous():
+        out, d_mc = fused.view, fused.multicast_ptr
     else:
         fused, d_mc = None, 0
         out = torch.empty(lead_shape + (N,), dtype=torch.bfloat16, device=a._data.device)
@@ -221,14 +250,15 @@ def _dispatch(aten_op, a, b, extra_front, extra_back):
             return None  # expanded (stride 0) batch: not expressible as a TMA stride
     else:
         strides = (0, 0, 0, 0)
-    ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out, a_fmt, b_fmt, d_mc)
+    static_b = not batched and _static_b(b_origin)
+    ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out, a_fmt, b_fmt, d_mc, static_b=static_b)
     if ok and fused is not None:
-        _fused_out = None  # consumed
+        fused.taken = True
         stats["fused_allreduce"] += 1
         return out.view(lead_shape + (N,))
     if not ok and fused is not None:  # shape not supported with the fused epilogue: plain output, the layer all-reduces it
         out = torch.empty(lead_shape + (N,), dtype=torch.bfloat16, device=a._data.device)
-        ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out, a_fmt, b_fmt, 0)
+        ok = _launch(a_e, sfa, b_e, sfb, bias, batch, M, N, K, *strides, out, a_fmt, b_fmt, 0, static_b=static_b)
     return out if ok else None
 
 
@@ -237,11 +267,10 @@ _FUSED_ACT = os.environ.get("MXQ_FUSED_ACT_QUANT", "1") != "0"
 FUSED_ACT_MAX_ROWS = 64
 
 
-def linear_fused_act_quant(x: torch.Tensor, w: MXTensor, bias, hw_exact: bool) -> Optional[torch.Tensor]:
+def linear_fused_act_quant(x: torch.Tensor, w: MXTensor, bias, hw_exact: bool, fused: Optional[FusedOutput] = None) -> Optional[torch.Tensor]:
     """MXInferenceLinear.forward for decode-sized activations in ONE launch: y = quantize_mx(x, float8_e4m3, 32) @ w^T (+ bias)
     with the quantization done inside the weight-streaming kernel (bit-identical to the two-launch path).  Returns None when
     the operands do not qualify; the caller then quantizes with K1 and goes through `try_tensor_core`."""
-    global _fused_out
     if _DISABLED or not _FUSED_ACT or torch.compiler.is_compiling() or type(x) is not torch.Tensor or not x.is_cuda or x.dtype != torch.bfloat16 or not _qualifies(w):
         return None
     K = x.shape[-1]
@@ -255,23 +284,23 @@ def linear_fused_act_quant(x: torch.Tensor, w: MXTensor, bias, hw_exact: bool) -
         return None
     if bias is not None and (isinstance(bias, MXTensor) or bias.dtype != torch.bfloat16 or bias.dim() != 1 or not bias.is_contiguous()):
         return None
-    b_e, b_fmt = _operand_rows(wk[0], w._elem_dtype, getattr(w, "_mxq_origin", w))
+    w_origin = getattr(w, "_mxq_origin", w)
+    b_e, b_fmt = _operand_rows(wk[0], w._elem_dtype, w_origin)
     N = w.shape[0]
     x2 = x.view(rows, K)
-    fused = _fused_out
-    if fused is not None and fused[0].shape == (rows, N) and fused[0].is_contiguous():
-        out, d_mc = fused[0], fused[1]
+    if fused is not None and fused.view.shape == (rows, N) and fused.view.is_contiguous():
+        out, d_mc = fused.view, fused.multicast_ptr
     else:
         fused, d_mc = None, 0
         out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.bfloat16, device=x.device)
     ok = _launch(None, None, b_e, wk[1], bias, 1, rows, N, K, 0, 0, 0, 0, out, FMT_E4M3_BYTES, b_fmt, d_mc, x_hp=x2,
-                 x_flags=_C.FLAG_HW_EXACT if hw_exact else 0)
+                 x_flags=_C.FLAG_HW_EXACT if hw_exact else 0, static_b=_static_b(w_origin))
     if not ok:
         return None
     stats["tensor_core"] += 1
     stats["fused_act_quant"] = stats.get("fused_act_quant", 0) + 1
     if fused is not None:
-        _fused_out = None
+        fused.taken = True
         stats["fused_allreduce"] += 1
         return out.view(tuple(x.shape[:-1]) + (N,))
     return out
@@ -299,7 +328,7 @@ def unpack_weight(packed: torch.Tensor, fmt: int, elem: dtypes.DType) -> torch.T
     return out
 
 
-def linear_packed_weight(x, b_e: torch.Tensor, sfb: torch.Tensor, b_fmt: int, bias, act_elem: dtypes.DType, hw_exact: bool) -> torch.Tensor:
+def linear_packed_weight(x, b_e: torch.Tensor, sfb: torch.Tensor, b_fmt: int, bias, act_elem: dtypes.DType, hw_exact: bool, owner=None) -> torch.Tensor:
     """y = quantize_mx(x, act_elem, 32) @ W^T (+ bias) for a weight held only as its tensor-core operand (`pack_weight`).
     x: bf16 [..., K] or an MXTensor already quantized with the layer's activation config.  Decode-sized bf16 activations
     are quantized inside the GEMM; everything else goes K1 -> K3.  Raises if the launch is refused: there is no other path."""
@@ -312,10 +341,11 @@ def linear_packed_weight(x, b_e: torch.Tensor, sfb: torch.Tensor, b_fmt: int, bi
     out = torch.empty(lead + (N,), dtype=torch.bfloat16, device=b_e.device)
     if rows == 0:
         return out
+    static_b = owner is not None and _static_b(owner)
     if (not isinstance(x, MXTensor) and _FUSED_ACT and act_elem == dtypes.float8_e4m3 and rows <= FUSED_ACT_MAX_ROWS and x.is_contiguous()
             and x.dtype == torch.bfloat16):
         ok = _launch(None, None, b_e, sfb, bias, 1, rows, N, K, 0, 0, 0, 0, out, FMT_E4M3_BYTES, b_fmt, 0, x_hp=x.view(rows, K),
-                     x_flags=_C.FLAG_HW_EXACT if hw_exact else 0)
+                     x_flags=_C.FLAG_HW_EXACT if hw_exact else 0, static_b=static_b)
         if ok:
             stats["tensor_core"] += 1
             stats["fused_act_quant"] = stats.get("fused_act_quant", 0) + 1
@@ -324,7 +354,7 @@ def linear_packed_weight(x, b_e: torch.Tensor, sfb: torch.Tensor, b_fmt: int, bi
     assert _qualifies(x_mx) and x_mx._block_dim == x_mx._data.dim() - 1 and x_mx._data.is_contiguous(), "activation cannot run on the tensor-core path"
     a_codes, sfa = x_mx._data.reshape(rows, -1), x_mx._scale_e8m0.reshape(rows, -1)
     a_e, a_fmt = _operand_rows(a_codes, x_mx._elem_dtype, None)
-    if not _launch(a_e, sfa, b_e, sfb, bias, 1, rows, N, K, 0, 0, 0, 0, out, a_fmt, b_fmt, 0):
+    if not _launch(a_e, sfa, b_e, sfb, bias, 1, rows, N, K, 0, 0, 0, 0, out, a_fmt, b_fmt, 0, static_b=static_b):
         raise RuntimeError(f"mxq_gemm refused [{rows}, {K}] x [{N}, {K}]^T for a packed-only weight: {_C.lib().mxq_last_error().decode()}")
     stats["tensor_core"] += 1
     return out

@@ -105,8 +105,12 @@ def pack_linear_(model: torch.nn.Module) -> int:
     `PackedMXLinear` whose only copy of the weight is the dense 4 / 6-bit operand stream (0.5 / 0.75 B per element + scales;
     SURVEY §8f-3).  Same outputs bit for bit, smaller HBM footprint and `state_dict`.  Returns the number of layers packed;
     layers that need the dequantize path (int8 elements, in_features % 128 != 0, meta weights) are left alone."""
+    from .layers.mx_llama_attention import pack_stacked_
     from .layers.packed_linear import PackedMXLinear
     n = 0
+    for blk in list(model.modules()):  # blocks that own stacked q/k/v or gate/up weights: pack the stacked stream, alias the parts
+        if "_qkv" in blk.__dict__ or "_gate_up" in blk.__dict__:
+            n += pack_stacked_(blk)
 
     def replace(mod):
         nonlocal n
@@ -132,4 +136,8 @@ def unpack_linear_(model: torch.nn.Module) -> int:
         return mod.to_mx_linear()
 
     _swap_children(model, replacement_fn=replace, filter_fn=lambda mod, fqn: type(mod) is PackedMXLinear)
+    for blk in model.modules():  # stacked q/k/v / gate/up streams the blocks still hold: their parts are separate layers again
+        for attr in ("_qkv", "_gate_up"):
+            if type(blk.__dict__.get(attr)) is PackedMXLinear:
+                object.__setattr__(blk, attr, None)
     return n
