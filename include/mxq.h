@@ -159,6 +159,38 @@ typedef struct {
 #define MXQ_GEMM_NO_MXF4 8u
 MXQ_API int mxq_gemm(const mxq_gemm_args_t *args, int device, void *stream);
 
+/*
+ * MX matmul, general operands  <->  the same aten overrides (torchmx/ops.py:29-41, 60-68, 99-119) for every operand pair
+ * mxq_gemm cannot take: int8 elements (examples/quantized_llama_chat.py:41-71), block sizes other than 32
+ * (tests/layers/test_mx_linear.py:64-114 uses 2), blocks that do not run along the contraction (Readme.md:32-44: B blocked
+ * along N), padded tensors, K % 128 != 0, arbitrary strides / expanded batches.  It is the reference's own recipe --
+ * dequantize both operands to bf16 exactly as mxq_dequantize does, bf16 x bf16 products, fp32 accumulation, one rounding to
+ * bf16 -- fused into one kernel (tcgen05.mma kind::f16 on tiles dequantized into shared memory), so only the accumulation
+ * order differs from dequantize-then-matmul.
+ *
+ * An operand is the LOGICAL matrix X[batch][rows][K] (A: rows = M; B: rows = N, i.e. D = A * B^T) addressed through strides:
+ *   element (r, k) has its code byte at  codes + b*batch_stride + r*row_stride + k*k_stride ;
+ *   MXQ_ELEM_E2M1 is packed two per byte along the BLOCKED axis (high nibble = even index, torchmx/utils.py:145): the index
+ *   along that axis is halved (k >> 1 when blocked_along_k, else r >> 1) before the stride is applied;
+ *   its scale byte is at  scales + b*sbatch_stride + r*srow_stride + (k / block_size)*sk_stride  when blocked_along_k,
+ *   else at  scales + b*sbatch_stride + (r / block_size)*srow_stride + k*sk_stride.
+ * Any stride may be 0 (expanded dims) or describe a transposed view.  K is the logical extent (padding excluded).
+ * bias: NULL or N bf16; d: bf16 [batch][M][N], row stride ldd, batch stride d_batch_stride (elements).
+ */
+typedef struct {
+    const void *codes; const uint8_t *scales;
+    int64_t row_stride, k_stride, batch_stride;
+    int64_t srow_stride, sk_stride, sbatch_stride;
+    int elem /* mxq_elem_t */; int block_size; int blocked_along_k;
+} mxq_operand_t;
+typedef struct {
+    mxq_operand_t a, b;
+    const void *bias;
+    void *d; int64_t ldd, d_batch_stride;
+    int64_t batch, M, N, K;
+} mxq_gemm_dequant_args_t;
+MXQ_API int mxq_gemm_dequant(const mxq_gemm_dequant_args_t *args, int device, void *stream);
+
 /* Operand storage formats of mxq_gemm.  The packed formats are what the sm_100a TMA unit expands on the fly
  * (CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B / 16U6_ALIGN16B) and kind::mxf8f6f4 consumes natively, so a 4-bit operand
  * costs 0.5 B and a 6-bit operand 0.75 B of HBM traffic per element instead of 1 B:

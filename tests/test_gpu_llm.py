@@ -208,3 +208,69 @@ def test_stacked_projections_match_separate_launches(tiny_llama):
         a, b = fused(input_ids=ids8).logits, plain(input_ids=ids8).logits
     assert _sqnr(b, a) > 40, _sqnr(b, a)  # (a stale stacked k_proj would be a different weight matrix altogether)
     assert _sqnr(d_f, a) < 30             # ... and the swap did change the output
+
+
+def test_quantize_llm_then_pack_linear_runs_and_is_bit_identical(tiny_llama):
+    """`quantize_llm_` followed by `pack_linear_`: the blocks' stacked q/k/v and gate/up weights are packed ONCE and the
+    per-projection layers become views of that stream (nothing is left behind in the reference layout), prefill- and decode-sized
+    forwards work and equal the unpacked model bit for bit; `unpack_linear_` restores the reference `state_dict`."""
+    import copy
+    import torchmx  # noqa: F401
+    from torchmx.config import MXConfig, QAttentionConfig, QLinearConfig
+    from torchmx.layers.mx_linear import MXInferenceLinear
+    from torchmx.layers.packed_linear import PackedMXLinear
+    from torchmx.quant_api import pack_linear_, quantize_llm_, unpack_linear_
+    model, cfg = tiny_llama
+    lin = QLinearConfig(weights_config=MXConfig("float6_e3m2", 32), activations_config=MXConfig("float8_e4m3", 32))
+    qm = copy.deepcopy(model)
+    quantize_llm_(qm, QAttentionConfig(projection_config=lin), lin)
+    sd_ref = {k: (v._data.clone(), v._scale_e8m0.clone()) for k, v in qm.state_dict().items() if hasattr(v, "_data")}
+    ids = torch.randint(0, cfg.vocab_size, (2, 96), device=DEV)
+    with torch.no_grad():
+        want_prefill, want_decode = qm(input_ids=ids).logits, qm(input_ids=ids[:, :3]).logits
+    n = pack_linear_(qm)
+    assert n == 2 * 7 + 1
+    att, mlp = qm.model.layers[0].self_attn, qm.model.layers[0].mlp
+    assert all(type(getattr(att, k)) is PackedMXLinear for k in ("q_proj", "k_proj", "v_proj", "o_proj"))
+    assert type(att.__dict__["_qkv"]) is PackedMXLinear and type(mlp.__dict__["_gate_up"]) is PackedMXLinear
+    assert att.k_proj.weight_packed.data_ptr() == att.__dict__["_qkv"].weight_packed[att.q_proj.out_features:].data_ptr()
+    assert not any(isinstance(m, MXInferenceLinear) for m in qm.modules())
+    with torch.no_grad():
+        assert torch.equal(qm(input_ids=ids).logits, want_prefill)
+        assert torch.equal(qm(input_ids=ids[:, :3]).logits, want_decode)
+    assert unpack_linear_(qm) == 2 * 7 + 1
+    for k, v in qm.state_dict().items():
+        if hasattr(v, "_data"):
+            assert torch.equal(v._data, sd_ref[k][0]) and torch.equal(v._scale_e8m0, sd_ref[k][1]), k
+    with torch.no_grad():
+        assert torch.equal(qm(input_ids=ids).logits, want_prefill)
+
+
+def test_left_padded_batch_with_sdpa_mask_has_no_nan(tiny_llama):
+    """transformers' sdpa mask interface hands the attention block BOOLEAN masks in which the query rows of left-padding
+    tokens may attend to nothing.  The MX attention block must not turn those rows into NaN (an all -inf softmax row would,
+    and the NaN would reach every real token through the next layer's K / V): it fills with finfo.min like the reference's
+    additive mask.  Real tokens of the padded sequence must match the same sequence run alone."""
+    import copy
+    import torchmx  # noqa: F401
+    from torchmx.config import MXConfig, QAttentionConfig, QLinearConfig
+    from torchmx.quant_api import quantize_llm_
+    model, cfg = tiny_llama
+    qm = copy.deepcopy(model)
+    qm.config._attn_implementation = "sdpa"
+    lin = QLinearConfig(weights_config=MXConfig("float6_e3m2", 32), activations_config=MXConfig("float8_e4m3", 32))
+    e = MXConfig("float8_e4m3", 32)
+    quantize_llm_(qm, QAttentionConfig(projection_config=lin, query_config=e, key_config=e, value_config=e, attention_weights_config=e), lin)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    ids = torch.randint(1, cfg.vocab_size, (2, 64), device=DEV, generator=g)
+    mask = torch.ones(2, 64, dtype=torch.long, device=DEV)
+    pad = 24
+    mask[1, :pad] = 0  # sequence 1 is left-padded
+    with torch.no_grad():
+        out = qm(input_ids=ids, attention_mask=mask).logits
+    assert not torch.isnan(out[0]).any() and not torch.isnan(out[1, pad:]).any(), "NaN leaked into real tokens"
+    with torch.no_grad():
+        alone = qm(input_ids=ids[1:, pad:], position_ids=torch.arange(64 - pad, device=DEV)[None]).logits
+        both = qm(input_ids=ids, attention_mask=mask, position_ids=(mask.cumsum(-1) - 1).clamp(min=0)).logits
+    assert not torch.isnan(both[1, pad:]).any()
+    assert _sqnr(alone[0], both[1, pad:]) > 20, _sqnr(alone[0], both[1, pad:])

@@ -16,7 +16,7 @@ GEMM_B_STATIC, GEMM_WIDE_TILES, GEMM_NO_PDL, GEMM_NO_MXF4 = 1, 2, 4, 8
 ABI_VERSION = 2
 MAX_DIMS = 6
 
-EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
+EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_gemm_dequant", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
            "mxq_softmax_quantize", "mxq_silu_mul_quantize", "mxq_last_error", "mxq_version", "mxq_arch")
 
 
@@ -33,6 +33,24 @@ class GemmArgs(ctypes.Structure):
         ("d_multicast", ctypes.c_void_p),
         ("x_bf16", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("x_quant_flags", ctypes.c_int),
         ("flags", ctypes.c_uint), ("split_k", ctypes.c_int),
+    ]
+
+
+class Operand(ctypes.Structure):
+    _fields_ = [
+        ("codes", ctypes.c_void_p), ("scales", ctypes.c_void_p),
+        ("row_stride", ctypes.c_int64), ("k_stride", ctypes.c_int64), ("batch_stride", ctypes.c_int64),
+        ("srow_stride", ctypes.c_int64), ("sk_stride", ctypes.c_int64), ("sbatch_stride", ctypes.c_int64),
+        ("elem", ctypes.c_int), ("block_size", ctypes.c_int), ("blocked_along_k", ctypes.c_int),
+    ]
+
+
+class GemmDequantArgs(ctypes.Structure):
+    _fields_ = [
+        ("a", Operand), ("b", Operand),
+        ("bias", ctypes.c_void_p),
+        ("d", ctypes.c_void_p), ("ldd", ctypes.c_int64), ("d_batch_stride", ctypes.c_int64),
+        ("batch", ctypes.c_int64), ("M", ctypes.c_int64), ("N", ctypes.c_int64), ("K", ctypes.c_int64),
     ]
 
 
@@ -78,6 +96,8 @@ def lib() -> ctypes.CDLL:
                                              i32, i32, i32, i32, vp, i32, vp]
         L.mxq_gemm.restype = i32
         L.mxq_gemm.argtypes = [ctypes.POINTER(GemmArgs), i32, vp]
+        L.mxq_gemm_dequant.restype = i32
+        L.mxq_gemm_dequant.argtypes = [ctypes.POINTER(GemmDequantArgs), i32, vp]
         L.mxq_transcode_to_e4m3.restype = i32
         L.mxq_transcode_to_e4m3.argtypes = [vp, i32, i64, vp, i32, vp]
         L.mxq_pack_operand.restype = i32

@@ -16,6 +16,7 @@ cudaError_t launch_transcode(const void*, int, int64_t, void*, int, cudaStream_t
 cudaError_t launch_pack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 cudaError_t launch_unpack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 int launch_gemm(const mxq_gemm_args_t*, int, int, cudaStream_t, char*, size_t);
+namespace gemm { int launch_gemm_dequant(const mxq_gemm_dequant_args_t*, int, cudaStream_t, char*, size_t); }
 cudaError_t launch_silu_mul_quantize(const void*, const void*, int64_t, int64_t, int64_t, int64_t, int, unsigned, void*, uint8_t*, int, cudaStream_t);
 int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size_t);
 }  // namespace mxq
@@ -183,6 +184,24 @@ int mxq_gemm(const mxq_gemm_args_t* a, int device, void* stream) {
     char msg[400] = "";
     const int rc = mxq::launch_gemm(a, sm_count_of(scope.cur), scope.cur, (cudaStream_t)stream, msg, sizeof(msg));
     return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_gemm: %s", msg);
+}
+
+int mxq_gemm_dequant(const mxq_gemm_dequant_args_t* a, int device, void* stream) {
+    if (!a) return fail(MXQ_ERR_INVALID, "mxq_gemm_dequant: null args");
+    if (a->batch < 0 || a->M < 0 || a->N < 0 || a->K < 0) return fail(MXQ_ERR_INVALID, "mxq_gemm_dequant: negative extent");
+    if (a->batch == 0 || a->M == 0 || a->N == 0) return MXQ_OK;
+    if (!a->d) return fail(MXQ_ERR_INVALID, "mxq_gemm_dequant: null output");
+    for (int side = 0; side < 2; ++side) {
+        const mxq_operand_t& o = side ? a->b : a->a;
+        if (!valid_elem(o.elem)) return fail(MXQ_ERR_INVALID, "mxq_gemm_dequant: unknown element type %d", o.elem);
+        if (o.block_size < 1) return fail(MXQ_ERR_INVALID, "mxq_gemm_dequant: bad block size %d", o.block_size);
+        if (a->K > 0 && (!o.codes || !o.scales)) return fail(MXQ_ERR_INVALID, "mxq_gemm_dequant: null operand pointer");
+    }
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_gemm_dequant: selecting device");
+    char msg[400] = "";
+    const int rc = mxq::gemm::launch_gemm_dequant(a, scope.cur, (cudaStream_t)stream, msg, sizeof(msg));
+    return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_gemm_dequant: %s", msg);
 }
 
 int mxq_silu_mul_quantize(const void* gate, const void* up, int64_t rows, int64_t cols, int64_t ld_gate, int64_t ld_up, int elem, unsigned flags,

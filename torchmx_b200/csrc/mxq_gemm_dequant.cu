@@ -1,0 +1,316 @@
+// K3d: MX matmul for operands the block-scaled tensor-core instruction cannot take -- int8 elements, block sizes other than
+// 32, blocks that do not run along the contraction (README matmul: B blocked along N), padded tensors, K % 128 != 0, arbitrary
+// strides.  The reference handles every MX matmul this way (torchmx/ops.py:29-41, 60-68, 99-119): dequantize both operands to
+// bf16, then a bf16 GEMM with fp32 accumulation.  Here the two steps are one kernel:
+//
+//   D[b][m][n] = bf16( sum_k bf16(dec(A[b][m][k]) * 2^(sa-127)) * bf16(dec(B[b][n][k]) * 2^(sb-127)) (+ bias[n]) )
+//
+// * 8 producer warps read element codes and scales straight from the caller's (strided) tensors, dequantize with K2's
+//   arithmetic (exact decode, exact fp32 product, ONE rounding to bf16: bit-identical to mxq_dequantize) and write bf16
+//   K-major tiles into shared memory in the 128B-swizzled layout the tensor core reads: the bf16 operands never exist in HBM;
+// * one thread issues tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32 accumulator in TMEM, M = 128, N = 128, K = 16 per
+//   instruction), a 4-stage mbarrier ring decouples it from the producers;
+// * the producer warps then drain the accumulator (tcgen05.ld), add the bias, round once to bf16 and store.
+// Only the accumulation order differs from the reference's recipe.
+#include "mxq_tc.cuh"
+
+namespace mxq {
+namespace gemm {
+namespace dq {
+
+constexpr int TILE = 128;       // output tile: 128 x 128
+constexpr int BK = 64;          // bf16 elements per stage and row = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = kProducerThreads + 32;
+constexpr int STAGE_BYTES = TILE * BK * 2;  // 16 KB per operand
+
+struct Smem {
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + STAGES * STAGE_BYTES;
+    static constexpr int OFF_LUT = OFF_B + STAGES * STAGE_BYTES;  // 2 x 256 fp32: decoded value of every code byte, per operand
+    static constexpr int OFF_BAR = OFF_LUT + 2 * 256 * 4;
+    static constexpr int NUM_BARS = 2 * STAGES + 1;
+    static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+    static constexpr int TOTAL = OFF_TMEM_PTR + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+struct Operand {
+    const uint8_t* codes; const uint8_t* scales;
+    int64_t row_stride, k_stride, batch_stride, srow_stride, sk_stride, sbatch_stride;
+    int rows;         // M (A) or N (B)
+    int elem, block_size, along_k;
+    int bs_shift;     // log2(block_size) when it is a power of two, else -1
+};
+
+struct Params {
+    Operand a, b;
+    const uint16_t* bias; uint16_t* d;
+    int64_t ldd, d_batch;
+    int M, N, K, m_blocks, n_blocks;
+};
+
+__device__ __forceinline__ float lut_entry(int elem, uint32_t code) {
+    switch (elem) {
+    case MXQ_ELEM_E4M3: return decode_one<MXQ_ELEM_E4M3>(code);
+    case MXQ_ELEM_E3M2: return decode_one<MXQ_ELEM_E3M2>(code);
+    case MXQ_ELEM_E2M3: return decode_one<MXQ_ELEM_E2M3>(code);
+    case MXQ_ELEM_E2M1: return decode_one<MXQ_ELEM_E2M1>(code);
+    case MXQ_ELEM_E5M2: return decode_one<MXQ_ELEM_E5M2>(code);
+    default: return decode_one<MXQ_ELEM_INT8>(code);
+    }
+}
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// eight consecutive k of one operand row -> eight bf16 (one 16-byte shared-memory chunk).  `r` is the row inside the operand,
+// k0 a multiple of 8.  Rows / k past the edge give zeros.
+__device__ __forceinline__ uint4 dequant_chunk(const Operand& op, const uint8_t* codes, const uint8_t* scales, const float* lut, int r, int k0, int K) {
+    float f[8];
+    if (r >= op.rows || k0 >= K) return make_uint4(0u, 0u, 0u, 0u);
+    const bool fp4 = op.elem == MXQ_ELEM_E2M1;
+    uint32_t c[8];
+    // ---- codes
+    if (op.k_stride == 1 && (op.along_k || !fp4) && k0 + 8 <= K) {  // K-contiguous: eight codes are 8 (fp4: 4) adjacent bytes
+        if (fp4) {
+            const uint8_t* p = codes + (int64_t)r * op.row_stride + (k0 >> 1);
+            uint32_t w;
+            if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) w = *reinterpret_cast<const uint32_t*>(p);
+            else w = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // the earlier element sits in the HIGH nibble (torchmx/utils.py:145)
+                c[2 * j] = (w >> (8 * j + 4)) & 0xF;
+                c[2 * j + 1] = (w >> (8 * j)) & 0xF;
+            }
+        } else {
+            const uint8_t* p = codes + (int64_t)r * op.row_stride + k0;
+            uint32_t lo, hi;
+            if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+                const uint2 v = *reinterpret_cast<const uint2*>(p);
+                lo = v.x; hi = v.y;
+            } else {
+                lo = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+                hi = (uint32_t)p[4] | ((uint32_t)p[5] << 8) | ((uint32_t)p[6] << 16) | ((uint32_t)p[7] << 24);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c[j] = (lo >> (8 * j)) & 0xFF; c[4 + j] = (hi >> (8 * j)) & 0xFF; }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j;
+            if (k >= K) { c[j] = 0x100; continue; }  // marker: contributes zero
+            if (!fp4) {
+                c[j] = codes[(int64_t)r * op.row_stride + (int64_t)k * op.k_stride];
+            } else if (op.along_k) {
+                const uint32_t byte = codes[(int64_t)r * op.row_stride + (int64_t)(k >> 1) * op.k_stride];
+                c[j] = (k & 1) ? (byte & 0xF) : (byte >> 4);
+            } else {  // packed along the row index
+                const uint32_t byte = codes[(int64_t)(r >> 1) * op.row_stride + (int64_t)k * op.k_stride];
+                c[j] = (r & 1) ? (byte & 0xF) : (byte >> 4);
+            }
+        }
+    }
+    // ---- scales + product (exact in fp32; s == 255 -> NaN for the whole block, also for zero codes)
+    if (op.along_k && op.bs_shift >= 3) {  // the chunk lies inside one block
+        const float sc = scale_f32(scales[(int64_t)r * op.srow_stride + (int64_t)(k0 >> op.bs_shift) * op.sk_stride]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (c[j] & 0x100) ? 0.0f : lut[c[j]] * sc;
+    } else {
+        const int rb = op.along_k ? r : (op.bs_shift >= 0 ? (r >> op.bs_shift) : r / op.block_size);
+        int last = -1;
+        float sc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j;
+            if (c[j] & 0x100) { f[j] = 0.0f; continue; }
+            const int kb = op.along_k ? (op.bs_shift >= 0 ? (k >> op.bs_shift) : k / op.block_size) : k;
+            if (kb != last) {
+                sc = scale_f32(scales[(int64_t)rb * op.srow_stride + (int64_t)kb * op.sk_stride]);
+                last = kb;
+            }
+            f[j] = lut[c[j]] * sc;
+        }
+    }
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);
+    uint64_t* full = bars;             // both bf16 tiles of the stage written (count 256: every producer thread)
+    uint64_t* empty = bars + STAGES;   // MMAs of the stage retired (count 1, tcgen05.commit)
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::OFF_TMEM_PTR);
+    float* lut = reinterpret_cast<float*>(smem + Smem::OFF_LUT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_batch = p.m_blocks * p.n_blocks;
+    const int b = blockIdx.x / tiles_per_batch;
+    const int t = blockIdx.x - b * tiles_per_batch;
+    const int nb = t / p.m_blocks, mb = t - nb * p.m_blocks;  // m fastest: neighbouring CTAs share a B panel in L2
+    const int k_steps = (p.K + BK - 1) / BK;
+
+    if (threadIdx.x < 256) {
+        lut[threadIdx.x] = lut_entry(p.a.elem, threadIdx.x);
+        lut[256 + threadIdx.x] = lut_entry(p.b.elem, threadIdx.x);
+    }
+    if (warp == 8) {
+        if (elect_one()) {
+            for (int i = 0; i < STAGES; ++i) {
+                mbar_init(&full[i], kProducerThreads);
+                mbar_init(&empty[i], 1);
+            }
+            mbar_init(tmem_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<128>(tmem_ptr);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 8) {
+        // ================= producers: thread = one row of the A tile (threads 0..127) or of the B tile (128..255) =================
+        const bool is_b = threadIdx.x >= 128;
+        const Operand& op = is_b ? p.b : p.a;
+        const int row = threadIdx.x & 127;
+        const int r = (is_b ? nb : mb) * TILE + row;
+        const uint8_t* codes = op.codes + (int64_t)b * op.batch_stride;
+        const uint8_t* scales = op.scales + (int64_t)b * op.sbatch_stride;
+        const float* my_lut = lut + (is_b ? 256 : 0);
+        uint8_t* tile0 = smem + (is_b ? Smem::OFF_B : Smem::OFF_A) + row * 128;
+        uint32_t stage = 0, phase = 0;
+        for (int ks = 0; ks < k_steps; ++ks) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* dst = tile0 + stage * STAGE_BYTES;
+#pragma unroll 2
+            for (int c = 0; c < 8; ++c)  // 16-byte chunk c of the row lives at chunk c ^ (row & 7) (SWIZZLE_128B)
+                *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = dequant_chunk(op, codes, scales, my_lut, r, ks * BK + c * 8, p.K);
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&full[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        // ================= epilogue: warp (quadrant, column half) drains 32 rows x 64 columns =================
+        const int quad = warp & 3, half = warp >> 2;
+        if (k_steps > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        const int m = mb * TILE + quad * 32 + lane;
+        uint16_t* drow = p.d + (int64_t)b * p.d_batch + (int64_t)m * p.ldd;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            if (k_steps > 0) {
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * 64 + c * 32, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0u;
+            }
+            const int col0 = nb * TILE + half * 64 + c * 32;
+            if (m < p.M && col0 < p.N) {
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (col0 + i < p.N) f[i] += __uint_as_float((uint32_t)p.bias[col0 + i] << 16);
+                }
+                if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(drow + col0) & 15) == 0)) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 o;
+                        o.x = pack_bf16x2(f[8 * i + 0], f[8 * i + 1]);
+                        o.y = pack_bf16x2(f[8 * i + 2], f[8 * i + 3]);
+                        o.z = pack_bf16x2(f[8 * i + 4], f[8 * i + 5]);
+                        o.w = pack_bf16x2(f[8 * i + 6], f[8 * i + 7]);
+                        *reinterpret_cast<uint4*>(drow + col0 + 8 * i) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (col0 + i < p.N) drow[col0 + i] = (uint16_t)pack_bf16x2(f[i], 0.0f);
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+        // kind::f16 descriptor: fp32 accumulator (bit 4), bf16 A and B (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+        constexpr uint64_t HI_OPERAND = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutSw128 << 61);
+        const uint32_t a_lo0 = smem_u32(smem + Smem::OFF_A) >> 4, b_lo0 = smem_u32(smem + Smem::OFF_B) >> 4;
+        uint32_t stage = 0, phase = 0;
+        for (int ks = 0; ks < k_steps; ++ks) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4), b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)  // 16 bf16 = 32 bytes further along the swizzle row
+                    tc_mma_f16(tmem_base, HI_OPERAND | (a_lo + k * 2), HI_OPERAND | (b_lo + k * 2), idesc, (ks | k) != 0);
+                tc_commit(&empty[stage]);
+                if (ks == k_steps - 1) tc_commit(tmem_full);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<128>(tmem_base);
+    }
+}
+
+static bool fill_operand(Operand& o, const mxq_operand_t& s, int64_t rows) {
+    o.codes = (const uint8_t*)s.codes; o.scales = s.scales;
+    o.row_stride = s.row_stride; o.k_stride = s.k_stride; o.batch_stride = s.batch_stride;
+    o.srow_stride = s.srow_stride; o.sk_stride = s.sk_stride; o.sbatch_stride = s.sbatch_stride;
+    o.rows = (int)rows; o.elem = s.elem; o.block_size = s.block_size; o.along_k = s.blocked_along_k ? 1 : 0;
+    o.bs_shift = -1;
+    for (int sft = 0; sft < 31; ++sft)
+        if ((1 << sft) == s.block_size) o.bs_shift = sft;
+    return true;
+}
+
+}  // namespace dq
+
+int launch_gemm_dequant(const mxq_gemm_dequant_args_t* a, int device, cudaStream_t stream, char* msg, size_t msg_len) {
+    using namespace dq;
+    if (a->M > 0x7FFFFFFF || a->N > 0x7FFFFFFF || a->K > 0x7FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+    dq::Params p;
+    fill_operand(p.a, a->a, a->M);
+    fill_operand(p.b, a->b, a->N);
+    p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
+    p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
+    p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
+    p.m_blocks = (int)((a->M + TILE - 1) / TILE);
+    p.n_blocks = (int)((a->N + TILE - 1) / TILE);
+    const int64_t ctas = (int64_t)p.m_blocks * p.n_blocks * a->batch;
+    if (ctas > 0x7FFFFFFF) { snprintf(msg, msg_len, "too many output tiles"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+    cudaError_t e = ensure_smem_attr((const void*)mx_gemm_dequant_kernel, Smem::DYN_BYTES, device);
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    mx_gemm_dequant_kernel<<<(unsigned)ctas, dq::kThreads, Smem::DYN_BYTES, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (dequant gemm): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    return MXQ_OK;
+}
+
+}  // namespace gemm
+}  // namespace mxq

@@ -85,7 +85,7 @@ class MXInferenceLinear(torch.nn.Linear):
             if not isinstance(self.weight, MXTensor) and bias is not None:
                 bias = bias.to(torch.bfloat16)
             w_mx = self._weight_mx()
-            out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x, w_mx, (), (bias,), count_fallback=False, fused=_fused)
+            out = mx_gemm.contract(torch.ops.aten.linear.default, x, w_mx, (), (bias,), fused=_fused, count_fallback=False)
             return out if out is not None else F.linear(x, w_mx, bias)
         if not isinstance(self.weight, MXTensor) and bias is not None:
             bias = bias.to(torch.bfloat16)
@@ -98,7 +98,7 @@ class MXInferenceLinear(torch.nn.Linear):
         x_mx = MXTensor.to_mx(x, ac.elem_dtype, ac.block_size)
         # F.linear(x_mx, w_mx, bias) reaches the same kernel through the dispatcher (aten.t + aten.mm / addmm on MXTensor
         # views, ~50 us of host time per layer); hand the operands to the tensor-core path directly when they qualify
-        out = mx_gemm.try_tensor_core(torch.ops.aten.linear.default, x_mx, w_mx, (), (bias,), count_fallback=False, fused=_fused)
+        out = mx_gemm.contract(torch.ops.aten.linear.default, x_mx, w_mx, (), (bias,), fused=_fused, count_fallback=False)
         if out is not None:
             return out
         return F.linear(x_mx, w_mx, bias)

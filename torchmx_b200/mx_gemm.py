@@ -24,7 +24,10 @@ aten = torch.ops.aten
 _DISABLED = os.environ.get("MXQ_DISABLE_TC", "0") == "1"
 _SHADOW_ATTR = "_mxq_e4m3_shadow"
 
-stats = {"tensor_core": 0, "fallback": 0, "transcode": 0, "fused_allreduce": 0}
+# tensor_core: launches of the block-scaled tcgen05 kernels (K3a/b/c); dequant_gemm: launches of the fused dequantize + bf16
+# tcgen05 kernel (K3d) for operands the block-scaled instruction cannot take; fallback: contractions that reached neither and
+# ran as K2 + aten (torch.compile tracing, non-bf16 advertised dtypes)
+stats = {"tensor_core": 0, "dequant_gemm": 0, "fallback": 0, "transcode": 0, "fused_allreduce": 0}
 
 class FusedOutput:
     """Target of a fused GEMM + all-reduce launch, handed EXPLICITLY from RowParallelMXLinear.forward down to the launch (no
@@ -175,12 +178,137 @@ def _launch(a_codes, sfa, b_codes, sfb, bias, batch, M, N, K, a_bs, sfa_bs, b_bs
 
 def try_tensor_core(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back, count_fallback: bool = True,
                     fused: Optional[FusedOutput] = None) -> Optional[torch.Tensor]:
+    """-> the contraction on the block-scaled tensor-core kernels, or None when the operands do not qualify (`count_fallback` is
+    kept for callers of the first round and ignored: `contract` does the counting)"""
     out = None
     if not _DISABLED and not torch.compiler.is_compiling() and _qualifies(a) and _qualifies(b):
         out = _dispatch(aten_op, a, b, extra_front, extra_back, fused)
     if out is not None:
         stats["tensor_core"] += 1
-    elif count_fallback:
+    return out
+
+
+# ---- K3d: every other operand pair (fused dequantize + bf16 tcgen05 GEMM, csrc/mxq_gemm_dequant.cu) ---------------------
+_DEQUANT_GEMM = os.environ.get("MXQ_DEQUANT_GEMM", "1") != "0"
+
+
+def set_dequant_gemm(flag: bool) -> bool:
+    """tests: switch K3d off so that the same call takes the reference's own recipe (K2 + aten matmul); returns the old value"""
+    global _DEQUANT_GEMM
+    prev, _DEQUANT_GEMM = _DEQUANT_GEMM, bool(flag)
+    return prev
+
+
+def _plain(t: MXTensor) -> bool:
+    return (isinstance(t, MXTensor) and type(t._data) is torch.Tensor and type(t._scale_e8m0) is torch.Tensor and t._data.is_cuda
+            and t._orig_dtype == torch.bfloat16 and t._elem_dtype.name in dtypes.ELEM_ID)
+
+
+def _collapse_rows(t: torch.Tensor):
+    """[..., K] -> row stride over all leading dims taken as ONE row index, or None when they do not collapse"""
+    if t.dim() == 1:
+        return 0
+    ld = t.stride(-2)
+    expect = ld * t.shape[-2]
+    for size, stride in zip(reversed(t.shape[:-2]), reversed(t.stride()[:-2])):
+        if size > 1 and stride != expect:
+            return None
+        expect *= size
+    return ld
+
+
+def _fill_operand(o: "_C.Operand", t: MXTensor, rows_dim: int, k_dim: int, batched: bool, collapse: bool):
+    """-> the (codes, scales) tensors the descriptor points into (the caller keeps them alive across the launch call), or None"""
+    d, s = t._data, t._scale_e8m0
+    nd = d.dim()
+    rows_dim, k_dim = rows_dim % nd, k_dim % nd
+    if t._block_dim not in (rows_dim, k_dim):
+        return None
+    if collapse and nd > 2:  # aten.linear on [..., K]: all leading dims form the row index
+        if k_dim != nd - 1:
+            return None
+        cr, sr = _collapse_rows(d), _collapse_rows(s)
+        if cr is None or sr is None:  # (not produced by the layers: make the operand dense once)
+            d, s = d.contiguous(), s.contiguous()
+            cr, sr = d.stride(-2), s.stride(-2)
+        o.row_stride, o.srow_stride = cr, sr
+    else:
+        o.row_stride, o.srow_stride = d.stride(rows_dim), s.stride(rows_dim)
+    o.codes, o.scales = d.data_ptr(), s.data_ptr()
+    o.k_stride, o.sk_stride = d.stride(k_dim), s.stride(k_dim)
+    o.batch_stride, o.sbatch_stride = (d.stride(0), s.stride(0)) if batched else (0, 0)
+    o.elem, o.block_size, o.blocked_along_k = dtypes.ELEM_ID[t._elem_dtype.name], t._block_size, 1 if t._block_dim == k_dim else 0
+    return d, s
+
+
+def try_dequant_gemm(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back) -> Optional[torch.Tensor]:
+    """The contraction of two MXTensors of ANY element type / block size / block orientation / padding / strides as one
+    kernel (`mxq_gemm_dequant`): what the reference computes as dequantize + bf16 matmul (torchmx/ops.py:29-41, 60-68,
+    99-119), without materialising the bf16 operands and without a library GEMM.  None when the call is not one of the four
+    compute overrides on plain CUDA MXTensors that advertise bf16."""
+    if not _DEQUANT_GEMM or torch.compiler.is_compiling() or not _plain(a) or not _plain(b) or a._data.device != b._data.device:
+        return None
+    bias = None
+    if aten_op is aten.linear.default:
+        bias = extra_back[0] if extra_back else None
+        b_rows, b_k = -2, -1   # weight [N, K]
+    elif aten_op is aten.addmm.default:
+        bias = extra_front[0]
+        b_rows, b_k = -1, -2   # mat2 [K, N]
+    elif aten_op in (aten.mm.default, aten.bmm.default):
+        b_rows, b_k = -1, -2
+    else:
+        return None
+    batched = aten_op is aten.bmm.default
+    if batched:
+        if a.dim() != 3 or b.dim() != 3 or a.shape[0] != b.shape[0]:
+            return None
+    elif b.dim() != 2 or a.dim() < 1 or (aten_op is not aten.linear.default and a.dim() != 2):
+        return None
+    K = a.shape[-1]
+    if K != b.shape[b_k]:
+        return None
+    N = b.shape[b_rows]
+    lead = tuple(a.shape[:-1])
+    M = 1
+    for v in (lead[1:] if batched else lead):
+        M *= v
+    batch = a.shape[0] if batched else 1
+    if bias is not None:
+        if isinstance(bias, MXTensor) or bias.dim() != 1 or bias.shape[0] != N or not bias.is_cuda:
+            return None
+        if bias.dtype != torch.bfloat16 or not bias.is_contiguous():
+            return None
+    g = _C.GemmDequantArgs()
+    keep_a = _fill_operand(g.a, a, -2, -1, batched, collapse=aten_op is aten.linear.default)
+    keep_b = _fill_operand(g.b, b, b_rows, b_k, batched, False)
+    if keep_a is None or keep_b is None:
+        return None
+    if a.dim() == 1:
+        g.a.row_stride = g.a.srow_stride = 0
+    out = torch.empty(lead + (N,), dtype=torch.bfloat16, device=a._data.device)
+    if out.numel() == 0:
+        return out
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.d, g.ldd, g.d_batch_stride = out.data_ptr(), N, M * N
+    g.batch, g.M, g.N, g.K = batch, M, N, K
+    rc = _C.lib().mxq_gemm_dequant(ctypes.byref(g), out.device.index, _stream_ptr(out))
+    if rc == _C.ERR_UNSUPPORTED_SHAPE:
+        return None
+    _C.check(rc, "mxq_gemm_dequant")
+    del keep_a, keep_b
+    stats["dequant_gemm"] += 1
+    return out
+
+
+def contract(aten_op, a: MXTensor, b: MXTensor, extra_front=(), extra_back=(), fused: Optional[FusedOutput] = None,
+             count_fallback: bool = True) -> Optional[torch.Tensor]:
+    """the MX matmul of the four compute overrides on this library's kernels: block-scaled tensor cores when the operands
+    qualify, the fused dequantize GEMM otherwise; None (counted as `fallback`) only when neither applies"""
+    out = try_tensor_core(aten_op, a, b, extra_front, extra_back, fused=fused)
+    if out is None:
+        out = try_dequant_gemm(aten_op, a, b, extra_front, extra_back)
+    if out is None and count_fallback:
         stats["fallback"] += 1
     return out
 

@@ -45,9 +45,11 @@ def _contract(aten_op, a: MXTensor, b: MXTensor, *extra_front, extra_back=()):
     """Shared body of the four compute overrides."""
     from . import mx_gemm  # late import: the GEMM host module needs MXTensor defined
 
-    out = mx_gemm.try_tensor_core(aten_op, a, b, extra_front, extra_back)
+    out = mx_gemm.contract(aten_op, a, b, extra_front, extra_back)
     if out is not None:
         return out
+    # Not reached for plain CUDA MXTensors that advertise bf16.  What is left: torch.compile tracing (the inner tensors are fake;
+    # the traced graph spells the reference's recipe with the two custom ops) and advertised dtypes other than bf16.
     return aten_op(*extra_front, _hp(a), _hp(b), *extra_back)
 
 
