@@ -285,6 +285,65 @@ def mx_matmul_extras(dev):
     return out
 
 
+def llama8b_extras():
+    """BASELINE configs[3] ("MX-Llama tokens/s"): random-init HF Llama-3-8B, weights fp6_e3m2 / activations fp8_e4m3 through the
+    public API -- `quantize_linear_` (the reference's call) and `quantize_llm_` (MX attention / MLP blocks) -- prefill of 2048
+    tokens and decode at batch 32, CUDA events; each with its roofline: prefill against the block-scaled tensor peak
+    (2 * weight elements * tokens flop), decode against streaming the weight codes + scales once per step."""
+    import gc
+
+    import torch
+    from tools import llama_bench
+    out = {}
+    peak_hbm, _ = measured_peak_gbs()
+    for key, kw in (("quantize_linear_", dict(llm_api=False)), ("quantize_llm_fused_norm", dict(llm_api=True, fuse_norm=True))):
+        try:
+            r = llama_bench.run_cfg(model="8b", steps=32, prefill_iters=3, **kw)
+        except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+            out[key] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+            continue
+        w_el = r["weight_elements"]
+        stream_bytes = w_el * (1 + 1 / 32)  # reference layout: one byte per fp6 code + one scale byte per 32
+        pre_ms = r.get("prefill_graph_ms", r["prefill_eager_ms"])
+        dec_ms = r.get("decode_graph_ms_per_step", r["decode_eager_ms_per_step"])
+        out[key] = {
+            "quantize": {"wall_s": round(r["quantize_wall_s"], 4), "gpu_ms": round(r["quantize_gpu_ms"], 2), "GB/s": round(r["quantize_GBps_gpu"], 1),
+                         "algorithmic_bytes": w_el * (2 + 1 + 1 / 32), "frac_of_hbm_peak": round(r["quantize_GBps_gpu"] / peak_hbm, 4), "linears": r["linears"]},
+            "prefill_2048": {"ms": round(pre_ms, 3), "tok/s": round(2048 / pre_ms * 1e3, 1), "eager_ms": round(r["prefill_eager_ms"], 3),
+                             "flop": 2.0 * w_el * 2048, "TFLOP/s": round(2.0 * w_el * 2048 / pre_ms / 1e9, 1),
+                             "frac_of_block_scaled_peak": round(2.0 * w_el * 2048 / pre_ms / 1e9 / 4500.0, 4)},
+            "decode_batch32": {"ms_per_step": round(dec_ms, 3), "tok/s": round(32 / dec_ms * 1e3, 1), "eager_ms_per_step": round(r["decode_eager_ms_per_step"], 3),
+                               "weight_stream_bytes": stream_bytes, "weight_stream_floor_ms": round(stream_bytes / peak_hbm / 1e6, 3),
+                               "frac_of_weight_stream_roofline": round(stream_bytes / peak_hbm / 1e6 / dec_ms, 4)},
+            "timing": "CUDA-graph replay of the whole forward (eager numbers beside it include Python dispatch)",
+            "gemm_stats": r["gemm_stats"], "resident_GB": round(r["resident_after_run_GB"], 2),
+        }
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
+
+
+def tp70b_extras(world, rank):
+    """BASELINE configs[4]: Llama-3-70B shape, fp4_e2m1 weights / fp8_e4m3 activations.  (i) layer-sharded weight quantization
+    (80 layers / N ranks, no collective), (ii) tensor-parallel MX-linear inference: column-parallel q/k/v/gate/up, row-parallel
+    o/down with an all-reduce of the bf16 [tokens, 8192] partials -- NCCL, and fused into the GEMM epilogue (NVLink multicast)
+    for decode.  Strong scaling: the same model on N GPUs; compare the lines of the N = 1, 2, 4, 8 runs."""
+    import torch
+    from tools import tp_llama_bench as tp
+    out = {}
+    try:
+        out["tp_infer"] = tp.run_infer(tp.default_args(iters=3, also_fused=True), world, rank)
+    except Exception as e:  # noqa: BLE001
+        out["tp_infer"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    torch.cuda.empty_cache()
+    try:
+        out["layer_sharded_quantize"] = tp.run_quantize(tp.default_args(mode="quantize"), world, rank)
+    except Exception as e:  # noqa: BLE001
+        out["layer_sharded_quantize"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -438,11 +497,21 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e_value = world * step_bytes(n_elems) * e2e_steps / e2e_s / 1e9 if e2e_steps else 0.0
 
-    extras = None
+    extras = llama = tp70b = None
+    del xs, xh, yhs, chs
+    torch.cuda.empty_cache()
     if rank == 0 and not args.skip_gemm and world == 1:  # single-GPU numbers; under torchrun the other ranks would only wait
-        del xs, xh, yhs, chs
-        torch.cuda.empty_cache()
         extras = mx_matmul_extras(dev)
+        torch.cuda.empty_cache()
+    if not args.skip_llama:
+        if world == 1:
+            llama = llama8b_extras()
+            import torch.distributed as dist1
+            if not dist1.is_initialized():  # the tensor-parallel harness synchronises through a process group, also with one rank
+                import socket
+                sk = socket.socket(); sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]; sk.close()
+                dist1.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=dev)
+        tp70b = tp70b_extras(world, rank)
     if rank == 0:
         cpu_threads = os.cpu_count() or 1
         cpu_rows = 2048
@@ -468,6 +537,8 @@ def run_b200(args):
                 "sample": f"{cpu_rows}x{COLS} rows of the workload (1/8), all 5 elem dtypes, quantize+dequantize, best of 2, {cpu_dt:.2f} s"},
             "kernels": {k: {"us": round(v["ms"] * 1e3, 2), "GB/s": round(v["GB/s"], 1)} for k, v in kernels.items()},
             "mx_matmul": extras,
+            "llama8b": llama,
+            "tp70b": tp70b,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -483,6 +554,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: skip the cpu_baseline leg")
     ap.add_argument("--skip-gemm", action="store_true", help="skip the secondary MX matmul numbers (rank 0, after the timed sweep)")
+    ap.add_argument("--skip-llama", action="store_true", help="skip the MX-Llama extras (8B through the public API at N = 1, 70B tensor-parallel at every N)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

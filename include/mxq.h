@@ -257,6 +257,44 @@ MXQ_API int mxq_softmax_quantize(const mxq_softmax_args_t *args, int device, voi
 MXQ_API int mxq_silu_mul_quantize(const void *gate, const void *up, int64_t rows, int64_t cols, int64_t ld_gate, int64_t ld_up,
                           int elem /* mxq_elem_t */, unsigned flags /* MXQ_FLAG_* */, void *codes, uint8_t *scales, int device, void *stream);
 
+/*
+ * (residual add +) RMSNorm (+ MX quantization)  <->  the activation every MX linear of a decoder layer receives: transformers'
+ * LlamaRMSNorm / Qwen2RMSNorm output, which the reference quantizes on entry to q/k/v and to gate/up
+ * (torchmx/layers/mx_linear.py:63-66) -- once per consuming layer; here once, inside the pass that normalises the row.
+ *     h = x (+ residual, rounded to bf16; written to residual_out);  n = bf16(h * rsqrt(mean(h^2) + eps));  y = weight * n  (bf16)
+ *     codes, scales = quantize_mx(y, elem, 32)        (same arithmetic as mxq_quantize, bit-identical given y)
+ *   x, residual, residual_out, y : bf16 [rows, hidden], row strides in elements (multiples of 8), 16-byte aligned bases
+ *   y may be NULL when only the quantized form is wanted; codes / scales may be NULL when only y is wanted
+ *   hidden % 32 == 0 and hidden <= 16384, else MXQ_ERR_UNSUPPORTED_SHAPE (the caller runs the module and mxq_quantize)
+ */
+typedef struct {
+    const void *x; int64_t ldx;
+    const void *residual; int64_t ld_res;
+    void *residual_out; int64_t ld_res_out;
+    const void *weight; float eps;
+    int64_t rows, hidden;
+    void *y; int64_t ldy;
+    void *codes; uint8_t *scales; int elem /* mxq_elem_t */; unsigned flags /* MXQ_FLAG_* */;
+} mxq_rmsnorm_args_t;
+MXQ_API int mxq_rmsnorm(const mxq_rmsnorm_args_t *args, int device, void *stream);
+
+/*
+ * rotary position embedding of the query and key heads between the q/k projections and the attention contraction
+ * (torchmx/layers/mx_llama_attention.py:171-187 calls transformers' apply_rotary_pos_emb: five elementwise launches per tensor):
+ *     out = (x * cos) + (rotate_half(x) * sin), every product and the sum rounded to bf16 as the tensor ops round them
+ *   q / k   : bf16, element (b, t, h, d) at  base + b*batch_stride + t*tok_stride + h*head_dim + d  (the projection output, read in place)
+ *   cos/sin : bf16 [batch | 1, tokens, head_dim] (batch stride 0 broadcasts)
+ *   q_out / k_out : bf16 [batch, heads, tokens, head_dim] contiguous
+ */
+typedef struct {
+    const void *q; int64_t q_tok_stride, q_batch_stride; int q_heads;
+    const void *k; int64_t k_tok_stride, k_batch_stride; int k_heads;
+    const void *cos; const void *sin; int64_t cs_tok_stride, cs_batch_stride;
+    int64_t batch, tokens; int head_dim;
+    void *q_out; void *k_out;
+} mxq_rope_args_t;
+MXQ_API int mxq_rope(const mxq_rope_args_t *args, int device, void *stream);
+
 #define MXQ_OK 0
 #define MXQ_ERR_INVALID 1
 #define MXQ_ERR_UNSUPPORTED_SHAPE 2

@@ -31,7 +31,8 @@ SHAPES = {
 PACK = False
 
 
-def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: bool = True, llm_api: bool = False, mx_attention: bool = False):
+def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: bool = True, llm_api: bool = False, mx_attention: bool = False,
+          fuse_norm: bool | None = None):
     from transformers import LlamaConfig, LlamaForCausalLM
 
     import torchmx_b200  # noqa: F401
@@ -66,7 +67,7 @@ def build(model_name: str, layers: int | None, wdt: str, adt: str, quantize: boo
             e = MXConfig(adt, 32)  # Q, K, V and the attention probabilities as MX operands too (reference :195-243)
             qa = QAttentionConfig(projection_config=qc, query_config=e, key_config=e, value_config=e, attention_weights_config=e) if mx_attention \
                 else QAttentionConfig(projection_config=qc)
-            quantize_llm_(model, qa, qc, fuse_rmsnorm=FUSE_NORM)
+            quantize_llm_(model, qa, qc, fuse_rmsnorm=FUSE_NORM if fuse_norm is None else fuse_norm)
         else:
             quantize_linear_(model, qc)
         e1.record()
@@ -122,7 +123,8 @@ def capture(fn):
 def run(args) -> dict:
     from transformers.cache_utils import StaticCache
 
-    model, cfg, info = build(args.model, args.layers, args.wdtype, args.adtype, quantize=not args.no_quant, llm_api=args.llm_api, mx_attention=args.mx_attention)
+    model, cfg, info = build(args.model, args.layers, args.wdtype, args.adtype, quantize=not args.no_quant, llm_api=args.llm_api, mx_attention=args.mx_attention,
+                             fuse_norm=getattr(args, "fuse_norm", None))
     res = {"api": "none (bf16 HF)" if args.no_quant else (("quantize_llm_ + MX attention" if args.mx_attention else "quantize_llm_") if args.llm_api else "quantize_linear_"), "model": args.model, "layers": cfg.num_hidden_layers, "weights": args.wdtype, "activations": args.adtype, **info}
     dev = "cuda"
 
@@ -188,6 +190,14 @@ def run(args) -> dict:
     res["resident_after_run_GB"] = torch.cuda.memory_allocated() / 1e9
     res["max_mem_GB"] = torch.cuda.max_memory_allocated() / 1e9
     return res
+
+
+def run_cfg(**kw) -> dict:
+    """`run` with keyword arguments (bench.py calls this in-process): defaults = the command line's"""
+    base = dict(model="8b", layers=None, prefill=2048, prefill_iters=5, batch=32, ctx=128, steps=64, wdtype="float6_e3m2", adtype="float8_e4m3",
+                no_graph=False, llm_api=False, mx_attention=False, no_quant=False, fuse_norm=None)
+    base.update(kw)
+    return run(argparse.Namespace(**base))
 
 
 if __name__ == "__main__":

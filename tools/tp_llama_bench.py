@@ -197,6 +197,17 @@ def run_infer(args, world, rank):
     posd = torch.tensor([ctx], device="cuda")
     ms, out = time_graph(lambda: stack(xd, posd, caches, ctx), args.iters * 4)
     res["decode_ms_per_step"], res["decode_tok_s"] = round(ms, 3), round(B / ms * 1e3, 1)
+    if getattr(args, "also_fused", False) and world > 1 and pool is None:
+        # the same layers once more with the reduction done in the GEMM epilogue (NVLink multicast) instead of NCCL
+        from torchmx_b200.layers.tp_linear import FusedAllReducePool
+        pool = FusedAllReducePool(h, max(args.batch, 128), None, fused_max_rows=args.fused_max_rows)
+        for l in layers:
+            l.o.enable_fused_allreduce(pool)
+            l.down.enable_fused_allreduce(pool)
+        ms, out = time_graph(lambda: stack(xd, posd, caches, ctx), args.iters * 4)
+        res["decode_fused_ms_per_step"], res["decode_fused_tok_s"] = round(ms, 3), round(B / ms * 1e3, 1)
+    res["allreduce_per_step"] = 2 * cfg["layers"] if world > 1 else 0
+    res["allreduce_bytes_decode"], res["allreduce_bytes_prefill"] = B * h * 2, P * h * 2
     elems = cfg["layers"] * (2 * h * h + 2 * (h // cfg["heads"]) * cfg["kv_heads"] * h + 3 * h * cfg["inter"])
     bpe = (0.5 if args.wdtype == "float4_e2m1" else 1.0) + 1 / 32
     res["decode_weight_stream_floor_ms_per_rank"] = round(elems * bpe / world / 6.5e12 * 1e3, 3)
@@ -294,6 +305,14 @@ def run_quantize(args, world, rank):
             "weight_elements": int(t[2].item()), "gpu_s_max": round(float(tmax[0]), 4), "wall_s_max": round(float(tmax[1]), 4),
             "aggregate_GBps": round(float(t[2].item()) * bpe / float(tmax[0]) / 1e9, 1),
             "linears_per_rank": (hi - lo) * len(shapes), "host_issue_s_rank0": round(host_issue_s, 4), "cudaMalloc_calls_in_timed_region_rank0": n_malloc}
+
+
+def default_args(**kw):
+    """argparse defaults as a namespace (bench.py calls run_infer / run_quantize in-process on its own process group)"""
+    base = dict(mode="infer", model="70b", layers=None, prefill=2048, batch=32, ctx=128, iters=5, wdtype="float4_e2m1", adtype="float8_e4m3",
+                check=False, fused_max_rows=128, fused=False, also_fused=False)
+    base.update(kw)
+    return argparse.Namespace(**base)
 
 
 def main():

@@ -17,7 +17,7 @@ ABI_VERSION = 2
 MAX_DIMS = 6
 
 EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_gemm_dequant", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
-           "mxq_softmax_quantize", "mxq_silu_mul_quantize", "mxq_last_error", "mxq_version", "mxq_arch")
+           "mxq_softmax_quantize", "mxq_silu_mul_quantize", "mxq_rmsnorm", "mxq_rope", "mxq_last_error", "mxq_version", "mxq_arch")
 
 
 class GemmArgs(ctypes.Structure):
@@ -66,6 +66,28 @@ class SoftmaxArgs(ctypes.Structure):
     ]
 
 
+class RmsNormArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("ldx", ctypes.c_int64),
+        ("residual", ctypes.c_void_p), ("ld_res", ctypes.c_int64),
+        ("residual_out", ctypes.c_void_p), ("ld_res_out", ctypes.c_int64),
+        ("weight", ctypes.c_void_p), ("eps", ctypes.c_float),
+        ("rows", ctypes.c_int64), ("hidden", ctypes.c_int64),
+        ("y", ctypes.c_void_p), ("ldy", ctypes.c_int64),
+        ("codes", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("elem", ctypes.c_int), ("flags", ctypes.c_uint),
+    ]
+
+
+class RopeArgs(ctypes.Structure):
+    _fields_ = [
+        ("q", ctypes.c_void_p), ("q_tok_stride", ctypes.c_int64), ("q_batch_stride", ctypes.c_int64), ("q_heads", ctypes.c_int),
+        ("k", ctypes.c_void_p), ("k_tok_stride", ctypes.c_int64), ("k_batch_stride", ctypes.c_int64), ("k_heads", ctypes.c_int),
+        ("cos", ctypes.c_void_p), ("sin", ctypes.c_void_p), ("cs_tok_stride", ctypes.c_int64), ("cs_batch_stride", ctypes.c_int64),
+        ("batch", ctypes.c_int64), ("tokens", ctypes.c_int64), ("head_dim", ctypes.c_int),
+        ("q_out", ctypes.c_void_p), ("k_out", ctypes.c_void_p),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -108,6 +130,10 @@ def lib() -> ctypes.CDLL:
         L.mxq_silu_mul_quantize.argtypes = [vp, vp, i64, i64, i64, i64, i32, u32, vp, vp, i32, vp]
         L.mxq_softmax_quantize.restype = i32
         L.mxq_softmax_quantize.argtypes = [ctypes.POINTER(SoftmaxArgs), i32, vp]
+        L.mxq_rmsnorm.restype = i32
+        L.mxq_rmsnorm.argtypes = [ctypes.POINTER(RmsNormArgs), i32, vp]
+        L.mxq_rope.restype = i32
+        L.mxq_rope.argtypes = [ctypes.POINTER(RopeArgs), i32, vp]
         if L.mxq_version() != ABI_VERSION:
             raise RuntimeError(f"torchmx_b200: libmxq.so has ABI v{L.mxq_version()}, this package needs v{ABI_VERSION}: rebuild with `python -m torchmx_b200.build --force`")
         if L.mxq_arch() != 1000:

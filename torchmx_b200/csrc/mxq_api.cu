@@ -19,6 +19,8 @@ int launch_gemm(const mxq_gemm_args_t*, int, int, cudaStream_t, char*, size_t);
 namespace gemm { int launch_gemm_dequant(const mxq_gemm_dequant_args_t*, int, cudaStream_t, char*, size_t); }
 cudaError_t launch_silu_mul_quantize(const void*, const void*, int64_t, int64_t, int64_t, int64_t, int, unsigned, void*, uint8_t*, int, cudaStream_t);
 int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size_t);
+int launch_rmsnorm(const mxq_rmsnorm_args_t*, cudaStream_t, char*, size_t);
+int launch_rope(const mxq_rope_args_t*, int, cudaStream_t, char*, size_t);
 }  // namespace mxq
 
 namespace {
@@ -216,6 +218,33 @@ int mxq_silu_mul_quantize(const void* gate, const void* up, int64_t rows, int64_
     if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_silu_mul_quantize: selecting device");
     const cudaError_t e = mxq::launch_silu_mul_quantize(gate, up, rows, cols, ld_gate, ld_up, elem, flags, codes, scales, sm_count_of(scope.cur), (cudaStream_t)stream);
     return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_silu_mul_quantize: launch");
+}
+
+int mxq_rmsnorm(const mxq_rmsnorm_args_t* a, int device, void* stream) {
+    if (!a) return fail(MXQ_ERR_INVALID, "mxq_rmsnorm: null args");
+    if (a->rows < 0 || a->hidden < 0) return fail(MXQ_ERR_INVALID, "mxq_rmsnorm: negative extent");
+    if (a->rows == 0 || a->hidden == 0) return MXQ_OK;
+    if (!a->x || !a->weight || (!a->y && !a->codes)) return fail(MXQ_ERR_INVALID, "mxq_rmsnorm: null pointer");
+    if ((a->codes == nullptr) != (a->scales == nullptr)) return fail(MXQ_ERR_INVALID, "mxq_rmsnorm: codes and scales go together");
+    if (a->codes && !valid_elem(a->elem)) return fail(MXQ_ERR_INVALID, "mxq_rmsnorm: unknown element type %d", a->elem);
+    if (a->residual_out && !a->residual) return fail(MXQ_ERR_INVALID, "mxq_rmsnorm: residual_out without residual");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_rmsnorm: selecting device");
+    char msg[400] = "";
+    const int rc = mxq::launch_rmsnorm(a, (cudaStream_t)stream, msg, sizeof(msg));
+    return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_rmsnorm: %s", msg);
+}
+
+int mxq_rope(const mxq_rope_args_t* a, int device, void* stream) {
+    if (!a) return fail(MXQ_ERR_INVALID, "mxq_rope: null args");
+    if (a->batch < 0 || a->tokens < 0 || a->q_heads < 0 || a->k_heads < 0) return fail(MXQ_ERR_INVALID, "mxq_rope: negative extent");
+    if (a->batch == 0 || a->tokens == 0 || a->q_heads + a->k_heads == 0) return MXQ_OK;
+    if ((a->q_heads && (!a->q || !a->q_out)) || (a->k_heads && (!a->k || !a->k_out)) || !a->cos || !a->sin) return fail(MXQ_ERR_INVALID, "mxq_rope: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_rope: selecting device");
+    char msg[400] = "";
+    const int rc = mxq::launch_rope(a, sm_count_of(scope.cur), (cudaStream_t)stream, msg, sizeof(msg));
+    return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_rope: %s", msg);
 }
 
 int mxq_softmax_quantize(const mxq_softmax_args_t* a, int device, void* stream) {

@@ -12,6 +12,8 @@
 //   instruction), a 4-stage mbarrier ring decouples it from the producers;
 // * the producer warps then drain the accumulator (tcgen05.ld), add the bias, round once to bf16 and store.
 // Only the accumulation order differs from the reference's recipe.
+#include <cstring>
+
 #include "mxq_tc.cuh"
 
 namespace mxq {
@@ -20,20 +22,25 @@ namespace dq {
 
 constexpr int TILE = 128;       // output tile: 128 x 128
 constexpr int BK = 64;          // bf16 elements per stage and row = one 128-byte swizzle row
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;       // bf16 operand stages (what the tensor core reads)
+constexpr int RAW_STAGES = 6;   // raw code stages (what TMA writes): the deep ring that covers the DRAM / L2 latency
 constexpr int kProducerThreads = 256;
-constexpr int kThreads = kProducerThreads + 32;
+constexpr int kThreads = kProducerThreads + 64;  // + MMA warp + TMA warp
 constexpr int STAGE_BYTES = TILE * BK * 2;  // 16 KB per operand
+constexpr int RAW_BYTES = TILE * BK;        // 8 KB per operand (fp4 uses half of it)
 
 struct Smem {
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * STAGE_BYTES;
-    static constexpr int OFF_LUT = OFF_B + STAGES * STAGE_BYTES;  // 2 x 256 fp32: decoded value of every code byte, per operand
+    static constexpr int OFF_RAW_A = OFF_B + STAGES * STAGE_BYTES;
+    static constexpr int OFF_RAW_B = OFF_RAW_A + RAW_STAGES * RAW_BYTES;
+    static constexpr int OFF_LUT = OFF_RAW_B + RAW_STAGES * RAW_BYTES;  // 2 x 256 fp32: decoded value of every code byte, per operand
     static constexpr int OFF_BAR = OFF_LUT + 2 * 256 * 4;
-    static constexpr int NUM_BARS = 2 * STAGES + 1;
+    static constexpr int NUM_BARS = 2 * STAGES + 2 * RAW_STAGES + 1;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM_PTR + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
+    static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct Operand {
@@ -42,6 +49,8 @@ struct Operand {
     int rows;         // M (A) or N (B)
     int elem, block_size, along_k;
     int bs_shift;     // log2(block_size) when it is a power of two, else -1
+    int fast;         // codes K-contiguous, 16-byte aligned rows, blocks of >= 16 along K: raw tiles arrive by TMA
+    int tma_batched;  // the raw tensor map has a batch dimension (batch stride != 0)
 };
 
 struct Params {
@@ -71,8 +80,8 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
         : "memory");
 }
 
-// eight consecutive k of one operand row -> eight bf16 (one 16-byte shared-memory chunk).  `r` is the row inside the operand,
-// k0 a multiple of 8.  Rows / k past the edge give zeros.
+// ---- generic path: eight consecutive k of one operand row -> eight bf16 (one 16-byte shared-memory chunk).  `r` is the row
+// inside the operand, k0 a multiple of 8.  Rows / k past the edge give zeros.  Any strides, any block size / orientation.
 __device__ __forceinline__ uint4 dequant_chunk(const Operand& op, const uint8_t* codes, const uint8_t* scales, const float* lut, int r, int k0, int K) {
     float f[8];
     if (r >= op.rows || k0 >= K) return make_uint4(0u, 0u, 0u, 0u);
@@ -143,13 +152,75 @@ __device__ __forceinline__ uint4 dequant_chunk(const Operand& op, const uint8_t*
     return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
-__global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const Params p) {
+// ---- fast path: sixteen consecutive codes of one block (one 16-byte raw chunk; fp4: 8 bytes) times one scale -> 16 bf16 ----
+// Same arithmetic as K2 (exact decode, exact fp32 product, one rounding to bf16).
+template <int ELEM>
+__device__ __forceinline__ void dequant16(const uint32_t (&raw)[4], int s_byte, uint32_t (&out)[8]) {
+    const float sc = scale_f32(s_byte);
+    if constexpr (ELEM == MXQ_ELEM_INT8) {
+        if (s_byte <= 230) {
+            // v + 128 placed in the low mantissa byte of 2^23: f = 2^23 + 128 + v exactly; (f - (2^23 + 128)) * sc as one FMA whose
+            // exact result v * sc is representable, so the single rounding of the FMA does not round at all
+            const float neg_c = -8388736.0f * sc;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t x = raw[w] ^ 0x80808080u;
+                const float f0 = fmaf(__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7540)), sc, neg_c);
+                const float f1 = fmaf(__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7541)), sc, neg_c);
+                const float f2 = fmaf(__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7542)), sc, neg_c);
+                const float f3 = fmaf(__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7543)), sc, neg_c);
+                out[2 * w] = pack_bf16x2(f0, f1);
+                out[2 * w + 1] = pack_bf16x2(f2, f3);
+            }
+        } else {  // 2^23 * sc would overflow: plain conversion (also the NaN scale)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                float f[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[j] = (float)(int)(int8_t)(raw[w] >> (8 * j)) * sc;
+                out[2 * w] = pack_bf16x2(f[0], f[1]);
+                out[2 * w + 1] = pack_bf16x2(f[2], f[3]);
+            }
+        }
+    } else if constexpr (ELEM == MXQ_ELEM_E2M1) {  // raw[0], raw[1]: eight bytes = sixteen codes, earlier element in the HIGH nibble
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t h = decode_e2m1_byte_f16x2((raw[w] >> (8 * j)) & 0xFF);
+                out[4 * w + j] = pack_bf16x2(f16hi_to_f32(h) * sc, f16lo_to_f32(h) * sc);
+            }
+    } else {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t h0 = decode_pair_f16x2<ELEM>(raw[w] & 0xFFFF), h1 = decode_pair_f16x2<ELEM>(raw[w] >> 16);
+            out[2 * w] = pack_bf16x2(f16lo_to_f32(h0) * sc, f16hi_to_f32(h0) * sc);
+            out[2 * w + 1] = pack_bf16x2(f16lo_to_f32(h1) * sc, f16hi_to_f32(h1) * sc);
+        }
+    }
+}
+
+__device__ __forceinline__ void dequant16_rt(int elem, const uint32_t (&raw)[4], int s_byte, uint32_t (&out)[8]) {
+    switch (elem) {  // uniform over the CTA
+    case MXQ_ELEM_E4M3: dequant16<MXQ_ELEM_E4M3>(raw, s_byte, out); break;
+    case MXQ_ELEM_E3M2: dequant16<MXQ_ELEM_E3M2>(raw, s_byte, out); break;
+    case MXQ_ELEM_E2M3: dequant16<MXQ_ELEM_E2M3>(raw, s_byte, out); break;
+    case MXQ_ELEM_E2M1: dequant16<MXQ_ELEM_E2M1>(raw, s_byte, out); break;
+    case MXQ_ELEM_E5M2: dequant16<MXQ_ELEM_E5M2>(raw, s_byte, out); break;
+    default: dequant16<MXQ_ELEM_INT8>(raw, s_byte, out); break;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                                      const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);
-    uint64_t* full = bars;             // both bf16 tiles of the stage written (count 256: every producer thread)
-    uint64_t* empty = bars + STAGES;   // MMAs of the stage retired (count 1, tcgen05.commit)
-    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* full = bars;                           // both bf16 tiles of the stage written (count 256: every producer thread)
+    uint64_t* empty = bars + STAGES;                 // MMAs of the stage retired (count 1, tcgen05.commit)
+    uint64_t* raw_full = bars + 2 * STAGES;          // raw code tiles landed (count 1 + tx)
+    uint64_t* raw_empty = raw_full + RAW_STAGES;     // raw stage read into registers (count 4 per TMA-fed operand: one per warp)
+    uint64_t* tmem_full = raw_empty + RAW_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::OFF_TMEM_PTR);
     float* lut = reinterpret_cast<float*>(smem + Smem::OFF_LUT);
 
@@ -159,6 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const Para
     const int t = blockIdx.x - b * tiles_per_batch;
     const int nb = t / p.m_blocks, mb = t - nb * p.m_blocks;  // m fastest: neighbouring CTAs share a B panel in L2
     const int k_steps = (p.K + BK - 1) / BK;
+    const int n_fast = p.a.fast + p.b.fast;
 
     if (threadIdx.x < 256) {
         lut[threadIdx.x] = lut_entry(p.a.elem, threadIdx.x);
@@ -170,11 +242,19 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const Para
                 mbar_init(&full[i], kProducerThreads);
                 mbar_init(&empty[i], 1);
             }
+            for (int i = 0; i < RAW_STAGES; ++i) {
+                mbar_init(&raw_full[i], 1);
+                mbar_init(&raw_empty[i], 4 * (n_fast > 0 ? n_fast : 1));
+            }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
         }
         __syncwarp();
         tmem_alloc<128>(tmem_ptr);
+    }
+    if (warp == 9 && elect_one()) {
+        if (p.a.fast) tma_prefetch_desc(&map_a);
+        if (p.b.fast) tma_prefetch_desc(&map_b);
     }
     tc_fence_before();
     __syncthreads();
@@ -182,25 +262,95 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const Para
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp < 8) {
-        // ================= producers: thread = one row of the A tile (threads 0..127) or of the B tile (128..255) =================
+        // ================= producers: warps 0..3 build the A tile, warps 4..7 the B tile =================
         const bool is_b = threadIdx.x >= 128;
         const Operand& op = is_b ? p.b : p.a;
-        const int row = threadIdx.x & 127;
-        const int r = (is_b ? nb : mb) * TILE + row;
+        const int tidx = threadIdx.x & 127;
+        const int row0 = (is_b ? nb : mb) * TILE;
         const uint8_t* codes = op.codes + (int64_t)b * op.batch_stride;
         const uint8_t* scales = op.scales + (int64_t)b * op.sbatch_stride;
         const float* my_lut = lut + (is_b ? 256 : 0);
-        uint8_t* tile0 = smem + (is_b ? Smem::OFF_B : Smem::OFF_A) + row * 128;
-        uint32_t stage = 0, phase = 0;
-        for (int ks = 0; ks < k_steps; ++ks) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* dst = tile0 + stage * STAGE_BYTES;
-#pragma unroll 2
-            for (int c = 0; c < 8; ++c)  // 16-byte chunk c of the row lives at chunk c ^ (row & 7) (SWIZZLE_128B)
-                *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = dequant_chunk(op, codes, scales, my_lut, r, ks * BK + c * 8, p.K);
-            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&full[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        uint8_t* tile_base = smem + (is_b ? Smem::OFF_B : Smem::OFF_A);
+        const uint8_t* raw_base = smem + (is_b ? Smem::OFF_RAW_B : Smem::OFF_RAW_A);
+        uint32_t stage = 0, phase = 0, rs = 0, rphase = 0;
+        if (op.fast) {
+            // TMA-fed: the raw tile is [128 rows][64 B] (fp4: 32 B), no swizzle.  Work item = (row, 16-element chunk q); a warp
+            // reads 512 (256) contiguous raw bytes per instruction.  item = i * 128 + tidx -> row = item >> 2, q = item & 3.
+            const bool fp4 = op.elem == MXQ_ELEM_E2M1;
+            const int q = tidx & 3;
+            int rows_i[4];
+            const uint8_t* sc_ptr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                rows_i[i] = (i * 128 + tidx) >> 2;
+                const int r = min(row0 + rows_i[i], op.rows - 1);  // rows past the edge carry zero codes; any in-range scale will do
+                sc_ptr[i] = scales + (int64_t)r * op.srow_stride;
+            }
+            auto load_scales = [&](int ks, int (&sb)[4]) {
+                const int kq = ks * BK + 16 * q;
+                const bool live = ks < k_steps && kq < p.K;
+                const int64_t off = (int64_t)(kq >> op.bs_shift) * op.sk_stride;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sb[i] = live ? (int)__ldg(sc_ptr[i] + off) : 127;
+            };
+            int sb_cur[4], sb_nxt[4];
+            load_scales(0, sb_cur);
+            for (int ks = 0; ks < k_steps; ++ks) {
+                load_scales(ks + 1, sb_nxt);
+                mbar_wait(&raw_full[rs], rphase);
+                const uint8_t* raw = raw_base + rs * RAW_BYTES;
+                uint32_t rw[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (fp4) {
+                        const uint2 v = *reinterpret_cast<const uint2*>(raw + rows_i[i] * 32 + q * 8);
+                        rw[i][0] = v.x; rw[i][1] = v.y; rw[i][2] = 0; rw[i][3] = 0;
+                    } else {
+                        const uint4 v = *reinterpret_cast<const uint4*>(raw + rows_i[i] * 64 + q * 16);
+                        rw[i][0] = v.x; rw[i][1] = v.y; rw[i][2] = v.z; rw[i][3] = v.w;
+                    }
+                }
+                fence_proxy_async_smem();  // our reads of the raw stage are ordered before the TMA refill
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_empty[rs]);
+                if (++rs == RAW_STAGES) { rs = 0; rphase ^= 1; }
+                const bool dead = ks * BK + 16 * q >= p.K;  // the whole chunk lies past K: zeros whatever the scale says
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* dst = tile_base + stage * STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t o[8];
+                    if (dead) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = 0u;
+                    } else {
+                        dequant16_rt(op.elem, rw[i], sb_cur[i], o);
+                    }
+                    const int row = rows_i[i];
+                    uint8_t* drow = dst + row * 128;
+                    *reinterpret_cast<uint4*>(drow + (((2 * q) ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(drow + (((2 * q + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&full[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sb_cur[i] = sb_nxt[i];
+            }
+        } else {
+            // generic: thread = one row of the tile, element-wise addressing through the operand's strides
+            const int row = tidx;
+            const int r = row0 + row;
+            for (int ks = 0; ks < k_steps; ++ks) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* dst = tile_base + stage * STAGE_BYTES + row * 128;
+#pragma unroll 4
+                for (int c = 0; c < 8; ++c)  // 16-byte chunk c of the row lives at chunk c ^ (row & 7) (SWIZZLE_128B)
+                    *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = dequant_chunk(op, codes, scales, my_lut, r, ks * BK + c * 8, p.K);
+                fence_proxy_async_smem();
+                mbar_arrive(&full[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
         }
         // ================= epilogue: warp (quadrant, column half) drains 32 rows x 64 columns =================
         const int quad = warp & 3, half = warp >> 2;
@@ -248,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const Para
             }
         }
         tc_fence_before();
-    } else {
+    } else if (warp == 8) {
         // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
         // kind::f16 descriptor: fp32 accumulator (bit 4), bf16 A and B (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
@@ -270,6 +420,24 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const Para
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_fence_before();
+    } else {
+        // ================= TMA producer of the raw code tiles (operands in the fast form only) =================
+        if (n_fast > 0 && elect_one()) {
+            const uint32_t a_bytes = p.a.fast ? (p.a.elem == MXQ_ELEM_E2M1 ? TILE * 32 : TILE * 64) : 0;
+            const uint32_t b_bytes = p.b.fast ? (p.b.elem == MXQ_ELEM_E2M1 ? TILE * 32 : TILE * 64) : 0;
+            uint32_t rs = 0, rphase = 0;
+            for (int ks = 0; ks < k_steps; ++ks) {
+                mbar_wait(&raw_empty[rs], rphase ^ 1);
+                mbar_arrive_expect_tx(&raw_full[rs], a_bytes + b_bytes);
+                if (p.a.fast)
+                    tma_load_3d(&map_a, &raw_full[rs], smem + Smem::OFF_RAW_A + rs * RAW_BYTES, ks * (p.a.elem == MXQ_ELEM_E2M1 ? 32 : 64), mb * TILE,
+                                p.a.tma_batched ? b : 0);
+                if (p.b.fast)
+                    tma_load_3d(&map_b, &raw_full[rs], smem + Smem::OFF_RAW_B + rs * RAW_BYTES, ks * (p.b.elem == MXQ_ELEM_E2M1 ? 32 : 64), nb * TILE,
+                                p.b.tma_batched ? b : 0);
+                if (++rs == RAW_STAGES) { rs = 0; rphase ^= 1; }
+            }
+        }
     }
     __syncthreads();
     if (warp == 8) {
@@ -278,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const Para
     }
 }
 
-static bool fill_operand(Operand& o, const mxq_operand_t& s, int64_t rows) {
+static void fill_operand(Operand& o, const mxq_operand_t& s, int64_t rows, int64_t K, int64_t batch) {
     o.codes = (const uint8_t*)s.codes; o.scales = s.scales;
     o.row_stride = s.row_stride; o.k_stride = s.k_stride; o.batch_stride = s.batch_stride;
     o.srow_stride = s.srow_stride; o.sk_stride = s.sk_stride; o.sbatch_stride = s.sbatch_stride;
@@ -286,7 +454,11 @@ static bool fill_operand(Operand& o, const mxq_operand_t& s, int64_t rows) {
     o.bs_shift = -1;
     for (int sft = 0; sft < 31; ++sft)
         if ((1 << sft) == s.block_size) o.bs_shift = sft;
-    return true;
+    // TMA-fed form: K-contiguous codes, blocks of a power of two >= 16 along K (a 16-element chunk never straddles a block), rows
+    // and batches on 16-byte boundaries
+    o.fast = (K > 0 && s.k_stride == 1 && o.along_k && o.bs_shift >= 4 && ((uintptr_t)s.codes % 16) == 0 && s.row_stride % 16 == 0 && s.row_stride > 0 &&
+              (batch <= 1 || s.batch_stride % 16 == 0) && s.batch_stride >= 0) ? 1 : 0;
+    o.tma_batched = (batch > 1 && s.batch_stride > 0) ? 1 : 0;
 }
 
 }  // namespace dq
@@ -295,8 +467,8 @@ int launch_gemm_dequant(const mxq_gemm_dequant_args_t* a, int device, cudaStream
     using namespace dq;
     if (a->M > 0x7FFFFFFF || a->N > 0x7FFFFFFF || a->K > 0x7FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
     dq::Params p;
-    fill_operand(p.a, a->a, a->M);
-    fill_operand(p.b, a->b, a->N);
+    fill_operand(p.a, a->a, a->M, a->K, a->batch);
+    fill_operand(p.b, a->b, a->N, a->K, a->batch);
     p.bias = (const uint16_t*)a->bias; p.d = (uint16_t*)a->d;
     p.ldd = a->ldd; p.d_batch = a->d_batch_stride;
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
@@ -304,9 +476,19 @@ int launch_gemm_dequant(const mxq_gemm_dequant_args_t* a, int device, cudaStream
     p.n_blocks = (int)((a->N + TILE - 1) / TILE);
     const int64_t ctas = (int64_t)p.m_blocks * p.n_blocks * a->batch;
     if (ctas > 0x7FFFFFFF) { snprintf(msg, msg_len, "too many output tiles"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+    CUtensorMap maps[2];
+    memset(maps, 0, sizeof(maps));
+    for (int side = 0; side < 2; ++side) {
+        Operand& o = side ? p.b : p.a;
+        if (!o.fast) continue;
+        const bool fp4 = o.elem == MXQ_ELEM_E2M1;
+        const int64_t k_bytes = fp4 ? (a->K + 1) / 2 : a->K;
+        if (!cached_raw_map(&maps[side], o.codes, k_bytes, o.rows, o.tma_batched ? a->batch : 1, o.row_stride, o.batch_stride, fp4 ? 32 : 64, TILE, device))
+            o.fast = 0;  // the driver refused the layout: element-wise path
+    }
     cudaError_t e = ensure_smem_attr((const void*)mx_gemm_dequant_kernel, Smem::DYN_BYTES, device);
     if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
-    mx_gemm_dequant_kernel<<<(unsigned)ctas, dq::kThreads, Smem::DYN_BYTES, stream>>>(p);
+    mx_gemm_dequant_kernel<<<(unsigned)ctas, dq::kThreads, Smem::DYN_BYTES, stream>>>(maps[0], maps[1], p);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (dequant gemm): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;

@@ -16,11 +16,13 @@ namespace mxq {
 
 constexpr int kQuantThreads = 256;
 
-template <int ELEM, int EPT>
+// BS = block size: 32 (the MX block; EPT 8 / 16 / 32), or 8 / 16 (EPT = BS: a thread owns a whole block) and 64 / 128 (EPT 32, two /
+// four lanes per block) -- same arithmetic, only the number of lanes that share a block maximum changes.
+template <int ELEM, int EPT, int BS = 32>
 __global__ void __launch_bounds__(kQuantThreads) quantize_b32_bf16_kernel(const uint16_t* __restrict__ src, uint8_t* __restrict__ codes,
                                                                            uint8_t* __restrict__ scales, int64_t n_blocks, uint32_t flags) {
     pdl_launch_dependents();       // a dependent MX GEMM may start streaming its weights while the activation is quantized
-    constexpr int LPB = 32 / EPT;  // lanes per MX block
+    constexpr int LPB = BS / EPT;  // lanes per MX block
     constexpr int NW = EPT / 2;    // 32-bit words of bf16 pairs per thread
     constexpr int NO = (ELEM == MXQ_ELEM_E2M1) ? NW / 4 : NW / 2;
     const int64_t n_chunks = n_blocks * LPB;
@@ -69,6 +71,80 @@ __global__ void __launch_bounds__(kQuantThreads) quantize_b32_bf16_kernel(const 
                 stg256_stream(q, o);
             }
             if ((threadIdx.x & (LPB - 1)) == 0) scales[c / LPB] = (uint8_t)s;
+        }
+    }
+}
+
+// ---- fp32 input (extension: the reference asserts bf16, torchmx/mx_tensor.py:59-61; the exponent rule is its fp32 branch,
+// mx_quantization_utils.py:532-540), block 32: a thread owns 16 consecutive fp32 values (two 256-bit loads), two lanes share a
+// block.  code = RNE_satfinite(x * 2^(127-s)) straight from fp32 (one rounding), int8 through the same magic-constant FMA.
+// Algorithmic traffic: 4 B in + 1 B (0.5 B fp4) + 1/32 B out per element.
+template <int ELEM>
+__global__ void __launch_bounds__(kQuantThreads) quantize_b32_f32_kernel(const float* __restrict__ src, uint8_t* __restrict__ codes,
+                                                                          uint8_t* __restrict__ scales, int64_t n_blocks) {
+    pdl_launch_dependents();
+    constexpr int EPT = 16;
+    const int64_t n_chunks = n_blocks * 2;
+    const int64_t stride = (int64_t)gridDim.x * kQuantThreads;
+    for (int64_t c0 = (int64_t)blockIdx.x * kQuantThreads; c0 < n_chunks; c0 += stride) {
+        const int64_t c = c0 + threadIdx.x;
+        const bool live = c < n_chunks;
+        uint32_t w[EPT];
+        if (live) {
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(src) + c * (EPT * 4);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const u32x8 v = ldg256_stream(p + 32 * j);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[8 * j + k] = v.v[k];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) w[i] = 0;
+        }
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) m = max(m, w[i] & 0x7FFFFFFFu);
+        m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
+        const int s = shared_exp_from_maxE<ELEM>((int)(m >> 23));
+        constexpr int NO = (ELEM == MXQ_ELEM_E2M1) ? 2 : 4;
+        uint32_t out[NO];
+#pragma unroll
+        for (int i = 0; i < NO; ++i) out[i] = 0;
+        if (s != 255) {  // NaN-scale block: all codes +0 (mx_quantization_utils.py:473)
+            const float inv = inv_scale_f32(s);
+            if constexpr (ELEM == MXQ_ELEM_INT8) {
+                constexpr float kMagic = 12582912.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t b[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float t = fmaf(__uint_as_float(w[4 * i + j]), inv, kMagic);
+                        t = fminf(fmaxf(t, kMagic - 127.0f), kMagic + 127.0f);
+                        b[j] = __float_as_uint(t);
+                    }
+                    out[i] = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+                }
+            } else if constexpr (ELEM == MXQ_ELEM_E2M1) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        out[i] |= cvt_e2m1_byte(__uint_as_float(w[8 * i + 2 * j]) * inv, __uint_as_float(w[8 * i + 2 * j + 1]) * inv) << (8 * j);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t p0 = cvt_pair<ELEM>(__uint_as_float(w[4 * i]) * inv, __uint_as_float(w[4 * i + 1]) * inv);
+                    const uint32_t p1 = cvt_pair<ELEM>(__uint_as_float(w[4 * i + 2]) * inv, __uint_as_float(w[4 * i + 3]) * inv);
+                    out[i] = p0 | (p1 << 16);
+                }
+            }
+        }
+        if (live) {
+            if constexpr (ELEM == MXQ_ELEM_E2M1) stg64_stream(codes + c * 8, make_uint2(out[0], out[1]));
+            else stg128_stream(codes + c * 16, make_uint4(out[0], out[1], out[2], out[3]));
+            if ((threadIdx.x & 1) == 0) scales[c >> 1] = (uint8_t)s;
         }
     }
 }
@@ -140,6 +216,26 @@ static cudaError_t launch_quantize_elem(const void* src, int src_dtype, int64_t 
         if (ept == 8) quantize_b32_bf16_kernel<ELEM, 8><<<grid, kQuantThreads, 0, stream>>>(s16, c8, scales, n_blocks, flags);
         else if (ept == 32) quantize_b32_bf16_kernel<ELEM, 32><<<grid, kQuantThreads, 0, stream>>>(s16, c8, scales, n_blocks, flags);
         else quantize_b32_bf16_kernel<ELEM, 16><<<grid, kQuantThreads, 0, stream>>>(s16, c8, scales, n_blocks, flags);
+        return cudaGetLastError();
+    }
+    if (src_dtype == MXQ_HP_BF16 && (a_src % 32) == 0 && (a_codes % 32) == 0 && (block_size == 8 || block_size == 16 || block_size == 64 || block_size == 128)) {
+        // the same kernel with 1, 2 or 4 lanes per block (every access stays a whole, aligned vector)
+        const int lpb = block_size <= 32 ? 1 : block_size / 32;
+        const int64_t n_chunks = n_blocks * lpb;
+        const int64_t want = (n_chunks + kQuantThreads - 1) / kQuantThreads;
+        const int grid = (int)(want < 0x7FFFFFFF ? want : 0x7FFFFFFF);
+        const uint16_t* s16 = (const uint16_t*)src;
+        uint8_t* c8 = (uint8_t*)codes;
+        if (block_size == 8) quantize_b32_bf16_kernel<ELEM, 8, 8><<<grid, kQuantThreads, 0, stream>>>(s16, c8, scales, n_blocks, flags);
+        else if (block_size == 16) quantize_b32_bf16_kernel<ELEM, 16, 16><<<grid, kQuantThreads, 0, stream>>>(s16, c8, scales, n_blocks, flags);
+        else if (block_size == 64) quantize_b32_bf16_kernel<ELEM, 32, 64><<<grid, kQuantThreads, 0, stream>>>(s16, c8, scales, n_blocks, flags);
+        else quantize_b32_bf16_kernel<ELEM, 32, 128><<<grid, kQuantThreads, 0, stream>>>(s16, c8, scales, n_blocks, flags);
+        return cudaGetLastError();
+    }
+    if (block_size == 32 && src_dtype == MXQ_HP_F32 && (a_src % 32) == 0 && (a_codes % 16) == 0) {
+        const int64_t want = (n_blocks * 2 + kQuantThreads - 1) / kQuantThreads;
+        const int grid = (int)(want < 0x7FFFFFFF ? want : 0x7FFFFFFF);
+        quantize_b32_f32_kernel<ELEM><<<grid, kQuantThreads, 0, stream>>>((const float*)src, (uint8_t*)codes, scales, n_blocks);
         return cudaGetLastError();
     }
     const int64_t n_elems = n_blocks * block_size;

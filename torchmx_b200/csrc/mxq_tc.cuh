@@ -445,6 +445,9 @@ bool cached_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t r
                         int operand_format, int device);
 // E8M0 scales [rows][K/32 bytes] row-major: box = 16 bytes (4 K blocks) x 128 rows, rows / bytes past the edge read as zero
 bool cached_scale_map(CUtensorMap* map, const void* base, int64_t scale_bytes_per_row, int64_t rows, int64_t ld, int device);
+// raw code bytes [batch][rows][k_bytes] (K3d): box = box_bytes x box_rows, no swizzle, bytes / rows past the edge read as zero
+bool cached_raw_map(CUtensorMap* map, const void* base, int64_t k_bytes, int64_t rows, int64_t batch, int64_t ld, int64_t batch_stride, int box_bytes,
+                    int box_rows, int device);
 // D: [batch][M][N] bf16, box = 64 columns x 32 rows, 128B swizzle (one epilogue warp's staging buffer)
 bool cached_d_map(CUtensorMap* map, void* base, int64_t N, int64_t M, int64_t batch, int64_t ldd, int64_t batch_stride, int device);
 // The dynamic shared-memory opt-in is a per-(kernel, device) attribute: set the first time a kernel is launched on a device,

@@ -21,7 +21,7 @@ from typing import Optional, Tuple
 import torch
 from torch import nn
 
-from .. import attention_ops, mlp_ops, mx_gemm
+from .. import attention_ops, glue_ops, mlp_ops, mx_gemm
 from ..config import QAttentionConfig, QLinearConfig
 from ..mx_tensor import MXTensor
 from .mx_linear import MXInferenceLinear
@@ -294,7 +294,8 @@ class _MXAttentionMixin:
         key_states = k.view(hidden_shape).transpose(1, 2)
         value_states = v.view(hidden_shape).transpose(1, 2)
         cos, sin = position_embeddings
-        query_states, key_states = mod_llama.apply_rotary_pos_emb(query_states, key_states, cos, sin)
+        rotated = glue_ops.rope(query_states, key_states, cos, sin)  # one launch, the eager chain's roundings (K5b)
+        query_states, key_states = rotated if rotated is not None else mod_llama.apply_rotary_pos_emb(query_states, key_states, cos, sin)
         if past_key_values is not None:
             key_states, value_states = past_key_values.update(key_states, value_states, self.layer_idx)
         if self.qconfig.is_qkv_quantization_enabled:

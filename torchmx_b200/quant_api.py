@@ -62,19 +62,49 @@ def quantize_linear_(model: torch.nn.Module, qconfig: QLinearConfig, layer_filte
 
 
 class FusedRMSNorm(torch.nn.Module):
-    """Drop-in for the transformers `LlamaRMSNorm` / `Qwen2RMSNorm` module: same parameters, one fused `F.rms_norm` launch
-    (fp32 statistics inside) instead of the six elementwise / reduction launches of the eager module.  Not part of the
-    reference; `quantize_llm_(..., fuse_rmsnorm=True)` opts in."""
+    """Drop-in for the transformers `LlamaRMSNorm` / `Qwen2RMSNorm` module: same parameters, ONE launch (K5a, `glue_ops.rmsnorm`:
+    fp32 statistics, the module's bf16 roundings) instead of the six elementwise / reduction launches of the eager module.
+    When the only consumers of the output are MX linears of one activation config (`to_mx`, set by `quantize_llm_` for the two
+    norms of a decoder layer whose attention and MLP blocks are MX blocks) and the input is larger than the decode sizes at which
+    those layers quantize inside their GEMM, the same launch also quantizes: the module returns the MXTensor the layers would
+    have produced from its bf16 output (`MXTensor.to_mx` of it, bit for bit) and the bf16 tensor is never written.
+    Not part of the reference; `quantize_llm_(..., fuse_rmsnorm=True)` opts in."""
 
-    def __init__(self, weight: torch.nn.Parameter, eps: float):
+    def __init__(self, weight: torch.nn.Parameter, eps: float, to_mx=None):
         super().__init__()
-        self.weight, self.variance_epsilon = weight, eps
+        self.weight, self.variance_epsilon, self.to_mx = weight, eps, to_mx
 
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        from . import glue_ops, mx_gemm
+        if not torch.compiler.is_compiling():
+            rows = hidden_states.numel() // max(hidden_states.shape[-1], 1)
+            quant = self.to_mx is not None and not (mx_gemm._FUSED_ACT and self.to_mx.name == "float8_e4m3" and rows <= mx_gemm.FUSED_ACT_MAX_ROWS)
+            r = glue_ops.rmsnorm(hidden_states, self.weight, self.variance_epsilon, to_mx=self.to_mx if quant else None, want_y=not quant)
+            if r is not None:
+                return r[1] if quant else r[0]
         return torch.nn.functional.rms_norm(hidden_states, (hidden_states.shape[-1],), self.weight, self.variance_epsilon)
 
     def extra_repr(self) -> str:
-        return f"{tuple(self.weight.shape)}, eps={self.variance_epsilon}"
+        return f"{tuple(self.weight.shape)}, eps={self.variance_epsilon}" + (f", to_mx={self.to_mx.name}" if self.to_mx is not None else "")
+
+
+def _fuse_norms_(model: torch.nn.Module) -> None:
+    """every Llama / Qwen2 RMSNorm -> FusedRMSNorm; the two norms of a decoder layer whose consumers are MX blocks quantize too"""
+    from .layers.mx_llama_attention import _MXAttentionMixin, _MXMLPMixin
+    is_norm = lambda m: type(m).__name__ in ("LlamaRMSNorm", "Qwen2RMSNorm")  # noqa: E731
+
+    def act_dtype(qc):
+        ac = qc.activations_config
+        return ac.elem_dtype if ac.block_size == 32 else None
+
+    for layer in model.modules():
+        for norm_name, consumer_name, mixin in (("input_layernorm", "self_attn", _MXAttentionMixin), ("post_attention_layernorm", "mlp", _MXMLPMixin)):
+            norm, consumer = getattr(layer, norm_name, None), getattr(layer, consumer_name, None)
+            if norm is None or not is_norm(norm) or not isinstance(consumer, mixin):
+                continue
+            qc = consumer.qconfig.projection_config if mixin is _MXAttentionMixin else consumer.qconfig
+            setattr(layer, norm_name, FusedRMSNorm(norm.weight, norm.variance_epsilon, to_mx=act_dtype(qc)))
+    _swap_children(model, replacement_fn=lambda mod: FusedRMSNorm(mod.weight, mod.variance_epsilon), filter_fn=lambda mod, fqn: is_norm(mod))
 
 
 def quantize_llm_(model: torch.nn.Module, qattention_config: QAttentionConfig, qmlp_config: QLinearConfig, fuse_rmsnorm: bool = False) -> None:
@@ -96,8 +126,7 @@ def quantize_llm_(model: torch.nn.Module, qattention_config: QAttentionConfig, q
     _swap_children(model, replacement_fn=replace, filter_fn=lambda mod, fqn: type(mod) in table)
     quantize_linear_(model, qmlp_config)
     if fuse_rmsnorm:
-        _swap_children(model, replacement_fn=lambda mod: FusedRMSNorm(mod.weight, mod.variance_epsilon),
-                       filter_fn=lambda mod, fqn: type(mod).__name__ in ("LlamaRMSNorm", "Qwen2RMSNorm"))
+        _fuse_norms_(model)
 
 
 def pack_linear_(model: torch.nn.Module) -> int:
