@@ -246,6 +246,40 @@ typedef struct {
 MXQ_API int mxq_softmax_quantize(const mxq_softmax_args_t *args, int device, void *stream);
 
 /*
+ * MX attention as one kernel  <->  the attention of the reference's MX blocks (torchmx/layers/mx_llama_attention.py:195-243,
+ * mx_qwen2_attention.py): scores = Q_mx K_mx^T, P = quantize_mx(softmax(scores * scaling + mask)), out = P_mx V_mx -- with
+ * neither the scores nor the codes of P written to device memory.  Both contractions run as tcgen05 block-scaled MMAs; every
+ * rounding step between them is mxq_softmax_quantize's, so P's codes and scales are the ones that entry point produces from
+ * the bf16 scores, bit for bit (`p_codes` / `p_scales`, when given, receive them: the block's attention weights).
+ *   q_codes  : [batch, heads, q_len, 128] one byte per element (MXQ_OPERAND_E4M3_BYTES or _E5M2_BYTES; fp6 / fp4 reference codes
+ *              transcoded exactly with mxq_transcode_to_e4m3), contiguous; q_scales: [batch, heads, q_len, 4] E8M0
+ *   k_codes  : [batch, kv_heads, kv_len, 128], k_scales [batch, kv_heads, kv_len, 4]; query head h reads key / value head
+ *              h / (heads / kv_heads) (grouped-query attention: no repeated copies)
+ *   vt_codes : [batch, kv_heads, 128, kv_len] -- V quantized along the key axis, as the reference does it (quantize the
+ *              transpose, :209-213); vt_scales [batch, kv_heads, 128, kv_len / 32]
+ *   mask     : NULL or additive bf16, element (b, h, q, j) at mask + b*stride_b + h*stride_h + q*stride_q + j (0 strides broadcast)
+ *   causal   : additionally hide key j > q + (kv_len - q_len); key chunks no row of a tile can see are skipped
+ *   out      : bf16, element (b, h, q, d) at out + b*out_batch_stride + h*out_head_stride + q*out_row_stride + d (so the caller
+ *              picks [b, h, q, d] or the transposed [b, q, h, d] the reference produces next, :245)
+ *   p_elem   : element type of P (any floating-point mxq_elem_t), flags: MXQ_FLAG_*
+ * MXQ_ERR_UNSUPPORTED_SHAPE unless head_dim == 128, kv_len % 128 == 0, kv_len >= q_len, and the row is one whose block sums
+ * mxq_softmax_quantize adds in an order this kernel reproduces (masked / causal: kv_len <= 8192; unmasked: kv_len <= 1024).
+ */
+typedef struct {
+    const void *q_codes; const uint8_t *q_scales; int q_format;
+    const void *k_codes; const uint8_t *k_scales; int k_format;
+    const void *vt_codes; const uint8_t *vt_scales; int v_format;
+    int64_t batch, heads, kv_heads, q_len, kv_len; int head_dim;
+    float scaling;
+    const void *mask; int64_t mask_stride_b, mask_stride_h, mask_stride_q;
+    int causal;
+    int p_elem /* mxq_elem_t */; unsigned flags /* MXQ_FLAG_* */;
+    void *out; int64_t out_batch_stride, out_head_stride, out_row_stride;
+    void *p_codes; uint8_t *p_scales;
+} mxq_attention_args_t;
+MXQ_API int mxq_flash_attention(const mxq_attention_args_t *args, int device, void *stream);
+
+/*
  * SwiGLU gating + quantization  <->  the MLP block of the reference (torchmx/layers/mx_llama_attention.py:19-59 around
  * transformers' `down_proj(act_fn(gate_proj(x)) * up_proj(x))`) followed by the activation quantization on entry to down_proj
  * (torchmx/layers/mx_linear.py:63-66): codes, scales = quantize_mx(bf16(bf16(silu(gate)) * up), elem, 32) in one pass,

@@ -50,12 +50,15 @@ def test_quantize_llm_swaps_blocks_and_matches_the_dequantize_path(tiny_llama, q
     assert all(type(getattr(layer.self_attn, n)) is MXInferenceLinear for n in ("q_proj", "k_proj", "v_proj", "o_proj"))
     assert type(qm.lm_head) is MXInferenceLinear and "qconfig" in repr(layer.self_attn)
     assert layer.self_attn.qconfig.is_qkv_quantization_enabled == qkv
-    before = dict(mx_gemm.stats)
+    from torchmx import attention_ops
+    before, before_attn = dict(mx_gemm.stats), dict(attention_ops.stats)
     with torch.no_grad():
         out_tc = qm(input_ids=ids).logits
     n_mm = mx_gemm.stats["tensor_core"] - before["tensor_core"]
-    # 2 layers x (4 projections + stacked gate/up + down) + lm_head, plus 2 attention contractions per layer when Q/K/V are quantized
-    assert n_mm == 13 + (4 if qkv else 0) and mx_gemm.stats["fallback"] == before["fallback"]
+    # 2 layers x (4 projections + stacked gate/up + down) + lm_head; when Q/K/V are quantized both attention contractions of a
+    # layer run inside one K4b launch (head_dim 128, 128 keys)
+    assert n_mm == 13 and mx_gemm.stats["fallback"] == before["fallback"]
+    assert attention_ops.stats["flash_attention"] - before_attn["flash_attention"] == (2 if qkv else 0)
     mx_gemm.set_enabled(False)
     try:
         with torch.no_grad():
@@ -118,11 +121,20 @@ def test_quantize_llm_qwen2_with_projection_biases():
     layer = qm.model.layers[0]
     assert type(layer.self_attn) is MXInferenceQwen2Attention and type(layer.mlp) is MXInferenceQwen2MLP
     assert layer.self_attn.q_proj.bias is not None
-    before, soft0 = dict(mx_gemm.stats), attention_ops.stats["fused_softmax"]
+    before, soft0, flash0 = dict(mx_gemm.stats), attention_ops.stats["fused_softmax"], attention_ops.stats["flash_attention"]
     with torch.no_grad():
         out_tc = qm(input_ids=ids).logits
-    assert mx_gemm.stats["tensor_core"] - before["tensor_core"] == 17 and mx_gemm.stats["fallback"] == before["fallback"]
-    assert attention_ops.stats["fused_softmax"] == soft0 + 2
+    # 13 linears on the tensor cores; the attention of each layer (both contractions + softmax + quantization of P) is one K4b launch
+    assert mx_gemm.stats["tensor_core"] - before["tensor_core"] == 13 and mx_gemm.stats["fallback"] == before["fallback"]
+    assert attention_ops.stats["flash_attention"] == flash0 + 2 and attention_ops.stats["fused_softmax"] == soft0
+    prev = attention_ops.set_flash_attention(False)  # the chain K4b replaces: two bmm launches + K4a per layer
+    try:
+        with torch.no_grad():
+            out_chain = qm(input_ids=ids).logits
+    finally:
+        attention_ops.set_flash_attention(prev)
+    assert mx_gemm.stats["tensor_core"] - before["tensor_core"] == 13 + 17 and attention_ops.stats["fused_softmax"] == soft0 + 2
+    assert _sqnr(out_chain, out_tc) > 60, _sqnr(out_chain, out_tc)
     mx_gemm.set_enabled(False)
     try:
         with torch.no_grad():

@@ -17,7 +17,7 @@ ABI_VERSION = 2
 MAX_DIMS = 6
 
 EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_gemm_dequant", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
-           "mxq_softmax_quantize", "mxq_silu_mul_quantize", "mxq_rmsnorm", "mxq_rope", "mxq_last_error", "mxq_version", "mxq_arch")
+           "mxq_softmax_quantize", "mxq_flash_attention", "mxq_silu_mul_quantize", "mxq_rmsnorm", "mxq_rope", "mxq_last_error", "mxq_version", "mxq_arch")
 
 
 class GemmArgs(ctypes.Structure):
@@ -63,6 +63,22 @@ class SoftmaxArgs(ctypes.Structure):
         ("causal", ctypes.c_int),
         ("elem", ctypes.c_int), ("flags", ctypes.c_uint),
         ("codes", ctypes.c_void_p), ("scales", ctypes.c_void_p),
+    ]
+
+
+class AttentionArgs(ctypes.Structure):
+    _fields_ = [
+        ("q_codes", ctypes.c_void_p), ("q_scales", ctypes.c_void_p), ("q_format", ctypes.c_int),
+        ("k_codes", ctypes.c_void_p), ("k_scales", ctypes.c_void_p), ("k_format", ctypes.c_int),
+        ("vt_codes", ctypes.c_void_p), ("vt_scales", ctypes.c_void_p), ("v_format", ctypes.c_int),
+        ("batch", ctypes.c_int64), ("heads", ctypes.c_int64), ("kv_heads", ctypes.c_int64), ("q_len", ctypes.c_int64), ("kv_len", ctypes.c_int64),
+        ("head_dim", ctypes.c_int),
+        ("scaling", ctypes.c_float),
+        ("mask", ctypes.c_void_p), ("mask_stride_b", ctypes.c_int64), ("mask_stride_h", ctypes.c_int64), ("mask_stride_q", ctypes.c_int64),
+        ("causal", ctypes.c_int),
+        ("p_elem", ctypes.c_int), ("flags", ctypes.c_uint),
+        ("out", ctypes.c_void_p), ("out_batch_stride", ctypes.c_int64), ("out_head_stride", ctypes.c_int64), ("out_row_stride", ctypes.c_int64),
+        ("p_codes", ctypes.c_void_p), ("p_scales", ctypes.c_void_p),
     ]
 
 
@@ -130,6 +146,8 @@ def lib() -> ctypes.CDLL:
         L.mxq_silu_mul_quantize.argtypes = [vp, vp, i64, i64, i64, i64, i32, u32, vp, vp, i32, vp]
         L.mxq_softmax_quantize.restype = i32
         L.mxq_softmax_quantize.argtypes = [ctypes.POINTER(SoftmaxArgs), i32, vp]
+        L.mxq_flash_attention.restype = i32
+        L.mxq_flash_attention.argtypes = [ctypes.POINTER(AttentionArgs), i32, vp]
         L.mxq_rmsnorm.restype = i32
         L.mxq_rmsnorm.argtypes = [ctypes.POINTER(RmsNormArgs), i32, vp]
         L.mxq_rope.restype = i32

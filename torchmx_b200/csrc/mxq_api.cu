@@ -17,6 +17,7 @@ cudaError_t launch_pack_operand(const void*, int, int64_t, void*, int, cudaStrea
 cudaError_t launch_unpack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 int launch_gemm(const mxq_gemm_args_t*, int, int, cudaStream_t, char*, size_t);
 namespace gemm { int launch_gemm_dequant(const mxq_gemm_dequant_args_t*, int, cudaStream_t, char*, size_t); }
+namespace gemm { int launch_flash_attention(const mxq_attention_args_t*, int, cudaStream_t, char*, size_t); }
 cudaError_t launch_silu_mul_quantize(const void*, const void*, int64_t, int64_t, int64_t, int64_t, int, unsigned, void*, uint8_t*, int, cudaStream_t);
 int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size_t);
 int launch_rmsnorm(const mxq_rmsnorm_args_t*, cudaStream_t, char*, size_t);
@@ -245,6 +246,22 @@ int mxq_rope(const mxq_rope_args_t* a, int device, void* stream) {
     char msg[400] = "";
     const int rc = mxq::launch_rope(a, sm_count_of(scope.cur), (cudaStream_t)stream, msg, sizeof(msg));
     return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_rope: %s", msg);
+}
+
+int mxq_flash_attention(const mxq_attention_args_t* a, int device, void* stream) {
+    if (!a) return fail(MXQ_ERR_INVALID, "mxq_flash_attention: null args");
+    if (!valid_elem(a->p_elem)) return fail(MXQ_ERR_INVALID, "mxq_flash_attention: unknown element type %d", a->p_elem);
+    if (a->batch < 0 || a->heads < 0 || a->kv_heads < 0 || a->q_len < 0 || a->kv_len < 0) return fail(MXQ_ERR_INVALID, "mxq_flash_attention: negative extent");
+    if (a->batch == 0 || a->heads == 0 || a->q_len == 0) return MXQ_OK;
+    if (a->kv_heads == 0 || a->kv_len == 0) return fail(MXQ_ERR_INVALID, "mxq_flash_attention: no keys");
+    if (!a->q_codes || !a->q_scales || !a->k_codes || !a->k_scales || !a->vt_codes || !a->vt_scales || !a->out)
+        return fail(MXQ_ERR_INVALID, "mxq_flash_attention: null pointer");
+    if ((a->p_codes == nullptr) != (a->p_scales == nullptr)) return fail(MXQ_ERR_INVALID, "mxq_flash_attention: p_codes and p_scales go together");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_flash_attention: selecting device");
+    char msg[400] = "";
+    const int rc = mxq::gemm::launch_flash_attention(a, scope.cur, (cudaStream_t)stream, msg, sizeof(msg));
+    return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_flash_attention: %s", msg);
 }
 
 int mxq_softmax_quantize(const mxq_softmax_args_t* a, int device, void* stream) {

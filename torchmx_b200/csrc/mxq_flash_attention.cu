@@ -1,0 +1,601 @@
+// K4b: the MX attention block of the reference as ONE kernel (torchmx/layers/mx_llama_attention.py:195-243):
+//
+//     scores = matmul(Q_mx, K_mx^T)                  (MX operands blocked along head_dim; bf16 result)
+//     P      = to_mx(softmax(scores * scaling + mask, fp32).to(bf16), attention_weights_config)   (blocked along the kv axis)
+//     out    = matmul(P_mx, V_mx)                    (V quantized along the kv axis)
+//
+// The unfused path (K3 bmm -> K4a -> K3 bmm) writes the [b, h, q, kv] scores (268 MB per Llama-8B layer at 2048 tokens) and the
+// codes of P to HBM and reads them back.  Here neither exists in HBM: both contractions run on tcgen05 block-scaled MMAs
+// (kind::mxf8f6f4, E8M0 scale factors in TMEM), the accumulator of the first is read by the softmax threads straight from TMEM,
+// and the codes + scales of P go through shared memory into the second.
+//
+// The reference quantizes the NORMALISED probabilities, so the row maximum and the row sum must be final before the first code
+// of a row exists: an online (rescaling) softmax cannot reproduce the codes.  The kernel therefore makes three passes over the
+// key tiles of a query tile -- (A) row maximum, (B) row sum of expf(x - max), (C) P, its MX quantization and P @ V -- and
+// recomputes Q K^T in each (the tensor core has the time: the kernel is bound by the fp32 softmax arithmetic).  Every rounding
+// step is K4a's (mxq_softmax_core.cuh), and the per-block sums are added in K4a's order, so the codes of P are K4a's bit for bit.
+//
+// CTA = 256 query rows of one (batch, head): two warpgroups of 128 softmax threads (thread = query row = TMEM lane), each with
+// its own 128 x 64 score tile and 128 x 128 output accumulator in TMEM, sharing the K / V tiles the TMA warp streams in.
+//   warps 0..3 / 4..7  softmax warpgroup 0 / 1: tcgen05.ld two MX blocks of scores, K4a arithmetic, P codes -> swizzled shared
+//                      memory tile + scale words in the tcgen05.cp layout; finally drain the output accumulator
+//   warp 8             TMA producer: Q tiles once, then per pass the K tiles (128 keys x 128 B) and, in pass C, the V^T tiles
+//                      (128 channels x 128 keys)
+//   warp 9             MMA issuer (one elected lane): S = Q K^T as two N = 64 halves per 128-key chunk, O += P V per chunk
+//   warp 10            scale-factor loader: Q / K / V E8M0 scales from their reference layout into the tcgen05.cp chunk layout
+// Causal attention without an explicit mask skips the key chunks a warpgroup's rows cannot see.
+#include <cstring>
+
+#include "mxq_softmax_core.cuh"
+#include "mxq_tc.cuh"
+
+namespace mxq {
+namespace gemm {
+namespace fa {
+
+constexpr int QT = 128;     // query rows per warpgroup
+constexpr int KC = 128;     // keys per chunk: four MX blocks of P = one 32-bit scale word per row
+constexpr int HD = 128;     // head_dim
+constexpr int K_STAGES = 3, V_STAGES = 2;
+constexpr int kThreads = 256 + 96;
+constexpr int TILE_BYTES = 128 * 128;
+
+struct Smem {
+    static constexpr int OFF_Q = 0;
+    static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
+    static constexpr int OFF_V = OFF_K + K_STAGES * TILE_BYTES;
+    static constexpr int OFF_P = OFF_V + V_STAGES * TILE_BYTES;
+    static constexpr int OFF_SFQ = OFF_P + 2 * TILE_BYTES;
+    static constexpr int OFF_SFK = OFF_SFQ + 2 * 512;             // per stage: two 512-byte chunks (keys 0..63, 64..127)
+    static constexpr int OFF_SFV = OFF_SFK + K_STAGES * 1024;
+    static constexpr int OFF_SFP = OFF_SFV + V_STAGES * 512;
+    static constexpr int OFF_BAR = OFF_SFP + 2 * 512;
+    // q_full, qsf_full, k_full/ksf_full/k_empty[K_STAGES], v_full/vsf_full/v_empty[V_STAGES], s_full/s_free/p_full/p_free/o_full[2]
+    static constexpr int NUM_BARS = 2 + 3 * K_STAGES + 3 * V_STAGES + 10;
+    static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+    static constexpr int TOTAL = OFF_TMEM_PTR + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;
+    static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+// TMEM columns (512 allocated)
+constexpr uint32_t TM_S = 0;       // + 64 * wg
+constexpr uint32_t TM_O = 128;     // + 128 * wg
+constexpr uint32_t TM_SFQ = 384;   // + 4 * wg
+constexpr uint32_t TM_SFK = 392;   // + 8 * (chunk & 1) + 4 * half
+constexpr uint32_t TM_SFP = 408;   // + 4 * wg
+constexpr uint32_t TM_SFV = 416;   // + 4 * (chunk & 1)
+
+struct Params {
+    const uint8_t* q_sf; const uint8_t* k_sf; const uint8_t* v_sf;
+    const uint16_t* mask; int64_t mask_sb, mask_sh, mask_sq; int mask_vec;
+    uint16_t* out; int64_t out_sb, out_sh, out_sq;
+    uint8_t* p_codes; uint8_t* p_scales;
+    int batch, heads, kv_heads, q_len, kv_len;
+    int causal, causal_offset, skip_hidden_chunks;
+    int layout;  // sm::sum_layout of a row of kv_len / 32 blocks
+    float scaling;
+    uint32_t idesc_qk, idesc_pv;
+    uint32_t flags;
+    int q_tiles;
+};
+
+__device__ __forceinline__ uint32_t to_e4m3_pair(uint32_t h2) {  // f16x2 -> two e4m3 bytes (exact for every fp6 / fp4 value)
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+    return r;
+}
+
+// the 32 codes of a block as the tensor core wants them: one byte per element in an 8-bit container (e5m2 as it is, every other
+// element type as the E4M3 byte of the same value -- exact)
+template <int ELEM>
+__device__ __forceinline__ void container_bytes(const uint32_t (&out)[(ELEM == MXQ_ELEM_E2M1) ? 4 : 8], uint32_t (&c)[8]) {
+    if constexpr (ELEM == MXQ_ELEM_E4M3 || ELEM == MXQ_ELEM_E5M2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = out[i];
+    } else if constexpr (ELEM == MXQ_ELEM_E2M1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t b0 = (out[i] >> (16 * k)) & 0xFF, b1 = (out[i] >> (16 * k + 8)) & 0xFF;
+                // the earlier element sits in the HIGH nibble = high f16 half: swap the halves
+                const uint32_t p0 = to_e4m3_pair(__byte_perm(decode_e2m1_byte_f16x2(b0), 0, 0x1032));
+                const uint32_t p1 = to_e4m3_pair(__byte_perm(decode_e2m1_byte_f16x2(b1), 0, 0x1032));
+                c[2 * i + k] = p0 | (p1 << 16);
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            c[i] = to_e4m3_pair(decode_pair_f16x2<ELEM>(out[i] & 0xFFFF)) | (to_e4m3_pair(decode_pair_f16x2<ELEM>(out[i] >> 16)) << 16);
+    }
+}
+
+// K4a's order of adding the per-block sums of a row, fed one block at a time in block order
+struct RowSum {
+    float acc, a0, a1, a2, a3;
+    int n;  // blocks seen
+    __device__ __forceinline__ void init() { acc = 0.0f; a0 = a1 = a2 = a3 = 0.0f; n = 0; }
+};
+
+template <int ELEM>
+__global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                                                                         const __grid_constant__ CUtensorMap map_v, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);
+    uint64_t* q_full = bars;                       // both Q tiles landed (count 1 + tx)
+    uint64_t* qsf_full = bars + 1;                 // Q scales in shared memory (count 1)
+    uint64_t* k_full = bars + 2;                   // K tile landed (count 1 + tx)
+    uint64_t* ksf_full = k_full + K_STAGES;        // its scales (count 1)
+    uint64_t* k_empty = ksf_full + K_STAGES;       // MMAs reading the stage retired (count 1, commit)
+    uint64_t* v_full = k_empty + K_STAGES;
+    uint64_t* vsf_full = v_full + V_STAGES;
+    uint64_t* v_empty = vsf_full + V_STAGES;
+    uint64_t* s_full = v_empty + V_STAGES;         // [wg] score tile complete (count 1, commit)
+    uint64_t* s_free = s_full + 2;                 // [wg] score tile read into registers (count 128)
+    uint64_t* p_full = s_free + 2;                 // [wg] codes + scales of a chunk of P in shared memory (count 128)
+    uint64_t* p_free = p_full + 2;                 // [wg] MMAs reading them retired (count 1, commit)
+    uint64_t* o_full = p_free + 2;                 // [wg] output accumulator complete (count 1, commit)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::OFF_TMEM_PTR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh_count = p.batch * p.heads;
+    const int qt = p.q_tiles - 1 - (int)(blockIdx.x / bh_count);  // the tiles with the most visible keys first
+    const int bh = (int)(blockIdx.x % bh_count);
+    const int b = bh / p.heads, h = bh - b * p.heads;
+    const int bhk = b * p.kv_heads + h / (p.heads / p.kv_heads);  // grouped-query attention: the key / value head of this query head
+    const int n_total = p.kv_len / KC;
+    int nv[2];
+    bool active[2];
+#pragma unroll
+    for (int wg = 0; wg < 2; ++wg) {
+        const int q0 = qt * 2 * QT + wg * QT;
+        active[wg] = q0 < p.q_len;
+        const int last_row = min(q0 + QT - 1, p.q_len - 1);
+        nv[wg] = !active[wg] ? 0 : (p.skip_hidden_chunks ? min(n_total, (last_row + p.causal_offset) / KC + 1) : n_total);
+    }
+    const int n_cta = max(nv[0], nv[1]);
+
+    if (warp == 8 && elect_one()) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_k);
+        tma_prefetch_desc(&map_v);
+    }
+    if (warp == 9 && elect_one()) {
+        mbar_init(q_full, 1);
+        mbar_init(qsf_full, 1);
+        for (int i = 0; i < K_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&ksf_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < V_STAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&vsf_full[i], 1); mbar_init(&v_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], QT); mbar_init(&p_full[i], QT); mbar_init(&p_free[i], 1); mbar_init(&o_full[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 10) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 8) {
+        // ================= softmax warpgroups =================
+        const int wg = warp >> 2, quad = warp & 3;
+        const int r = quad * 32 + lane;                 // row inside the warpgroup's tile = TMEM lane
+        const int q = qt * 2 * QT + wg * QT + r;        // query row
+        const bool row_live = active[wg] && q < p.q_len;
+        const int my_n = nv[wg];
+        const uint32_t tm_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const uint16_t* mrow = (p.mask != nullptr && row_live) ? p.mask + (int64_t)b * p.mask_sb + (int64_t)h * p.mask_sh + (int64_t)q * p.mask_sq : nullptr;
+        const int tpr = p.kv_len / 32;
+        const bool hw_exact = (p.flags & MXQ_FLAG_HW_EXACT) != 0;
+        uint8_t* p_tile = smem + Smem::OFF_P + wg * TILE_BYTES + r * 128;
+        uint32_t* sfp_word = reinterpret_cast<uint32_t*>(smem + Smem::OFF_SFP + wg * 512 + 16 * (r & 31) + 4 * (r >> 5));
+        constexpr int NO = (ELEM == MXQ_ELEM_E2M1) ? 4 : 8;
+        uint8_t* dump_codes = (p.p_codes != nullptr && row_live) ? p.p_codes + ((int64_t)bh * p.q_len + q) * tpr * (NO * 4) : nullptr;
+        uint8_t* dump_scales = (p.p_codes != nullptr && row_live) ? p.p_scales + ((int64_t)bh * p.q_len + q) * tpr : nullptr;
+
+        float row_max = -INFINITY, row_sum = 0.0f;
+        uint32_t s_par = 0, pfree_par = 0;
+        for (int pass = 0; pass < 3 && active[wg]; ++pass) {
+            RowSum rs;
+            rs.init();
+            bool have_acc = false;
+            uint32_t sf_word = 0;
+            for (int j = 0; j < my_n; ++j) {
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    mbar_wait(&s_full[wg], s_par);
+                    s_par ^= 1;
+                    tc_fence_after();
+                    uint32_t v[64];
+                    {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld_32x32b_x32(tm_lane + TM_S + wg * 64, v0);
+                        tmem_ld_32x32b_x32(tm_lane + TM_S + wg * 64 + 32, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { v[i] = v0[i]; v[32 + i] = v1[i]; }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&s_free[wg]);  // the tensor core may overwrite the tile with the next one while we compute
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const int bl = 2 * hf + blk;   // block inside the chunk
+                        const int t = 4 * j + bl;      // block inside the row
+                        int vis = row_live ? 32 : 0;
+                        if (p.causal && row_live) vis = min(32, max(0, q + p.causal_offset + 1 - t * 32));
+                        float x[32];
+                        float m = -INFINITY, lo = INFINITY;
+                        if (vis > 0) {
+                            uint32_t w[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)  // the matmul result is a bf16 tensor
+                                w[i] = pack_bf16x2(__uint_as_float(v[32 * blk + 2 * i]), __uint_as_float(v[32 * blk + 2 * i + 1]));
+                            sm::scale_round(w, p.scaling, x);
+                            if (mrow != nullptr) {
+                                uint32_t mw[16];
+                                sm::load_mask(mrow + t * 32, p.mask_vec != 0, mw);
+                                sm::add_mask(x, mw);
+                            }
+                            if (vis < 32) sm::hide_from(x, vis);
+                            sm::block_max(x, m, lo);
+                        }
+                        if (pass == 0) {
+                            row_max = sm::max_nan(row_max, m);
+                            continue;
+                        }
+                        const bool dead = sm::block_dead(vis, m, row_max);
+                        if (pass == 1) {
+                            const float s = dead ? 0.0f : sm::exp_sum(x, row_max);
+                            // K4a's order (sm::sum_layout): blocks in order, or butterfly-reduced groups of 8 added in order
+                            if (p.layout == 0) {
+                                rs.acc = rs.acc + s;
+                            } else {
+                                const int k8 = t & 7;
+                                if (k8 == 0) rs.a0 = s;
+                                else if (k8 == 1) rs.a1 = s;
+                                else if (k8 == 2) rs.a2 = s;
+                                else if (k8 == 3) rs.a3 = s;
+                                else if (k8 == 4) rs.a0 = rs.a0 + s;
+                                else if (k8 == 5) rs.a1 = rs.a1 + s;
+                                else if (k8 == 6) rs.a2 = rs.a2 + s;
+                                else {
+                                    const float g = (rs.a0 + rs.a2) + (rs.a1 + (rs.a3 + s));
+                                    rs.acc = have_acc ? rs.acc + g : g;
+                                    have_acc = true;
+                                }
+                            }
+                            continue;
+                        }
+                        // ---- pass C: the codes of this block of P ----
+                        uint32_t c[8];
+                        int sc;
+                        if (dead) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) c[i] = 0;
+                            sc = row_live ? sm::dead_block_scale<ELEM>(row_max, row_sum) : 127;
+                            if (dump_codes != nullptr) {
+                                if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(0, 0, 0, 0);
+                                else { *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(0, 0, 0, 0); }
+                            }
+                        } else {
+                            sm::exp_sum(x, row_max);
+                            uint32_t w[16];
+                            sm::normalize(x, lo, row_max, row_sum, w);
+                            uint32_t out[NO];
+                            sc = quantize_block32<ELEM>(w, hw_exact, out);
+                            if (dump_codes != nullptr) {
+                                if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+                                else {
+                                    *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(out[0], out[1], out[2], out[3]);
+                                    *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(out[4], out[5], out[6], out[7]);
+                                }
+                            }
+                            container_bytes<ELEM>(out, c);
+                        }
+                        if (dump_scales != nullptr) dump_scales[t] = (uint8_t)sc;
+                        if (bl == 0) {
+                            sf_word = 0;
+                            if (j > 0) {  // the tensor core must be done with the previous chunk's codes before they are overwritten
+                                mbar_wait(&p_free[wg], pfree_par);
+                                pfree_par ^= 1;
+                            }
+                        }
+                        sf_word |= (uint32_t)sc << (8 * bl);
+                        // K-major 128B-swizzled operand tile: 16-byte chunk cc of row r lives at chunk cc ^ (r & 7)
+                        *reinterpret_cast<uint4*>(p_tile + (((2 * bl) ^ (r & 7)) << 4)) = make_uint4(c[0], c[1], c[2], c[3]);
+                        *reinterpret_cast<uint4*>(p_tile + (((2 * bl + 1) ^ (r & 7)) << 4)) = make_uint4(c[4], c[5], c[6], c[7]);
+                        if (bl == 3) {
+                            *sfp_word = sf_word;
+                            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                            mbar_arrive(&p_full[wg]);
+                        }
+                    }
+                }
+            }
+            if (pass == 1) {
+                if (p.layout != 0 && ((4 * my_n) & 7) != 0) {  // a half-filled last group (the rest of it: hidden blocks, sum 0)
+                    const float g = ((rs.a0 + 0.0f) + (rs.a2 + 0.0f)) + ((rs.a1 + 0.0f) + (rs.a3 + 0.0f));
+                    rs.acc = have_acc ? rs.acc + g : g;
+                }
+                row_sum = rs.acc;
+            }
+        }
+        if (active[wg]) {
+            // chunks this warpgroup skipped (hidden by the causal rule): their codes are +0 and the scale is that of a zero block
+            if (dump_codes != nullptr) {
+                const int sc = sm::dead_block_scale<ELEM>(row_max, row_sum);
+                for (int t = 4 * my_n; t < tpr; ++t) {
+                    if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(0, 0, 0, 0);
+                    else { *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(0, 0, 0, 0); }
+                    dump_scales[t] = (uint8_t)sc;
+                }
+            }
+            // ---- drain the output accumulator: thread = row, 128 bf16 = 256 contiguous bytes ----
+            mbar_wait(&o_full[wg], 0);
+            tc_fence_after();
+            uint16_t* orow = p.out + (int64_t)b * p.out_sb + (int64_t)h * p.out_sh + (int64_t)q * p.out_sq;
+#pragma unroll 1
+            for (int cg = 0; cg < 4; ++cg) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tm_lane + TM_O + wg * 128 + cg * 32, v);
+                tmem_ld_wait();
+                if (row_live) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+                        o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+                        o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+                        o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+                        *reinterpret_cast<uint4*>(orow + cg * 32 + 8 * i) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    } else if (warp == 8) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, (active[1] ? 2 : 1) * TILE_BYTES);
+            tma_load_3d(&map_q, q_full, smem + Smem::OFF_Q, 0, qt * 2 * QT, bh);  // rows past q_len read as zero
+            if (active[1]) tma_load_3d(&map_q, q_full, smem + Smem::OFF_Q + TILE_BYTES, 0, qt * 2 * QT + QT, bh);
+            uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+            for (int pass = 0; pass < 3; ++pass)
+                for (int j = 0; j < n_cta; ++j) {
+                    mbar_wait(&k_empty[ks], kph ^ 1);
+                    mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
+                    tma_load_3d(&map_k, &k_full[ks], smem + Smem::OFF_K + ks * TILE_BYTES, 0, j * KC, bhk);
+                    if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
+                    if (pass == 2) {
+                        mbar_wait(&v_empty[vs], vph ^ 1);
+                        mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+                        tma_load_3d(&map_v, &v_full[vs], smem + Smem::OFF_V + vs * TILE_BYTES, j * KC, 0, bhk);
+                        if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
+                    }
+                }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer =================
+        uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+        uint32_t sfree_par[2] = {0, 0}, pfull_par[2] = {0, 0};
+        const uint32_t q_addr = smem_u32(smem + Smem::OFF_Q), k_addr0 = smem_u32(smem + Smem::OFF_K), v_addr0 = smem_u32(smem + Smem::OFF_V);
+        const uint32_t p_addr = smem_u32(smem + Smem::OFF_P);
+        mbar_wait(q_full, 0);
+        mbar_wait(qsf_full, 0);
+        tc_fence_after();
+        if (elect_one()) {
+            tc_copy_sf(tmem_base + TM_SFQ, smem_desc(smem_u32(smem + Smem::OFF_SFQ), 128, kLayoutNone));
+            tc_copy_sf(tmem_base + TM_SFQ + 4, smem_desc(smem_u32(smem + Smem::OFF_SFQ + 512), 128, kLayoutNone));
+        }
+        __syncwarp();
+        // O[wg] += P[wg] (chunk jj) x V (chunk jj)
+        auto pv = [&](int jj) {
+            mbar_wait(&v_full[vs], vph);
+            mbar_wait(&vsf_full[vs], vph);
+            tc_fence_after();
+            const uint32_t tm_sfv = tmem_base + TM_SFV + 4 * (jj & 1);
+            if (elect_one()) tc_copy_sf(tm_sfv, smem_desc(smem_u32(smem + Smem::OFF_SFV + vs * 512), 128, kLayoutNone));
+            __syncwarp();
+#pragma unroll
+            for (int wg = 0; wg < 2; ++wg) {
+                if (!active[wg] || jj >= nv[wg]) continue;
+                mbar_wait(&p_full[wg], pfull_par[wg]);
+                pfull_par[wg] ^= 1;
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t tm_sfp = tmem_base + TM_SFP + 4 * wg;
+                    tc_copy_sf(tm_sfp, smem_desc(smem_u32(smem + Smem::OFF_SFP + wg * 512), 128, kLayoutNone));
+#pragma unroll
+                    for (int k = 0; k < KC / UMMA_K; ++k) {
+                        const uint64_t da = smem_desc(p_addr + wg * TILE_BYTES + k * UMMA_K, 1024, kLayoutSw128);
+                        const uint64_t db = smem_desc(v_addr0 + vs * TILE_BYTES + k * UMMA_K, 1024, kLayoutSw128);
+                        tc_mma_mx(tmem_base + TM_O + wg * 128, da, db, idesc_with_sf(p.idesc_pv, k, k), (jj | k) != 0, tm_sfp, tm_sfv);
+                    }
+                    tc_commit(&p_free[wg]);
+                    if (jj == nv[wg] - 1) tc_commit(&o_full[wg]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) tc_commit(&v_empty[vs]);
+            __syncwarp();
+            if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
+        };
+        for (int pass = 0; pass < 3; ++pass) {
+            for (int j = 0; j < n_cta; ++j) {
+                mbar_wait(&k_full[ks], kph);
+                mbar_wait(&ksf_full[ks], kph);
+                tc_fence_after();
+                const uint32_t tm_sfk = tmem_base + TM_SFK + 8 * (j & 1);
+                if (elect_one()) {
+                    tc_copy_sf(tm_sfk, smem_desc(smem_u32(smem + Smem::OFF_SFK + ks * 1024), 128, kLayoutNone));
+                    tc_copy_sf(tm_sfk + 4, smem_desc(smem_u32(smem + Smem::OFF_SFK + ks * 1024 + 512), 128, kLayoutNone));
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                    for (int wg = 0; wg < 2; ++wg) {
+                        if (!active[wg] || j >= nv[wg]) continue;
+                        mbar_wait(&s_free[wg], sfree_par[wg] ^ 1);
+                        sfree_par[wg] ^= 1;
+                        tc_fence_after();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < HD / UMMA_K; ++k) {
+                                const uint64_t da = smem_desc(q_addr + wg * TILE_BYTES + k * UMMA_K, 1024, kLayoutSw128);
+                                const uint64_t db = smem_desc(k_addr0 + ks * TILE_BYTES + hf * (64 * 128) + k * UMMA_K, 1024, kLayoutSw128);
+                                tc_mma_mx(tmem_base + TM_S + wg * 64, da, db, idesc_with_sf(p.idesc_qk, k, k), k != 0, tmem_base + TM_SFQ + 4 * wg,
+                                          tm_sfk + 4 * hf);
+                            }
+                            tc_commit(&s_full[wg]);
+                        }
+                        __syncwarp();
+                    }
+                    // software pipeline of pass C: the P @ V of the previous chunk goes behind the first score tile of this one,
+                    // so the softmax threads never wait for a score tile behind their own P @ V
+                    if (pass == 2 && hf == 0 && j >= 1) pv(j - 1);
+                }
+                if (elect_one()) tc_commit(&k_empty[ks]);
+                __syncwarp();
+                if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
+            }
+            if (pass == 2) pv(n_cta - 1);
+        }
+        tc_fence_before();
+    } else {
+        // ================= scale-factor loader =================
+        // tcgen05.cp.32x128b.warpx4 wants 32 chunks of 16 B per 128 rows: chunk i = the 32-bit scale words of rows i, i+32, i+64, i+96
+        auto publish = [&](uint64_t* bar) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        };
+        {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.q_sf) + (int64_t)bh * p.q_len;
+#pragma unroll
+            for (int wg = 0; wg < 2; ++wg) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[i] = src[min(qt * 2 * QT + wg * QT + i * 32 + lane, p.q_len - 1)];
+                *reinterpret_cast<uint4*>(smem + Smem::OFF_SFQ + wg * 512 + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            publish(qsf_full);
+        }
+        const uint32_t* ksrc = reinterpret_cast<const uint32_t*>(p.k_sf) + (int64_t)bhk * p.kv_len;
+        const int vld = p.kv_len / 32;  // scale bytes per channel row of V^T
+        const uint8_t* vsrc = p.v_sf + (int64_t)bhk * HD * vld;
+        auto load_k = [&](int j, uint32_t (&w)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = __ldg(ksrc + j * KC + i * 32 + lane);
+        };
+        uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
+        uint32_t kw[4], kn[4];
+        const int total = 3 * n_cta;
+        if (total > 0) load_k(0, kw);
+        for (int it = 0; it < total; ++it) {
+            const int pass = it / n_cta, j = it - pass * n_cta;
+            if (it + 1 < total) load_k((it + 1) % n_cta, kn);
+            uint32_t vw[4];
+            if (pass == 2) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vw[i] = __ldg(reinterpret_cast<const uint32_t*>(vsrc + (int64_t)(i * 32 + lane) * vld + 4 * j));
+            }
+            mbar_wait(&k_empty[ks], kph ^ 1);
+            *reinterpret_cast<uint4*>(smem + Smem::OFF_SFK + ks * 1024 + 16 * lane) = make_uint4(kw[0], kw[1], 0u, 0u);        // keys 0..63 of the chunk
+            *reinterpret_cast<uint4*>(smem + Smem::OFF_SFK + ks * 1024 + 512 + 16 * lane) = make_uint4(kw[2], kw[3], 0u, 0u);  // keys 64..127
+            publish(&ksf_full[ks]);
+            if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
+            if (pass == 2) {
+                mbar_wait(&v_empty[vs], vph ^ 1);
+                *reinterpret_cast<uint4*>(smem + Smem::OFF_SFV + vs * 512 + 16 * lane) = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+                publish(&vsf_full[vs]);
+                if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) kw[i] = kn[i];
+        }
+    }
+    __syncthreads();
+    if (warp == 10) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace fa
+
+int launch_flash_attention(const mxq_attention_args_t* a, int device, cudaStream_t stream, char* msg, size_t msg_len) {
+    using namespace fa;
+    auto fmt_ok = [](int f) { return f == MXQ_OPERAND_E4M3_BYTES || f == MXQ_OPERAND_E5M2_BYTES; };
+    if (a->head_dim != HD || a->kv_len % KC || a->kv_len < KC || a->q_len < 1 || a->kv_len < a->q_len || a->heads % a->kv_heads) {
+        snprintf(msg, msg_len, "needs head_dim == 128, kv_len %% 128 == 0, kv_len >= q_len, heads %% kv_heads == 0");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    if (!fmt_ok(a->q_format) || !fmt_ok(a->k_format) || !fmt_ok(a->v_format) || a->p_elem == MXQ_ELEM_INT8) {
+        snprintf(msg, msg_len, "operands must be 8-bit floating-point containers and the probabilities a floating-point element type");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    const bool masked = a->causal || a->mask != nullptr;
+    const int tpr = (int)(a->kv_len / 32);
+    const int layout = sm::sum_layout(tpr, masked);
+    if (layout == 2) {
+        snprintf(msg, msg_len, "row sums of %d blocks (%s) are added in an order this kernel does not reproduce", tpr, masked ? "masked" : "unmasked");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    auto al16 = [](const void* ptr) { return ((uintptr_t)ptr % 16) == 0; };
+    if (!al16(a->q_codes) || !al16(a->k_codes) || !al16(a->vt_codes) || ((uintptr_t)a->q_scales % 4) || ((uintptr_t)a->k_scales % 4) || ((uintptr_t)a->vt_scales % 4) ||
+        !al16(a->out) || (a->out_batch_stride % 8) || (a->out_head_stride % 8) || (a->out_row_stride % 8) || (a->p_codes && !al16(a->p_codes))) {
+        snprintf(msg, msg_len, "misaligned operand");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    const int64_t bh = a->batch * a->heads, bhk = a->batch * a->kv_heads;
+    const int64_t q_tiles = (a->q_len + 2 * QT - 1) / (2 * QT);
+    if (bh * q_tiles > 0x7FFFFFFF || a->q_len > 0x3FFFFFFF || a->kv_len > 0x3FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+    CUtensorMap map_q, map_k, map_v;
+    if (!cached_operand_map(&map_q, a->q_codes, HD, a->q_len, bh, HD, a->q_len * HD, 128, a->q_format, device) ||
+        !cached_operand_map(&map_k, a->k_codes, HD, a->kv_len, bhk, HD, a->kv_len * HD, 128, a->k_format, device) ||
+        !cached_operand_map(&map_v, a->vt_codes, a->kv_len, HD, bhk, a->kv_len, (int64_t)HD * a->kv_len, 128, a->v_format, device)) {
+        snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed");
+        return MXQ_ERR_CUDA;
+    }
+    fa::Params p;
+    memset(&p, 0, sizeof(p));
+    p.q_sf = a->q_scales; p.k_sf = a->k_scales; p.v_sf = a->vt_scales;
+    p.mask = (const uint16_t*)a->mask; p.mask_sb = a->mask_stride_b; p.mask_sh = a->mask_stride_h; p.mask_sq = a->mask_stride_q;
+    p.mask_vec = a->mask && ((uintptr_t)a->mask % 16 == 0) && (a->mask_stride_b % 8 == 0) && (a->mask_stride_h % 8 == 0) && (a->mask_stride_q % 8 == 0);
+    p.out = (uint16_t*)a->out; p.out_sb = a->out_batch_stride; p.out_sh = a->out_head_stride; p.out_sq = a->out_row_stride;
+    p.p_codes = (uint8_t*)a->p_codes; p.p_scales = a->p_scales;
+    p.batch = (int)a->batch; p.heads = (int)a->heads; p.kv_heads = (int)a->kv_heads; p.q_len = (int)a->q_len; p.kv_len = (int)a->kv_len;
+    p.causal = a->causal ? 1 : 0;
+    p.causal_offset = (int)(a->kv_len - a->q_len);
+    p.skip_hidden_chunks = p.causal;  // (an explicit mask is data: every chunk is read)
+    p.layout = layout;
+    p.scaling = a->scaling;
+    // the probabilities travel as E4M3 bytes (exact for every fp6 / fp4 value) unless they ARE e5m2
+    const int p_format = a->p_elem == MXQ_ELEM_E5M2 ? MXQ_OPERAND_E5M2_BYTES : MXQ_OPERAND_E4M3_BYTES;
+    p.idesc_qk = make_idesc(QT, 64) | idesc_formats(a->q_format, a->k_format);
+    p.idesc_pv = make_idesc(QT, HD) | idesc_formats(p_format, a->v_format);
+    p.flags = a->flags;
+    p.q_tiles = (int)q_tiles;
+    const unsigned grid = (unsigned)(bh * q_tiles);
+#define MXQ_FA_CASE(E)                                                                                                              \
+    case E: {                                                                                                                       \
+        cudaError_t e = ensure_smem_attr((const void*)mx_flash_attention_kernel<E>, Smem::DYN_BYTES, device);                        \
+        if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }   \
+        mx_flash_attention_kernel<E><<<grid, fa::kThreads, Smem::DYN_BYTES, stream>>>(map_q, map_k, map_v, p);                          \
+        break;                                                                                                                      \
+    }
+    switch (a->p_elem) {
+        MXQ_FA_CASE(MXQ_ELEM_E4M3) MXQ_FA_CASE(MXQ_ELEM_E3M2) MXQ_FA_CASE(MXQ_ELEM_E2M3) MXQ_FA_CASE(MXQ_ELEM_E2M1) MXQ_FA_CASE(MXQ_ELEM_E5M2)
+    default: snprintf(msg, msg_len, "unknown element type %d", a->p_elem); return MXQ_ERR_INVALID;
+    }
+#undef MXQ_FA_CASE
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (flash attention): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    return MXQ_OK;
+}
+
+}  // namespace gemm
+}  // namespace mxq

@@ -16,10 +16,9 @@
 // Layout: one thread owns one 32-element MX block of a row (32 fp32 values in registers).  Rows of 8 .. 256 blocks (the
 // prefill sizes) are laid out 4 rows x 8 blocks per warp, so that causally hidden blocks fill whole warps; shorter rows share
 // a warp lane-segment-wise, longer ones span whole warps.  Row reductions: shuffles + one shared-memory exchange.  L <= 32768.
-#include "mxq_quant_core.cuh"
-
-#include <cmath>
 #include <cstdio>
+
+#include "mxq_softmax_core.cuh"
 
 namespace mxq {
 
@@ -39,16 +38,7 @@ struct SoftmaxParams {
     uint32_t flags;
 };
 
-__device__ __forceinline__ float max_nan(float a, float b) {
-    float r;
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ float max_nan3(float a, float b, float c) {  // FMNMX3.NAN: one issue slot for two comparisons
-    float r;
-    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
+using sm::max_nan;
 
 template <int ELEM, int MAXT>
 __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxParams p) {
@@ -103,39 +93,15 @@ __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxPar
 #pragma unroll
             for (int k = 0; k < 8; ++k) w[8 * j + k] = v.v[k];
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t r = pack_bf16x2(__uint_as_float(w[i] << 16) * p.scaling, __uint_as_float(w[i] & 0xFFFF0000u) * p.scaling);
-            x[2 * i] = __uint_as_float(r << 16);
-            x[2 * i + 1] = __uint_as_float(r & 0xFFFF0000u);
-        }
+        sm::scale_round(w, p.scaling, x);
         if (p.mask) {
             const int64_t q = row % p.q_len, bh = row / p.q_len;
             const int64_t h = bh % p.heads, b = bh / p.heads;
-            const uint16_t* m = p.mask + b * p.mask_sb + h * p.mask_sh + q * p.mask_sq + (int64_t)t * 32;
             uint32_t mw[16];
-            if (p.mask_vec) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(m + 8 * j);
-                    mw[4 * j] = v.x; mw[4 * j + 1] = v.y; mw[4 * j + 2] = v.z; mw[4 * j + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) mw[i] = (uint32_t)m[2 * i] | ((uint32_t)m[2 * i + 1] << 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint32_t r = pack_bf16x2(x[2 * i] + __uint_as_float(mw[i] << 16), x[2 * i + 1] + __uint_as_float(mw[i] & 0xFFFF0000u));
-                x[2 * i] = __uint_as_float(r << 16);
-                x[2 * i + 1] = __uint_as_float(r & 0xFFFF0000u);
-            }
+            sm::load_mask(p.mask + b * p.mask_sb + h * p.mask_sh + q * p.mask_sq + (int64_t)t * 32, p.mask_vec != 0, mw);
+            sm::add_mask(x, mw);
         }
-        if (vis < 32) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i >= vis) x[i] = -INFINITY;
-        }
+        if (vis < 32) sm::hide_from(x, vis);
     }
 
     // ---- row max ---------------------------------------------------------------------------------------------------
@@ -143,17 +109,7 @@ __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxPar
     // as the unfused softmax (whose max drops NaNs but whose sum picks them up).
     float m = -INFINITY;  // a block the query row cannot see at all (vis == 0) never touches x[]
     float lo = INFINITY;  // smallest entry: tells below whether any exp() can be denormal-ish without a per-element test
-    if (vis > 0) {
-        m = x[0];
-        lo = x[0];
-#pragma unroll
-        for (int i = 1; i < 31; i += 2) {
-            m = max_nan3(m, x[i], x[i + 1]);
-            lo = fminf(lo, fminf(x[i], x[i + 1]));
-        }
-        m = max_nan(m, x[31]);
-        lo = fminf(lo, x[31]);
-    }
+    if (vis > 0) sm::block_max(x, m, lo);
     auto row_reduce = [&](float v, bool is_max) -> float {
         if (layout == 0) {
             float acc = is_max ? -INFINITY : 0.0f;
@@ -185,21 +141,14 @@ __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxPar
     // zero below about -104): hidden by the causal rule, by a -inf / finfo.min additive mask, or simply negligible.  Its
     // exponentials, divides and conversions are skipped; NaNs fail the comparison and take the full path.
     float s = 0.0f;
-    const bool dead = vis == 0 || (m - row_max < -110.0f);
-    if (!dead) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            x[i] = expf(x[i] - row_max);
-            s += x[i];
-        }
-    }
+    const bool dead = sm::block_dead(vis, m, row_max);
+    if (!dead) s = sm::exp_sum(x, row_max);
     const float row_sum = row_reduce(s, false);
     if (!live) return;
     const int64_t blk = row * p.tpr + t;
     constexpr int NO = (ELEM == MXQ_ELEM_E2M1) ? 4 : 8;
     if (dead) {
         // hidden block: +0 everywhere -> codes 0, scale = shared exponent of an all-zero block; NaN row -> scale 255, codes 0
-        const bool nan_row = !(row_sum == row_sum) || row_max == -INFINITY;  // NaN score in the row / every position hidden
         uint8_t* dst = p.codes + blk * (NO * 4);
         if constexpr (NO == 4) stg128_stream(dst, make_uint4(0, 0, 0, 0));
         else {
@@ -208,36 +157,11 @@ __global__ void __launch_bounds__(MAXT) softmax_quantize_kernel(const SoftmaxPar
             for (int k = 0; k < 8; ++k) o.v[k] = 0;
             stg256_stream(dst, o);
         }
-        p.scales[blk] = (uint8_t)(nan_row ? 255 : shared_exp_from_maxE<ELEM>(0));
+        p.scales[blk] = (uint8_t)sm::dead_block_scale<ELEM>(row_max, row_sum);
         return;
     }
-    // p = e / row_sum, correctly rounded.  nvcc's own expansion of an fp32 divide is: r0 = MUFU.RCP(b); r = fma(r0, fma(-b, r0, 1), r0);
-    // q = a * r; q' = fma(r, fma(-b, q, a), q) -- guarded per divide by a range check (FCHK) that sends denormal-ish operands
-    // to a slow path.  Here b is shared by the whole row, so r is computed once and each element costs three instructions;
-    // the guard becomes "0 < e < 2^-80 or an unusual denominator", in which case the block takes the plain divide.
     uint32_t w[16];
-    const bool plain_b = row_sum >= 1.0f && row_sum <= 65536.0f;  // sum of <= 32768 terms in [0,1] with exp(0) = 1 among them
-    // 0 < e < 2^-80 anywhere?  Not if the smallest entry is within 55 of the row max (e >= exp(-55) > 2^-80); only blocks with
-    // very small (or masked) entries pay for the per-element test.
-    uint32_t tiny = 0;
-    if (!(lo - row_max >= -55.0f)) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tiny |= (uint32_t)((__float_as_uint(x[i]) - 1u) < 0x17800000u - 1u);
-    }
-    if (plain_b && !tiny) {
-        float r0;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(row_sum));
-        const float r = __fmaf_rn(r0, __fmaf_rn(-row_sum, r0, 1.0f), r0);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float a0 = x[2 * i], a1 = x[2 * i + 1];
-            const float q0 = a0 * r, q1 = a1 * r;
-            w[i] = pack_bf16x2(__fmaf_rn(r, __fmaf_rn(-row_sum, q0, a0), q0), __fmaf_rn(r, __fmaf_rn(-row_sum, q1, a1), q1));
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(x[2 * i] / row_sum, x[2 * i + 1] / row_sum);
-    }
+    sm::normalize(x, lo, row_max, row_sum, w);
 
     // ---- K1's block quantizer ------------------------------------------------------------------------------------------
     uint32_t out[NO];
@@ -278,18 +202,16 @@ int launch_softmax_quantize(const mxq_softmax_args_t* a, cudaStream_t stream, ch
     int threads;
     int64_t rows_per_cta;
     const bool masked = p.causal || p.mask;
-    if (p.tpr < 8 || (!masked && p.tpr <= 32)) {
-        p.layout = 0;
+    p.layout = sm::sum_layout(p.tpr, masked);  // (K4b adds the block sums of a row in the order this choice implies)
+    if (p.layout == 0) {
         threads = 256;
         rows_per_cta = (int64_t)(32 / p.tpr) * (threads / 32);
-    } else if (masked && p.tpr <= 256) {
-        p.layout = 1;  // measured on [32, 2048, 2048]: 6 % faster than B with a causal mask, 9 % slower without any mask
+    } else if (p.layout == 1) {  // measured on [32, 2048, 2048]: 6 % faster than layout 2 with a causal mask, 9 % slower without any mask
         const int wpr = (p.tpr + 7) / 8;
         const int groups = wpr >= 8 ? 1 : 8 / wpr;
         threads = wpr * groups * 32;
         rows_per_cta = 4 * groups;
     } else {
-        p.layout = 2;
         const int wpr = (p.tpr + 31) / 32;
         const int rpc = wpr >= 8 ? 1 : 8 / wpr;
         threads = wpr * rpc * 32;

@@ -245,14 +245,10 @@ class _MXAttentionMixin:
         dtype = query_states.dtype
         groups = self.num_key_value_groups
         q_mx = MXTensor.to_mx(query_states.contiguous(), qc.query_config.elem_dtype, qc.query_config.block_size)
-        # The reference repeats K and V to the number of query heads and then quantizes (:189-213).  Every MX block lives inside
-        # one head (K: along head_dim; V: along the sequence of one (head, channel) row), so quantizing the key/value heads once
-        # and repeating the CODES is bit-identical -- a quarter of the quantization work and of the bytes copied under 4-way GQA.
-        k_mx = _repeat_heads(MXTensor.to_mx(key_states.contiguous(), qc.key_config.elem_dtype, qc.key_config.block_size), groups)
-        v_mx = _repeat_heads(MXTensor.to_mx(value_states.transpose(2, 3).contiguous(), qc.value_config.elem_dtype, qc.value_config.block_size),
-                             groups).transpose(2, 3)
-        scores = torch.matmul(q_mx, k_mx.transpose(2, 3))
-        q_len, kv_len = scores.shape[-2], scores.shape[-1]
+        k_one = MXTensor.to_mx(key_states.contiguous(), qc.key_config.elem_dtype, qc.key_config.block_size)
+        vt_one = MXTensor.to_mx(value_states.transpose(2, 3).contiguous(), qc.value_config.elem_dtype, qc.value_config.block_size)
+        pc = qc.attention_weights_config
+        q_len, kv_len = q_mx.shape[-2], k_one.shape[-2]
         mask, causal = None, False
         if attention_mask is not None:  # no matter the length, we just slice it (reference :218-220)
             mask = attention_mask[:, :, :, :kv_len]
@@ -261,7 +257,18 @@ class _MXAttentionMixin:
         elif q_len > 1 and getattr(self, "is_causal", True):
             causal = True  # mask creation was skipped because the attention function is expected to apply is_causal itself
         dropout = self.training and getattr(self, "attention_dropout", 0.0)
-        pc = qc.attention_weights_config
+        if not dropout and 32 == qc.query_config.block_size == qc.key_config.block_size == qc.value_config.block_size:
+            # K4b: both contractions, the softmax chain and the quantization of P as one kernel -- the scores and P never reach HBM;
+            # key / value heads are read in place by the query heads that share them (no repeated copies)
+            out = attention_ops.flash_attention(q_mx, k_one, vt_one, scaling, mask, causal, pc.elem_dtype, pc.block_size)
+            if out is not None:
+                return out
+        # The reference repeats K and V to the number of query heads and then quantizes (:189-213).  Every MX block lives inside
+        # one head (K: along head_dim; V: along the sequence of one (head, channel) row), so quantizing the key/value heads once
+        # and repeating the CODES is bit-identical -- a quarter of the quantization work and of the bytes copied under 4-way GQA.
+        k_mx = _repeat_heads(k_one, groups)
+        v_mx = _repeat_heads(vt_one, groups).transpose(2, 3)
+        scores = torch.matmul(q_mx, k_mx.transpose(2, 3))
         # scale, mask, fp32 softmax, bf16 rounding and P quantization in one pass over the scores (K4a) ...
         p_mx = None if dropout else attention_ops.softmax_to_mx(scores, scaling, mask, causal, pc.elem_dtype, pc.block_size)
         if p_mx is None:  # ... or the chain as the reference spells it (:214-239)
