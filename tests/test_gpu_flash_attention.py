@@ -15,8 +15,13 @@ DEV = "cuda:0"
 
 
 def _repeat(t, n):
-    from torchmx_b200.layers.mx_llama_attention import _repeat_heads
-    return _repeat_heads(t, n)
+    """repeat_kv on the codes and scales, as contiguous copies (a single key / value head would otherwise come back as a stride-0
+    view, which the bmm serves through the dequantize GEMM: same products, another accumulation order)"""
+    from torchmx_b200.mx_tensor import MXTensor
+    if n == 1:
+        return t
+    rep = lambda x: x.repeat_interleave(n, dim=1).contiguous()  # noqa: E731
+    return MXTensor(rep(t._scale_e8m0), rep(t._data), t._elem_dtype, t._block_size, t._orig_dtype, t._padding, t._block_dim)
 
 
 def _chain(q_mx, k_mx, vt_mx, scaling, mask, causal, p_dt):
