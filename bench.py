@@ -280,6 +280,66 @@ def mx_matmul_extras(dev):
     del m8, m4
     _, us5 = timed(lambda: MXTensor.to_mx(x0, dtypes.float8_e5m2, BLOCK), n=4, rounds=3)
     out["to_mx_float8_e5m2_extension_16384x16384"] = {"us": round(us5, 1), "GB/s": round(n_el * (3 + 1 / 32) / us5 / 1e3, 1), "parity": "unpinned (element type absent from the reference)"}
+    del x0
+    # (7) fp4 x fp4 on kind::mxf4 (dense 4-bit operand streams, twice the rate of kind::mxf8f6f4) -- and the same operands on
+    # kind::mxf8f6f4 beside it
+    A4 = MXTensor.to_mx(torch.randn(M, K, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.float4_e2m1, BLOCK)
+    W4 = MXTensor.to_mx(torch.randn(N, K, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.float4_e2m1, BLOCK)
+    us_min, us_med = timed(lambda: torch.nn.functional.linear(A4, W4))
+    mx_gemm.overrides["no_mxf4"] = True
+    try:
+        _, us_f8 = timed(lambda: torch.nn.functional.linear(A4, W4))
+    finally:
+        mx_gemm.overrides["no_mxf4"] = False
+    out["linear_8192x8192x8192_e2m1xe2m1_mxf4"] = {
+        "us": round(us_med, 1), "us_best": round(us_min, 1), "TFLOP/s": round(flops / us_med / 1e6, 1), "same_operands_on_mxf8f6f4_us": round(us_f8, 1),
+        "roofline": {"bound": "tensor", "kernel": "mx_gemm_pair_kernel<MXF4> (tcgen05 cta_group::2 kind::mxf4.block_scale.scale_vec::2X)",
+                     "achieved": round(flops / us_med / 1e6, 1), "peak": 9000.0, "unit": "TFLOP/s", "frac": round(flops / us_med / 1e6 / 9000.0, 4),
+                     "peak_source": "nominal dense fp4 (9 PFLOP/s)", "frac_of_4x_measured_bf16": round(flops / us_med / 1e6 / (2 * meas2), 4)}}
+    del A4, W4
+    # (8) operands the block-scaled MMA cannot take (int8 elements: the reference's chat example) -> K3d, dequantize fused into a
+    # bf16 tcgen05 GEMM; beside it the recipe it replaces (two K2 launches + a cuBLAS bf16 GEMM)
+    Mi, Ni, Ki = 2048, 4096, 4096
+    Ai = MXTensor.to_mx(torch.randn(Mi, Ki, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.int8, BLOCK)
+    Wi = MXTensor.to_mx(torch.randn(Ni, Ki, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.int8, BLOCK)
+    d0 = mx_gemm.stats["dequant_gemm"]
+    _, us_k3d = timed(lambda: torch.nn.functional.linear(Ai, Wi), n=4)
+    used_k3d = mx_gemm.stats["dequant_gemm"] > d0
+    prev = mx_gemm.set_dequant_gemm(False)
+    try:
+        _, us_lib = timed(lambda: torch.nn.functional.linear(Ai, Wi), n=4)
+    finally:
+        mx_gemm.set_dequant_gemm(prev)
+    fi = 2.0 * Mi * Ni * Ki
+    out["linear_2048x4096x4096_int8_dequant_gemm"] = {
+        "us": round(us_k3d, 1), "TFLOP/s": round(fi / us_k3d / 1e6, 1), "kernel_used": "mx_gemm_dequant_kernel (K3d)" if used_k3d else "fallback",
+        "k2_plus_cublas_bf16_us": round(us_lib, 1),
+        "roofline": {"bound": "tensor", "achieved": round(fi / us_k3d / 1e6, 1), "peak": meas2 / 2, "unit": "TFLOP/s", "frac": round(fi / us_k3d / 1e6 / (meas2 / 2), 4),
+                     "peak_source": "measured cuBLAS bf16 (kind::f16 operands)", "note": "bound by the CUDA-core dequantization of both operand tiles, see DESIGN.md K3d"}}
+    del Ai, Wi
+    # (9) MX attention as one kernel (K4b) vs the bmm -> K4a -> bmm chain: a Llama-3-8B layer at 2048 tokens (32 query / 8 key-value
+    # heads, head_dim 128, e4m3 Q / K / V / P, causal)
+    from torchmx_b200.layers.mx_llama_attention import _repeat_heads
+    q = torch.randn(1, 32, 2048, 128, device=dev, dtype=torch.bfloat16, generator=gen)
+    k = torch.randn(1, 8, 2048, 128, device=dev, dtype=torch.bfloat16, generator=gen)
+    v = torch.randn(1, 8, 2048, 128, device=dev, dtype=torch.bfloat16, generator=gen)
+    E8 = dtypes.float8_e4m3
+    Qm, Km, Vt = MXTensor.to_mx(q, E8, BLOCK), MXTensor.to_mx(k, E8, BLOCK), MXTensor.to_mx(v.transpose(2, 3).contiguous(), E8, BLOCK)
+
+    def chain():
+        kk, vv = _repeat_heads(Km, 4), _repeat_heads(Vt, 4).transpose(2, 3)
+        p_ = attention_ops.softmax_to_mx(torch.matmul(Qm, kk.transpose(2, 3)), 128 ** -0.5, None, True, E8, BLOCK)
+        return torch.matmul(p_, vv).transpose(1, 2).contiguous()
+
+    f0 = attention_ops.stats["flash_attention"]
+    _, us_fa = timed(lambda: attention_ops.flash_attention(Qm, Km, Vt, 128 ** -0.5, None, True, E8, BLOCK))
+    _, us_ch = timed(chain, n=4)
+    io_bytes = (32 + 2 * 8) * 2048 * 128 * (1 + 1 / 32) + 32 * 2048 * 128 * 2
+    out["mx_attention_1x32x2048x128_causal"] = {
+        "flash_kernel_us": round(us_fa, 1), "bmm_softmax_bmm_chain_us": round(us_ch, 1), "kernel_used": attention_ops.stats["flash_attention"] > f0,
+        "algorithmic_bytes": int(io_bytes), "chain_extra_hbm_bytes": int(32 * 2048 * 2048 * (2 + 2 + 2 * (1 + 1 / 32))),
+        "bound": "instruction issue: three exact softmax passes over the visible scores (row max, row sum, P) -- the reference quantizes the NORMALISED probabilities"}
+    del q, k, v, Qm, Km, Vt
     out["tensor_core_calls"] = mx_gemm.stats["tensor_core"] - before["tensor_core"]
     out["fallback_calls"] = mx_gemm.stats["fallback"] - before["fallback"]
     return out
@@ -296,7 +356,8 @@ def llama8b_extras():
     from tools import llama_bench
     out = {}
     peak_hbm, _ = measured_peak_gbs()
-    for key, kw in (("quantize_linear_", dict(llm_api=False)), ("quantize_llm_fused_norm", dict(llm_api=True, fuse_norm=True))):
+    for key, kw in (("quantize_linear_", dict(llm_api=False)), ("quantize_llm_fused_norm", dict(llm_api=True, fuse_norm=True)),
+                    ("quantize_llm_mx_attention_fused_norm", dict(llm_api=True, fuse_norm=True, mx_attention=True))):
         try:
             r = llama_bench.run_cfg(model="8b", steps=32, prefill_iters=3, **kw)
         except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
@@ -316,7 +377,7 @@ def llama8b_extras():
                                "weight_stream_bytes": stream_bytes, "weight_stream_floor_ms": round(stream_bytes / peak_hbm / 1e6, 3),
                                "frac_of_weight_stream_roofline": round(stream_bytes / peak_hbm / 1e6 / dec_ms, 4)},
             "timing": "CUDA-graph replay of the whole forward (eager numbers beside it include Python dispatch)",
-            "gemm_stats": r["gemm_stats"], "resident_GB": round(r["resident_after_run_GB"], 2),
+            "gemm_stats": r["gemm_stats"], "attention_stats": r.get("attention_stats"), "resident_GB": round(r["resident_after_run_GB"], 2),
         }
         gc.collect()
         torch.cuda.empty_cache()
@@ -501,7 +562,10 @@ def run_b200(args):
     del xs, xh, yhs, chs
     torch.cuda.empty_cache()
     if rank == 0 and not args.skip_gemm and world == 1:  # single-GPU numbers; under torchrun the other ranks would only wait
-        extras = mx_matmul_extras(dev)
+        try:
+            extras = mx_matmul_extras(dev)
+        except Exception as e:  # noqa: BLE001  (secondary numbers must never cost the headline line)
+            extras = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
         torch.cuda.empty_cache()
     if not args.skip_llama:
         if world == 1:

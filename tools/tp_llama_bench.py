@@ -9,7 +9,9 @@ One process per GPU (torchrun).  Two measurements:
       RowParallelMXLinear (weights fp4_e2m1 by default, activations fp8_e4m3): q/k/v/gate/up split out_features,
       o/down split in_features and all-reduce their bf16 partial outputs over NCCL.  Prefill of 2048 tokens and decode
       at batch 32, each replayed from a CUDA graph; tokens/s = tokens / max-over-ranks device time.
-      Everything that is not a projection (RMSNorm, rotary, attention over the local heads, SiLU) is plain PyTorch.
+      Between the projections a layer is five more launches of this library (RMSNorm with the residual add and the activation
+      quantization folded in -- K5a --, rotary embedding -- K5b --, SiLU gating + quantization -- K1b) plus the KV-cache update
+      and the attention over the local heads (PyTorch SDPA).  `--no-glue` runs the same stack with plain PyTorch glue.
 
  `--check` runs a small configuration and compares the TP output with the same stack evaluated on one rank.
 
@@ -40,16 +42,21 @@ def rms_norm(x, w, eps=1e-5):
     return F.rms_norm(x, (x.shape[-1],), w, eps)
 
 
+GLUE = True  # --no-glue: RMSNorm / rotary / SiLU as plain PyTorch ops, one launch per projection
+
+
 def rope_tables(pos, d, theta=500000.0):
-    """cos / sin for the positions of this forward pass, shared by every layer: [1, 1, T, d/2] fp32"""
+    """cos / sin for the positions of this forward pass, shared by every layer: [1, 1, T, d/2] fp32 (plain path) and the
+    transformers-style bf16 [1, T, d] tables (cat(freqs, freqs)) the rotary kernel reads"""
     inv = 1.0 / (theta ** (torch.arange(0, d, 2, device=pos.device, dtype=torch.float32) / d))
     ang = pos.float()[:, None] * inv[None, :]
-    return ang.cos()[None, None], ang.sin()[None, None]
+    emb = torch.cat([ang, ang], -1)[None]
+    return ang.cos()[None, None], ang.sin()[None, None], emb.cos().to(torch.bfloat16), emb.sin().to(torch.bfloat16)
 
 
 def rope(x, cs):
     # x: [B, H, T, D] (query and key heads concatenated along H), rotate-half convention
-    cos, sin = cs
+    cos, sin = cs[0], cs[1]
     d = x.shape[-1]
     xf = x.float()
     x1, x2 = xf[..., : d // 2], xf[..., d // 2:]
@@ -91,9 +98,48 @@ class TPDecoderLayer(torch.nn.Module):
         self.down = lin(h, inter, "row")
         self.n1 = torch.ones(h, device="cuda", dtype=torch.bfloat16)
         self.n2 = torch.ones(h, device="cuda", dtype=torch.bfloat16)
+        self.act = qc.activations_config.elem_dtype if qc.activations_config.block_size == 32 else None
+        self.qkv = self.gate_up = None
+        if GLUE:  # q/k/v and gate/up read the same activation: one launch each on row-stacked weights the three / two layers alias
+            from torchmx_b200.layers.mx_llama_attention import _fuse_linears
+            self.qkv = _fuse_linears([self.q, self.k, self.v])
+            self.gate_up = _fuse_linears([self.gate, self.up])
 
-    def forward(self, x, pos, kc, vc, cache_len, cs):
-        # x: [B, T, hidden] replicated; kc/vc: [B, nkv_local, S, hd] this rank's KV cache; tokens are written at pos
+    def forward(self, x, res, pos, kc, vc, cache_len, cs):
+        """hidden state of the layer = x + res (res None for the first layer); returns (down-projection output, residual stream)
+        -- the add is folded into the next RMSNorm launch.  x: [B, T, hidden] replicated; kc / vc: [B, nkv_local, S, hd] this
+        rank's KV cache; tokens are written at pos."""
+        if not GLUE or self.qkv is None or self.gate_up is None or self.act is None:
+            return self.forward_plain(x if res is None else x + res, pos, kc, vc, cache_len, cs), None
+        from torchmx_b200 import glue_ops, mlp_ops, mx_gemm
+        B, T, _ = x.shape
+        to_mx = None if (self.act.name == "float8_e4m3" and B * T <= mx_gemm.FUSED_ACT_MAX_ROWS) else self.act  # decode: quantized inside the GEMM
+        r = glue_ops.rmsnorm(x, self.n1, 1e-5, residual=res, to_mx=to_mx, want_y=to_mx is None)
+        assert r is not None, "the RMSNorm kernel declined a [B, T, hidden] bf16 activation"
+        y, y_mx, h = r
+        h = x if res is None else h
+        q, k, v = self.qkv(y if to_mx is None else y_mx).split(self.qkv._split, dim=-1)
+        q = q.view(B, T, self.nh_local, self.hd).transpose(1, 2)
+        k = k.view(B, T, self.nkv_local, self.hd).transpose(1, 2)
+        v = v.view(B, T, self.nkv_local, self.hd).transpose(1, 2)
+        r = glue_ops.rope(q, k, cs[2], cs[3])
+        assert r is not None, "the rotary kernel declined the projection output"
+        q, k = r
+        kc.index_copy_(2, pos, k)
+        vc.index_copy_(2, pos, v)
+        if T > 1:  # prefill from an empty cache: causal attention over the new tokens
+            a = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True)
+        else:      # decode: attend to the first cache_len + 1 cache positions
+            a = F.scaled_dot_product_attention(q, kc[:, :, : cache_len + 1], vc[:, :, : cache_len + 1], enable_gqa=True)
+        o = self.o(a.transpose(1, 2).reshape(B, T, self.nh_local * self.hd))
+        r = glue_ops.rmsnorm(o, self.n2, 1e-5, residual=h, to_mx=to_mx, want_y=to_mx is None)
+        assert r is not None
+        y, y_mx, h = r
+        gate, up = self.gate_up(y if to_mx is None else y_mx).split(self.gate_up._split, dim=-1)
+        act = mlp_ops.silu_mul_to_mx(gate, up, self.act, 32)
+        return self.down(act if act is not None else F.silu(gate) * up), h
+
+    def forward_plain(self, x, pos, kc, vc, cache_len, cs):
         B, T, _ = x.shape
         y = self.q.prepare_input(rms_norm(x, self.n1))  # one activation quantization for q / k / v (prefill); bf16 for decode
         q = self.q(y).view(B, T, self.nh_local, self.hd).transpose(1, 2)
@@ -103,9 +149,9 @@ class TPDecoderLayer(torch.nn.Module):
         q, k = qk[:, : self.nh_local], qk[:, self.nh_local:]
         kc.index_copy_(2, pos, k)
         vc.index_copy_(2, pos, v)
-        if T > 1:  # prefill from an empty cache: causal attention over the new tokens
+        if T > 1:
             a = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True)
-        else:      # decode: attend to the first cache_len + 1 cache positions
+        else:
             a = F.scaled_dot_product_attention(q, kc[:, :, : cache_len + 1], vc[:, :, : cache_len + 1], enable_gqa=True)
         x = x + self.o(a.transpose(1, 2).reshape(B, T, self.nh_local * self.hd))
         y = self.gate.prepare_input(rms_norm(x, self.n2))
@@ -143,6 +189,8 @@ def time_graph(fn, iters, warmup=2):
 def run_infer(args, world, rank):
     import torchmx_b200  # noqa: F401
     from torchmx_b200.config import MXConfig, QLinearConfig
+    global GLUE
+    GLUE = not getattr(args, "no_glue", False)
     cfg = dict(SHAPES[args.model])
     if args.layers:
         cfg["layers"] = args.layers
@@ -163,16 +211,17 @@ def run_infer(args, world, rank):
         if pool is None:
             l.o._fused_pool = l.down._fused_pool = None
     gen = torch.Generator(device="cuda").manual_seed(5)
-    res = {"mode": "infer", "fused_allreduce": bool(args.fused and world > 1), "model": args.model, "layers": cfg["layers"], "world": world, "weights": args.wdtype, "activations": args.adtype,
+    res = {"mode": "infer", "glue_kernels": GLUE, "fused_allreduce": bool(args.fused and world > 1), "model": args.model, "layers": cfg["layers"], "world": world, "weights": args.wdtype, "activations": args.adtype,
            "build_s": round(build_s, 2), "weight_GB_per_rank": round(torch.cuda.memory_allocated() / 1e9, 2)}
 
     def stack(x, pos, caches, cache_len):
         if pool is not None and layers[0].o._fused_pool is not None:
             pool.reset()
         cs = rope_tables(pos, layers[0].hd)
+        res = None
         for l, (kc, vc) in zip(layers, caches):
-            x = l(x, pos, kc, vc, cache_len, cs)
-        return x
+            x, res = l(x, res, pos, kc, vc, cache_len, cs)
+        return x if res is None else x + res
 
     def make_caches(B, S):
         return [(torch.zeros(B, l.nkv_local, S, l.hd, device="cuda", dtype=torch.bfloat16), torch.zeros(B, l.nkv_local, S, l.hd, device="cuda", dtype=torch.bfloat16))
@@ -219,8 +268,10 @@ def run_infer(args, world, rank):
         xr = x.clone()
         c1 = [(torch.zeros(1, l.nkv_local, P, l.hd, device="cuda", dtype=torch.bfloat16), torch.zeros(1, l.nkv_local, P, l.hd, device="cuda", dtype=torch.bfloat16))
               for l in ref_layers]
+        rr = None
         for l, (kc, vc) in zip(ref_layers, c1):
-            xr = l(xr, pos, kc, vc, 0, rope_tables(pos, l.hd))
+            xr, rr = l(xr, rr, pos, kc, vc, 0, rope_tables(pos, l.hd))
+        xr = xr if rr is None else xr + rr
         c2 = make_caches(1, P)
         xt = stack(x, pos, c2, 0).clone()
         if pool is not None:
@@ -310,7 +361,7 @@ def run_quantize(args, world, rank):
 def default_args(**kw):
     """argparse defaults as a namespace (bench.py calls run_infer / run_quantize in-process on its own process group)"""
     base = dict(mode="infer", model="70b", layers=None, prefill=2048, batch=32, ctx=128, iters=5, wdtype="float4_e2m1", adtype="float8_e4m3",
-                check=False, fused_max_rows=128, fused=False, also_fused=False)
+                check=False, fused_max_rows=128, fused=False, also_fused=False, no_glue=False)
     base.update(kw)
     return argparse.Namespace(**base)
 
@@ -328,6 +379,7 @@ def main():
     ap.add_argument("--adtype", default="float8_e4m3")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--fused-max-rows", type=int, default=128, help="fused all-reduce for at most this many tokens, NCCL above")
+    ap.add_argument("--no-glue", action="store_true", help="plain PyTorch RMSNorm / rotary / SiLU between the projections, one launch per projection")
     ap.add_argument("--fused", action="store_true", help="row-parallel layers reduce in the GEMM epilogue (NVLink multicast) instead of NCCL")
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -50,8 +50,9 @@ struct Smem {
     static constexpr int OFF_SFV = OFF_SFK + K_STAGES * 1024;
     static constexpr int OFF_SFP = OFF_SFV + V_STAGES * 512;
     static constexpr int OFF_BAR = OFF_SFP + 2 * 512;
-    // q_full, qsf_full, k_full/ksf_full/k_empty[K_STAGES], v_full/vsf_full/v_empty[V_STAGES], s_full/s_free/p_full/p_free/o_full[2]
-    static constexpr int NUM_BARS = 2 + 3 * K_STAGES + 3 * V_STAGES + 10;
+    // q_full, qsf_full, k_full/ksf_full/k_empty[K_STAGES], v_full/vsf_full/v_empty[V_STAGES], sa_full/sa_free[2][2],
+    // sc_full/sc_free/p_full/p_free/o_full[2]
+    static constexpr int NUM_BARS = 2 + 3 * K_STAGES + 3 * V_STAGES + 18;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM_PTR + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
@@ -111,13 +112,6 @@ __device__ __forceinline__ void container_bytes(const uint32_t (&out)[(ELEM == M
     }
 }
 
-// K4a's order of adding the per-block sums of a row, fed one block at a time in block order
-struct RowSum {
-    float acc, a0, a1, a2, a3;
-    int n;  // blocks seen
-    __device__ __forceinline__ void init() { acc = 0.0f; a0 = a1 = a2 = a3 = 0.0f; n = 0; }
-};
-
 template <int ELEM>
 __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                                                                          const __grid_constant__ CUtensorMap map_v, const Params p) {
@@ -132,9 +126,11 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     uint64_t* v_full = k_empty + K_STAGES;
     uint64_t* vsf_full = v_full + V_STAGES;
     uint64_t* v_empty = vsf_full + V_STAGES;
-    uint64_t* s_full = v_empty + V_STAGES;         // [wg] score tile complete (count 1, commit)
-    uint64_t* s_free = s_full + 2;                 // [wg] score tile read into registers (count 128)
-    uint64_t* p_full = s_free + 2;                 // [wg] codes + scales of a chunk of P in shared memory (count 128)
+    uint64_t* sa_full = v_empty + V_STAGES;        // [wg][buf] passes A, B: score tile complete (count 1, commit)
+    uint64_t* sa_free = sa_full + 4;               // [wg][buf] passes A, B: score tile read into registers (count 128)
+    uint64_t* sc_full = sa_free + 4;               // [wg] pass C: score tile complete (count 1, commit)
+    uint64_t* sc_free = sc_full + 2;               // [wg] pass C: score tile read into registers (count 128)
+    uint64_t* p_full = sc_free + 2;                // [wg] codes + scales of a chunk of P in shared memory (count 128)
     uint64_t* p_free = p_full + 2;                 // [wg] MMAs reading them retired (count 1, commit)
     uint64_t* o_full = p_free + 2;                 // [wg] output accumulator complete (count 1, commit)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::OFF_TMEM_PTR);
@@ -167,8 +163,9 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         mbar_init(qsf_full, 1);
         for (int i = 0; i < K_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&ksf_full[i], 1); mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < V_STAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&vsf_full[i], 1); mbar_init(&v_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&sa_full[i], 1); mbar_init(&sa_free[i], QT); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], QT); mbar_init(&p_full[i], QT); mbar_init(&p_free[i], 1); mbar_init(&o_full[i], 1);
+            mbar_init(&sc_full[i], 1); mbar_init(&sc_free[i], QT); mbar_init(&p_full[i], QT); mbar_init(&p_free[i], 1); mbar_init(&o_full[i], 1);
         }
         fence_barrier_init();
     }
@@ -196,82 +193,153 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         uint8_t* dump_scales = (p.p_codes != nullptr && row_live) ? p.p_scales + ((int64_t)bh * p.q_len + q) * tpr : nullptr;
 
         float row_max = -INFINITY, row_sum = 0.0f;
-        uint32_t s_par = 0, pfree_par = 0;
-        for (int pass = 0; pass < 3 && active[wg]; ++pass) {
-            RowSum rs;
-            rs.init();
-            bool have_acc = false;
+        // passes A and B keep TWO 64-column score tiles per warpgroup inside its (still unused) output accumulator, so the tensor
+        // core works one tile ahead of the softmax threads; pass C has the accumulator in use and a single tile
+        const uint32_t tm_sa = tm_lane + TM_O + wg * 128, tm_sc = tm_lane + TM_S + wg * 64;
+        uint32_t ab_item = 0, c_par = 0, pfree_par = 0;
+        auto take_tile = [&](uint32_t taddr, uint64_t* full, uint32_t parity, uint64_t* free_bar, uint32_t (&v)[64]) {
+            mbar_wait(full, parity);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32b_x32(taddr, v0);
+            tmem_ld_32x32b_x32(taddr + 32, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = v0[i]; v[32 + i] = v1[i]; }
+            tc_fence_before();
+            mbar_arrive(free_bar);  // the tensor core may overwrite the tile while we compute
+        };
+        auto take_ab = [&](uint32_t (&v)[64]) {
+            const uint32_t buf = ab_item & 1;
+            take_tile(tm_sa + buf * 64, &sa_full[wg * 2 + buf], (ab_item >> 1) & 1, &sa_free[wg * 2 + buf], v);
+            ++ab_item;
+        };
+        auto visible = [&](int t) {  // how many of block t's 32 keys this query row may see
+            int vis = row_live ? 32 : 0;
+            if (p.causal && row_live) vis = min(32, max(0, q + p.causal_offset + 1 - t * 32));
+            return vis;
+        };
+        // the 32 scores of a block as the softmax sees them: bf16 matmul result, * scaling, + mask, causal rule (mxq_softmax_core.cuh)
+        auto scores_of = [&](const uint32_t* raw, int t, int vis, float (&x)[32]) {
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]));
+            sm::scale_round(w, p.scaling, x);
+            if (mrow != nullptr) {
+                uint32_t mw[16];
+                sm::load_mask(mrow + t * 32, p.mask_vec != 0, mw);
+                sm::add_mask(x, mw);
+            }
+            if (vis < 32) sm::hide_from(x, vis);
+        };
+        if (active[wg]) {
+            // ---- pass A: row maximum.  Without an additive mask the map score -> bf16(bf16(score) * scaling) is monotone
+            // (scaling > 0), so the maximum of the mapped scores is the map of the maximum raw score: one max per element.
+            const bool fast_max = p.mask == nullptr && p.scaling > 0.0f;
+            float raw_max = -INFINITY;
+            for (int j = 0; j < my_n; ++j) {
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[64];
+                    take_ab(v);
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const int t = 4 * j + 2 * hf + blk;
+                        const int vis = visible(t);
+                        if (vis == 0) continue;
+                        if (fast_max) {
+                            float m = -INFINITY;
+                            if (vis == 32) {
+                                m = __uint_as_float(v[32 * blk]);
+#pragma unroll
+                                for (int i = 1; i < 31; i += 2) m = sm::max_nan3(m, __uint_as_float(v[32 * blk + i]), __uint_as_float(v[32 * blk + i + 1]));
+                                m = sm::max_nan(m, __uint_as_float(v[32 * blk + 31]));
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) m = sm::max_nan(m, i < vis ? __uint_as_float(v[32 * blk + i]) : -INFINITY);
+                            }
+                            raw_max = sm::max_nan(raw_max, m);
+                        } else {
+                            float x[32];
+                            scores_of(&v[32 * blk], t, vis, x);
+                            row_max = sm::max_nan(row_max, sm::block_max_only(x));
+                        }
+                    }
+                }
+            }
+            if (fast_max) {
+                const uint32_t r1 = pack_bf16x2(raw_max, 0.0f);
+                const uint32_t r2 = pack_bf16x2(__uint_as_float(r1 << 16) * p.scaling, 0.0f);
+                row_max = __uint_as_float(r2 << 16);
+            }
+            // ---- pass B: row sum of expf(x - max), the per-block sums added in K4a's order (sm::sum_layout): blocks in order, or
+            // butterfly-reduced groups of 8 added in order
+            {
+                float acc = 0.0f, a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                bool have_acc = false;
+                for (int j = 0; j < my_n; ++j) {
+#pragma unroll 1
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t v[64];
+                        take_ab(v);
+#pragma unroll
+                        for (int blk = 0; blk < 2; ++blk) {
+                            const int t = 4 * j + 2 * hf + blk;
+                            const int vis = visible(t);
+                            float s = 0.0f;
+                            if (vis > 0) {
+                                float x[32];
+                                scores_of(&v[32 * blk], t, vis, x);
+                                if (!sm::block_dead(vis, sm::block_max_only(x), row_max)) s = sm::exp_sum(x, row_max);
+                            }
+                            if (p.layout == 0) {
+                                acc = acc + s;
+                            } else {
+                                const int k8 = t & 7;
+                                if (k8 == 0) a0 = s;
+                                else if (k8 == 1) a1 = s;
+                                else if (k8 == 2) a2 = s;
+                                else if (k8 == 3) a3 = s;
+                                else if (k8 == 4) a0 = a0 + s;
+                                else if (k8 == 5) a1 = a1 + s;
+                                else if (k8 == 6) a2 = a2 + s;
+                                else {
+                                    const float g = (a0 + a2) + (a1 + (a3 + s));
+                                    acc = have_acc ? acc + g : g;
+                                    have_acc = true;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (p.layout != 0 && ((4 * my_n) & 7) != 0) {  // a half-filled last group (the rest of it: hidden blocks, sum 0)
+                    const float g = ((a0 + 0.0f) + (a2 + 0.0f)) + ((a1 + 0.0f) + (a3 + 0.0f));
+                    acc = have_acc ? acc + g : g;
+                }
+                row_sum = acc;
+            }
+            // ---- pass C: the codes and scales of P, into the operand tile of the second contraction
             uint32_t sf_word = 0;
             for (int j = 0; j < my_n; ++j) {
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
-                    mbar_wait(&s_full[wg], s_par);
-                    s_par ^= 1;
-                    tc_fence_after();
                     uint32_t v[64];
-                    {
-                        uint32_t v0[32], v1[32];
-                        tmem_ld_32x32b_x32(tm_lane + TM_S + wg * 64, v0);
-                        tmem_ld_32x32b_x32(tm_lane + TM_S + wg * 64 + 32, v1);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) { v[i] = v0[i]; v[32 + i] = v1[i]; }
-                    }
-                    tc_fence_before();
-                    mbar_arrive(&s_free[wg]);  // the tensor core may overwrite the tile with the next one while we compute
+                    take_tile(tm_sc, &sc_full[wg], c_par, &sc_free[wg], v);
+                    c_par ^= 1;
 #pragma unroll
                     for (int blk = 0; blk < 2; ++blk) {
                         const int bl = 2 * hf + blk;   // block inside the chunk
                         const int t = 4 * j + bl;      // block inside the row
-                        int vis = row_live ? 32 : 0;
-                        if (p.causal && row_live) vis = min(32, max(0, q + p.causal_offset + 1 - t * 32));
+                        const int vis = visible(t);
                         float x[32];
                         float m = -INFINITY, lo = INFINITY;
                         if (vis > 0) {
-                            uint32_t w[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)  // the matmul result is a bf16 tensor
-                                w[i] = pack_bf16x2(__uint_as_float(v[32 * blk + 2 * i]), __uint_as_float(v[32 * blk + 2 * i + 1]));
-                            sm::scale_round(w, p.scaling, x);
-                            if (mrow != nullptr) {
-                                uint32_t mw[16];
-                                sm::load_mask(mrow + t * 32, p.mask_vec != 0, mw);
-                                sm::add_mask(x, mw);
-                            }
-                            if (vis < 32) sm::hide_from(x, vis);
+                            scores_of(&v[32 * blk], t, vis, x);
                             sm::block_max(x, m, lo);
                         }
-                        if (pass == 0) {
-                            row_max = sm::max_nan(row_max, m);
-                            continue;
-                        }
-                        const bool dead = sm::block_dead(vis, m, row_max);
-                        if (pass == 1) {
-                            const float s = dead ? 0.0f : sm::exp_sum(x, row_max);
-                            // K4a's order (sm::sum_layout): blocks in order, or butterfly-reduced groups of 8 added in order
-                            if (p.layout == 0) {
-                                rs.acc = rs.acc + s;
-                            } else {
-                                const int k8 = t & 7;
-                                if (k8 == 0) rs.a0 = s;
-                                else if (k8 == 1) rs.a1 = s;
-                                else if (k8 == 2) rs.a2 = s;
-                                else if (k8 == 3) rs.a3 = s;
-                                else if (k8 == 4) rs.a0 = rs.a0 + s;
-                                else if (k8 == 5) rs.a1 = rs.a1 + s;
-                                else if (k8 == 6) rs.a2 = rs.a2 + s;
-                                else {
-                                    const float g = (rs.a0 + rs.a2) + (rs.a1 + (rs.a3 + s));
-                                    rs.acc = have_acc ? rs.acc + g : g;
-                                    have_acc = true;
-                                }
-                            }
-                            continue;
-                        }
-                        // ---- pass C: the codes of this block of P ----
                         uint32_t c[8];
                         int sc;
-                        if (dead) {
+                        if (sm::block_dead(vis, m, row_max)) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) c[i] = 0;
                             sc = row_live ? sm::dead_block_scale<ELEM>(row_max, row_sum) : 127;
@@ -313,13 +381,6 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                         }
                     }
                 }
-            }
-            if (pass == 1) {
-                if (p.layout != 0 && ((4 * my_n) & 7) != 0) {  // a half-filled last group (the rest of it: hidden blocks, sum 0)
-                    const float g = ((rs.a0 + 0.0f) + (rs.a2 + 0.0f)) + ((rs.a1 + 0.0f) + (rs.a3 + 0.0f));
-                    rs.acc = have_acc ? rs.acc + g : g;
-                }
-                row_sum = rs.acc;
             }
         }
         if (active[wg]) {
@@ -379,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     } else if (warp == 9) {
         // ================= MMA issuer =================
         uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
-        uint32_t sfree_par[2] = {0, 0}, pfull_par[2] = {0, 0};
+        uint32_t pfull_par[2] = {0, 0};
         const uint32_t q_addr = smem_u32(smem + Smem::OFF_Q), k_addr0 = smem_u32(smem + Smem::OFF_K), v_addr0 = smem_u32(smem + Smem::OFF_V);
         const uint32_t p_addr = smem_u32(smem + Smem::OFF_P);
         mbar_wait(q_full, 0);
@@ -422,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             __syncwarp();
             if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
         };
+        uint32_t ab_item[2] = {0, 0}, cfree_par[2] = {0, 0};
         for (int pass = 0; pass < 3; ++pass) {
             for (int j = 0; j < n_cta; ++j) {
                 mbar_wait(&k_full[ks], kph);
@@ -438,18 +500,29 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
 #pragma unroll
                     for (int wg = 0; wg < 2; ++wg) {
                         if (!active[wg] || j >= nv[wg]) continue;
-                        mbar_wait(&s_free[wg], sfree_par[wg] ^ 1);
-                        sfree_par[wg] ^= 1;
+                        uint32_t tm_s;
+                        uint64_t* full_bar;
+                        if (pass < 2) {  // two tiles per warpgroup inside its output accumulator: run one tile ahead of the softmax threads
+                            const uint32_t buf = ab_item[wg] & 1;
+                            mbar_wait(&sa_free[wg * 2 + buf], ((ab_item[wg] >> 1) & 1) ^ 1);
+                            ++ab_item[wg];
+                            tm_s = tmem_base + TM_O + wg * 128 + buf * 64;
+                            full_bar = &sa_full[wg * 2 + buf];
+                        } else {
+                            mbar_wait(&sc_free[wg], cfree_par[wg] ^ 1);
+                            cfree_par[wg] ^= 1;
+                            tm_s = tmem_base + TM_S + wg * 64;
+                            full_bar = &sc_full[wg];
+                        }
                         tc_fence_after();
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < HD / UMMA_K; ++k) {
                                 const uint64_t da = smem_desc(q_addr + wg * TILE_BYTES + k * UMMA_K, 1024, kLayoutSw128);
                                 const uint64_t db = smem_desc(k_addr0 + ks * TILE_BYTES + hf * (64 * 128) + k * UMMA_K, 1024, kLayoutSw128);
-                                tc_mma_mx(tmem_base + TM_S + wg * 64, da, db, idesc_with_sf(p.idesc_qk, k, k), k != 0, tmem_base + TM_SFQ + 4 * wg,
-                                          tm_sfk + 4 * hf);
+                                tc_mma_mx(tm_s, da, db, idesc_with_sf(p.idesc_qk, k, k), k != 0, tmem_base + TM_SFQ + 4 * wg, tm_sfk + 4 * hf);
                             }
-                            tc_commit(&s_full[wg]);
+                            tc_commit(full_bar);
                         }
                         __syncwarp();
                     }
