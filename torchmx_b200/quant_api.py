@@ -34,32 +34,6 @@ def _swap_children(model: torch.nn.Module, replacement_fn: Callable, filter_fn: 
             _swap_children(child, replacement_fn, filter_fn, on_visit, fqn)
 
 
-def _reserve_output_arena(model: torch.nn.Module, qconfig: QLinearConfig, layer_filter) -> None:
-    """Whole-model quantization is bound by the host, and most of that by `cudaMalloc`: every early layer's codes need a fresh
-    segment from the driver (synchronous, ~1 ms per GB, one call per tensor) until enough bf16 source weights have been freed to
-    recycle.  Take the memory all codes + scales of this call will need from the driver ONCE and hand it to the caching allocator,
-    which then carves every output out of that segment (Llama-3-8B: 26 driver calls -> 1)."""
-    wc = qconfig.weights_config
-    per_elem = (0.5 if wc.elem_dtype_name == "float4_e2m1" else 1.0) + 1.0 / wc.block_size
-    need, dev = 0, None
-    for fqn, m in model.named_modules():
-        if type(m) is torch.nn.Linear and m.weight.device.type == "cuda" and (layer_filter is None or layer_filter(fqn)):
-            if dev is None:
-                dev = m.weight.device
-            if m.weight.device == dev:
-                need += int(m.weight.numel() * per_elem) + (4 << 20)  # (+ rounding of each tensor to the allocator's granularity)
-    if dev is None or need < (256 << 20) or torch.cuda.is_current_stream_capturing():
-        return
-    free, _ = torch.cuda.mem_get_info(dev)
-    cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-    if need > free or cached >= need:  # not enough room for a second copy of the outputs' worth, or the cache already holds enough
-        return
-    try:
-        torch.empty(need, dtype=torch.uint8, device=dev)  # freed at once: the segment stays in the caching allocator
-    except torch.cuda.OutOfMemoryError:
-        pass
-
-
 def quantize_linear_(model: torch.nn.Module, qconfig: QLinearConfig, layer_filter: Optional[Callable[[str], bool]] = None) -> None:
     """Replace every module whose type is exactly `torch.nn.Linear` (lm_head included) with
     `MXInferenceLinear.from_float(mod, qconfig)`, in place (reference: quant_api.py:188-215).
@@ -71,7 +45,6 @@ def quantize_linear_(model: torch.nn.Module, qconfig: QLinearConfig, layer_filte
     logger.warning("This method only replaces/quantizes the linear layers. Use this as an approximation as we do not "
                    "quantize QKV and other stuff. Use this only when a specific attention layer is not implemented.")
     logger.info(f"Quantizing Linear layers with config:\n{pformat(qconfig)}\n")
-    _reserve_output_arena(model, qconfig, layer_filter)
     try:
         from tqdm import tqdm
         bar = tqdm(desc="Quantizing linear layers in model...")
@@ -150,7 +123,6 @@ def quantize_llm_(model: torch.nn.Module, qattention_config: QAttentionConfig, q
         cls = table[type(mod)]
         return cls.from_float(mod, qattention_config if type(mod) in ATTENTION_LAYERS else qmlp_config)
 
-    _reserve_output_arena(model, qmlp_config, None)
     _swap_children(model, replacement_fn=replace, filter_fn=lambda mod, fqn: type(mod) in table)
     quantize_linear_(model, qmlp_config)
     if fuse_rmsnorm:
