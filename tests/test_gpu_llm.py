@@ -286,3 +286,35 @@ def test_left_padded_batch_with_sdpa_mask_has_no_nan(tiny_llama):
         both = qm(input_ids=ids, attention_mask=mask, position_ids=(mask.cumsum(-1) - 1).clamp(min=0)).logits
     assert not torch.isnan(both[1, pad:]).any()
     assert _sqnr(alone[0], both[1, pad:]) > 20, _sqnr(alone[0], both[1, pad:])
+
+
+def test_decode_under_sdpa_groups_query_heads_instead_of_repeating_kv(tiny_llama, monkeypatch):
+    """decode steps of a grouped-query model configured for sdpa: the block attends with the query heads of a key / value head
+    on the query-length axis (no repeat_kv copies of the cache); same logits as transformers' own sdpa path up to the
+    summation order of the attention kernel, and K1b feeds down_proj at decode sizes ([batch, 1, hidden] activations)"""
+    import copy
+    import torchmx  # noqa: F401
+    from torchmx import mlp_ops
+    from torchmx.config import MXConfig, QAttentionConfig, QLinearConfig
+    from torchmx.layers import mx_llama_attention as mla
+    from torchmx.quant_api import quantize_llm_
+    from transformers.cache_utils import StaticCache
+    model, cfg = tiny_llama
+    qm = copy.deepcopy(model)
+    qm.config._attn_implementation = "sdpa"
+    lin = QLinearConfig(weights_config=MXConfig("float6_e3m2", 32), activations_config=MXConfig("float8_e4m3", 32))
+    quantize_llm_(qm, QAttentionConfig(projection_config=lin), lin)
+    for layer in qm.model.layers:
+        layer.self_attn.config._attn_implementation = "sdpa"
+    ids = torch.randint(0, cfg.vocab_size, (3, 40), device=DEV)
+    outs = []
+    for grouped in (True, False):
+        monkeypatch.setattr(mla, "GROUPED_DECODE_SDPA", grouped)
+        cache = StaticCache(config=qm.config, max_cache_len=64)
+        n0 = mlp_ops.stats["fused_silu_mul"]
+        with torch.no_grad():
+            qm(input_ids=ids[:, :32], past_key_values=cache, use_cache=True)
+            steps = [qm(input_ids=ids[:, 32 + i:33 + i], past_key_values=cache, use_cache=True).logits for i in range(8)]
+        assert mlp_ops.stats["fused_silu_mul"] - n0 == 2 * 9  # prefill + 8 decode steps, two layers: gating + quantization in one launch
+        outs.append(torch.cat(steps, 1))
+    assert _sqnr(outs[1], outs[0]) > 35, _sqnr(outs[1], outs[0])

@@ -6,20 +6,25 @@ import torchmx_b200  # noqa
 from torchmx_b200 import dtypes
 from torchmx_b200.mx_tensor import MXTensor
 wdt = getattr(dtypes, os.environ.get("GT_W", "float6_e3m2"))
+FUSED = os.environ.get("GT_FUSED", "0") == "1"  # bf16 activation quantized inside the GEMM (what MXInferenceLinear does at decode sizes)
 M = int(os.environ.get("GT_M", "32"))
 for shape in os.environ.get("GT_SHAPES", "4096x4096,1024x4096,14336x4096,4096x14336").split(","):
     N, K = (int(v) for v in shape.split("x"))
     n_w = max(4, int(400e6 // (N * K)) + 1)
-    X = MXTensor.to_mx(torch.randn(M, K, device="cuda", dtype=torch.bfloat16), dtypes.float8_e4m3, 32)
+    xb = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    X = MXTensor.to_mx(xb, dtypes.float8_e4m3, 32)
+    from torchmx_b200 import mx_gemm
+    run = (lambda W: mx_gemm.linear_fused_act_quant(xb, W, None, False)) if FUSED else (lambda W: torch.nn.functional.linear(X, W))
     Ws = [MXTensor.to_mx(torch.randn(N, K, device="cuda", dtype=torch.bfloat16), wdt, 32) for _ in range(n_w)]
     for W in Ws:
-        torch.nn.functional.linear(X, W)
+        mx_gemm.mark_static(W)
+        run(W)
     torch.cuda.synchronize()
     g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
     with torch.cuda.stream(st):
         with torch.cuda.graph(g, stream=st):
             for W in Ws:
-                y = torch.nn.functional.linear(X, W)
+                y = run(W)
     ts = []
     for r in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -28,4 +33,4 @@ for shape in os.environ.get("GT_SHAPES", "4096x4096,1024x4096,14336x4096,4096x14
     us = min(ts[1:])
     bits = {"float4_e2m1": 4, "float6_e3m2": 6, "float6_e2m3": 6, "float8_e4m3": 8}[wdt.name]
     by = N * K * (bits / 8 + 1 / 32) + M * K * (1 + 1 / 32) + M * N * 2
-    print(f"M={M} N={N} K={K} W={wdt.name} ({n_w} distinct weights): {us:.1f} us per launch, {by/us/1e3:.0f} GB/s of packed operand bytes, {N*K/us/1e6:.2f} T weight elements/s", flush=True)
+    print(f"M={M} N={N} K={K} W={wdt.name} fused_act_quant={FUSED} ({n_w} distinct weights): {us:.1f} us per launch, {by/us/1e3:.0f} GB/s of packed operand bytes, {N*K/us/1e6:.2f} T weight elements/s", flush=True)

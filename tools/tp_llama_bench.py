@@ -111,9 +111,9 @@ class TPDecoderLayer(torch.nn.Module):
         rank's KV cache; tokens are written at pos."""
         if not GLUE or self.qkv is None or self.gate_up is None or self.act is None:
             return self.forward_plain(x if res is None else x + res, pos, kc, vc, cache_len, cs), None
-        from torchmx_b200 import glue_ops, mlp_ops, mx_gemm
+        from torchmx_b200 import glue_ops, mlp_ops
         B, T, _ = x.shape
-        to_mx = None if (self.act.name == "float8_e4m3" and B * T <= mx_gemm.FUSED_ACT_MAX_ROWS) else self.act  # decode: quantized inside the GEMM
+        to_mx = self.act  # (also at decode sizes: a GEMM fed codes streams packed weights faster than one that quantizes per CTA)
         r = glue_ops.rmsnorm(x, self.n1, 1e-5, residual=res, to_mx=to_mx, want_y=to_mx is None)
         assert r is not None, "the RMSNorm kernel declined a [B, T, hidden] bf16 activation"
         y, y_mx, h = r

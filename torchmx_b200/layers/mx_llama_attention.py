@@ -94,6 +94,7 @@ def _fuse_linears(mods) -> Optional[MXInferenceLinear]:
     return fused
 
 
+GROUPED_DECODE_SDPA = os.environ.get("MXQ_GROUPED_DECODE_SDPA", "1") != "0"  # decode under sdpa: no repeat_kv copies (see forward)
 STACKED_MAX_ROWS = 128  # measured on Llama-8B: decode 10.1 -> 9.8 ms/step stacked, but prefill 27.1 -> 29.3 ms (the column
 #                         slices of a stacked output make every following elementwise kernel and copy strided), so prefill keeps
 #                         one launch per projection
@@ -307,6 +308,19 @@ class _MXAttentionMixin:
             key_states, value_states = past_key_values.update(key_states, value_states, self.layer_idx)
         if self.qconfig.is_qkv_quantization_enabled:
             attn_output, attn_weights = self._mx_attention(query_states, key_states, value_states, attention_mask, self.scaling), None
+        elif (GROUPED_DECODE_SDPA and query_states.shape[2] == 1 and getattr(self.config, "_attn_implementation", "eager") == "sdpa" and not self.training
+              and self.num_key_value_groups > 1 and query_states.is_cuda and (attention_mask is None or attention_mask.dim() == 4)):
+            # Decode with grouped-query heads under the sdpa configuration.  transformers repeats K and V to the number of query
+            # heads whenever a mask is present (sdpa_attention_forward -> repeat_kv: two copies of the whole KV cache per layer and
+            # step, 82 us of a 245 us Llama-3-8B decoder layer at batch 32).  With ONE query position the query heads that share
+            # a key / value head can sit on the query-length axis instead -- the same dot products and the same softmax rows, and
+            # nothing is copied: q [b, h, 1, d] viewed as [b, h_kv, groups, d], the mask broadcast over the group rows.
+            b, h, _, d = query_states.shape
+            hk = key_states.shape[1]
+            mask = None if attention_mask is None else attention_mask[:, :, :, : key_states.shape[-2]]
+            out = nn.functional.scaled_dot_product_attention(query_states.reshape(b, hk, h // hk, d), key_states, value_states, attn_mask=mask,
+                                                             dropout_p=0.0, scale=self.scaling, is_causal=False)
+            attn_output, attn_weights = out.reshape(b, 1, h, d), None
         else:
             fn = mod_llama.eager_attention_forward
             impl = getattr(self.config, "_attn_implementation", "eager")

@@ -26,19 +26,22 @@ def set_fused_silu_mul(on: bool) -> bool:
 
 
 def _rows_view(t: torch.Tensor):
-    """[..., cols] with unit column stride and ONE row stride over all leading dims -> (row stride in elements) or None"""
+    """[..., cols] with unit column stride and ONE row stride over all leading dims (size-1 dims are free) -> row stride in
+    elements, or None"""
     cols = t.shape[-1]
     if t.stride(-1) != 1 and cols > 1:
         return None
-    if t.dim() == 1:
-        return cols
-    ld = t.stride(-2) if t.shape[-2] > 1 else cols
-    expect = ld * t.shape[-2]
-    for size, stride in zip(reversed(t.shape[:-2]), reversed(t.stride()[:-2])):
-        if size > 1 and stride != expect:
+    ld, expect = None, None
+    for size, stride in zip(reversed(t.shape[:-1]), reversed(t.stride()[:-1])):
+        if size == 1:
+            continue
+        if ld is None:
+            ld, expect = stride, stride * size
+        elif stride != expect:
             return None
-        expect *= size
-    return ld
+        else:
+            expect *= size
+    return cols if ld is None else ld
 
 
 def silu_mul_to_mx(gate: torch.Tensor, up: torch.Tensor, elem_dtype: dtypes.DType, block_size: int = 32) -> Optional[MXTensor]:

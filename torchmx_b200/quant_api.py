@@ -65,9 +65,11 @@ class FusedRMSNorm(torch.nn.Module):
     """Drop-in for the transformers `LlamaRMSNorm` / `Qwen2RMSNorm` module: same parameters, ONE launch (K5a, `glue_ops.rmsnorm`:
     fp32 statistics, the module's bf16 roundings) instead of the six elementwise / reduction launches of the eager module.
     When the only consumers of the output are MX linears of one activation config (`to_mx`, set by `quantize_llm_` for the two
-    norms of a decoder layer whose attention and MLP blocks are MX blocks) and the input is larger than the decode sizes at which
-    those layers quantize inside their GEMM, the same launch also quantizes: the module returns the MXTensor the layers would
-    have produced from its bf16 output (`MXTensor.to_mx` of it, bit for bit) and the bf16 tensor is never written.
+    norms of a decoder layer whose attention and MLP blocks are MX blocks) the same launch also quantizes: the module returns the
+    MXTensor the layers would have produced from its bf16 output (`MXTensor.to_mx` of it, bit for bit) and the bf16 tensor is never
+    written.  That holds at decode sizes too: a decode GEMM that quantizes its activation itself does so once per CTA (every CTA
+    needs the whole activation), which caps it at ~6 T weight elements/s; fed codes it streams 4 / 6-bit weights 15-30 % faster
+    (profiles/r2_decode_gemm_cold.txt).
     Not part of the reference; `quantize_llm_(..., fuse_rmsnorm=True)` opts in."""
 
     def __init__(self, weight: torch.nn.Parameter, eps: float, to_mx=None):
@@ -75,10 +77,9 @@ class FusedRMSNorm(torch.nn.Module):
         self.weight, self.variance_epsilon, self.to_mx = weight, eps, to_mx
 
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
-        from . import glue_ops, mx_gemm
+        from . import glue_ops
         if not torch.compiler.is_compiling():
-            rows = hidden_states.numel() // max(hidden_states.shape[-1], 1)
-            quant = self.to_mx is not None and not (mx_gemm._FUSED_ACT and self.to_mx.name == "float8_e4m3" and rows <= mx_gemm.FUSED_ACT_MAX_ROWS)
+            quant = self.to_mx is not None
             r = glue_ops.rmsnorm(hidden_states, self.weight, self.variance_epsilon, to_mx=self.to_mx if quant else None, want_y=not quant)
             if r is not None:
                 return r[1] if quant else r[0]
