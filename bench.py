@@ -492,7 +492,8 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "frac_of_8TBps": round(achieved / 8000.0, 4), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes("float8_e4m3", n_elems), "avg_launch_us": round(dom_launch_ms * 1e3, 2),
-                "traffic": ncu_traffic(dom), "share_of_step": round(fam_ms[dom] / (elapsed_ms / args.steps), 4)}
+                "traffic": ncu_traffic(dom), "traffic_source": "profiles/traffic.json (dram__bytes_read + dram__bytes_write of one ncu --set full capture; not re-measured in this run)",
+                "share_of_step": round(fam_ms[dom] / (elapsed_ms / args.steps), 4)}
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e_steps = max(1, min(args.steps, 5))
