@@ -49,10 +49,12 @@ struct Smem {
     static constexpr int OFF_SFK = OFF_SFQ + 2 * 512;             // per stage: two 512-byte chunks (keys 0..63, 64..127)
     static constexpr int OFF_SFV = OFF_SFK + K_STAGES * 1024;
     static constexpr int OFF_SFP = OFF_SFV + V_STAGES * 512;
-    static constexpr int OFF_BAR = OFF_SFP + 2 * 512;
+    static constexpr int OFF_CMAX = OFF_SFP + 2 * 512;            // [wg][chunk <= 64][row] bf16: largest score of the chunk, from pass A
+    static constexpr int OFF_LIVE = OFF_CMAX + 2 * 64 * 128 * 2;  // [wg][2] words: chunks with a row that still counts after the row maximum is known
+    static constexpr int OFF_BAR = OFF_LIVE + 16;
     // q_full, qsf_full, k_full/ksf_full/k_empty[K_STAGES], v_full/vsf_full/v_empty[V_STAGES], sa_full/sa_free[2][2],
     // sc_full/sc_free/p_full/p_free/o_full[2]
-    static constexpr int NUM_BARS = 2 + 3 * K_STAGES + 3 * V_STAGES + 18;
+    static constexpr int NUM_BARS = 2 + 3 * K_STAGES + 3 * V_STAGES + 18 + 2;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM_PTR + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
@@ -112,7 +114,7 @@ __device__ __forceinline__ void container_bytes(const uint32_t (&out)[(ELEM == M
     }
 }
 
-template <int ELEM>
+template <int ELEM, bool TABLE>
 __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                                                                          const __grid_constant__ CUtensorMap map_v, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -133,6 +135,8 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     uint64_t* p_full = sc_free + 2;                // [wg] codes + scales of a chunk of P in shared memory (count 128)
     uint64_t* p_free = p_full + 2;                 // [wg] MMAs reading them retired (count 1, commit)
     uint64_t* o_full = p_free + 2;                 // [wg] output accumulator complete (count 1, commit)
+    uint64_t* scan_done = o_full + 2;              // [wg] pass A finished, live-chunk words final (count 128)
+    uint32_t* live_words = reinterpret_cast<uint32_t*>(smem + Smem::OFF_LIVE);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::OFF_TMEM_PTR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -166,7 +170,9 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         for (int i = 0; i < 4; ++i) { mbar_init(&sa_full[i], 1); mbar_init(&sa_free[i], QT); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sc_full[i], 1); mbar_init(&sc_free[i], QT); mbar_init(&p_full[i], QT); mbar_init(&p_free[i], 1); mbar_init(&o_full[i], 1);
+            mbar_init(&scan_done[i], QT);
         }
+        for (int i = 0; i < 4; ++i) live_words[i] = 0;
         fence_barrier_init();
     }
     if (warp == 10) tmem_alloc<512>(tmem_ptr);
@@ -174,6 +180,23 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // With an explicit additive mask the kernel cannot know which key chunks a tile's rows see without looking.  Pass A looks at
+    // everything anyway; it leaves the largest score of every (row, chunk) behind, and once a row's maximum is final a chunk whose
+    // largest score lies more than 110 below it is +0 in every probability (sm::block_dead).  Chunks that are dead for all 128
+    // rows of a warpgroup are skipped by passes B and C -- by the softmax threads, the tensor core and the loaders alike.
+    constexpr bool use_table = TABLE;  // (launched with TABLE == (mask != nullptr): the implied-causal path carries none of this)
+    auto live_chunks = [&](uint64_t (&live)[2]) {  // (callers other than the softmax threads: waits for pass A of both warpgroups)
+#pragma unroll
+        for (int wg = 0; wg < 2; ++wg) {
+            if (!active[wg]) { live[wg] = 0; continue; }
+            if (use_table) {
+                mbar_wait(&scan_done[wg], 0);
+                live[wg] = (uint64_t)live_words[2 * wg] | ((uint64_t)live_words[2 * wg + 1] << 32);
+            } else {
+                live[wg] = nv[wg] >= 64 ? ~0ull : ((1ull << nv[wg]) - 1);
+            }
+        }
+    };
 
     if (warp < 8) {
         // ================= softmax warpgroups =================
@@ -183,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         const bool row_live = active[wg] && q < p.q_len;
         const int my_n = nv[wg];
         const uint32_t tm_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const uint16_t* mrow = (p.mask != nullptr && row_live) ? p.mask + (int64_t)b * p.mask_sb + (int64_t)h * p.mask_sh + (int64_t)q * p.mask_sq : nullptr;
+        const uint16_t* mrow = (TABLE && p.mask != nullptr && row_live) ? p.mask + (int64_t)b * p.mask_sb + (int64_t)h * p.mask_sh + (int64_t)q * p.mask_sq : nullptr;
         const int tpr = p.kv_len / 32;
         const bool hw_exact = (p.flags & MXQ_FLAG_HW_EXACT) != 0;
         uint8_t* p_tile = smem + Smem::OFF_P + wg * TILE_BYTES + r * 128;
@@ -235,8 +258,9 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         if (active[wg]) {
             // ---- pass A: row maximum.  Without an additive mask the map score -> bf16(bf16(score) * scaling) is monotone
             // (scaling > 0), so the maximum of the mapped scores is the map of the maximum raw score: one max per element.
-            const bool fast_max = p.mask == nullptr && p.scaling > 0.0f;
-            float raw_max = -INFINITY;
+            const bool fast_max = !TABLE && p.scaling > 0.0f;
+            float raw_max = -INFINITY, chunk_max = -INFINITY;
+            uint16_t* cmax = reinterpret_cast<uint16_t*>(smem + Smem::OFF_CMAX) + wg * 64 * 128 + r;
             for (int j = 0; j < my_n; ++j) {
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
@@ -262,8 +286,14 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                         } else {
                             float x[32];
                             scores_of(&v[32 * blk], t, vis, x);
-                            row_max = sm::max_nan(row_max, sm::block_max_only(x));
+                            const float m = sm::block_max_only(x);
+                            row_max = sm::max_nan(row_max, m);
+                            chunk_max = sm::max_nan(chunk_max, m);
                         }
+                    }
+                    if (use_table && hf == 1) {
+                        cmax[j * 128] = (uint16_t)pack_bf16x2(chunk_max, 0.0f);  // (the scores are bf16 values: exact)
+                        chunk_max = -INFINITY;
                     }
                 }
             }
@@ -272,12 +302,49 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                 const uint32_t r2 = pack_bf16x2(__uint_as_float(r1 << 16) * p.scaling, 0.0f);
                 row_max = __uint_as_float(r2 << 16);
             }
+            uint64_t my_live = my_n >= 64 ? ~0ull : ((1ull << my_n) - 1);
+            if (use_table) {
+                for (int j = 0; j < my_n; ++j) {
+                    const float cm = __uint_as_float((uint32_t)cmax[j * 128] << 16);
+                    const bool counts = row_live && !(cm - row_max < -110.0f);
+                    const unsigned any = __ballot_sync(0xFFFFFFFFu, counts);
+                    if (lane == 0 && any) atomicOr(&live_words[2 * wg + (j >> 5)], 1u << (j & 31));
+                }
+                if (r == 0) atomicOr(&live_words[2 * wg], 1u);  // (a warpgroup always walks its first chunk: the output accumulator gets written)
+                mbar_arrive(&scan_done[wg]);
+                mbar_wait(&scan_done[wg], 0);
+                my_live = (uint64_t)live_words[2 * wg] | ((uint64_t)live_words[2 * wg + 1] << 32);
+            }
             // ---- pass B: row sum of expf(x - max), the per-block sums added in K4a's order (sm::sum_layout): blocks in order, or
             // butterfly-reduced groups of 8 added in order
             {
                 float acc = 0.0f, a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
                 bool have_acc = false;
+                auto add_block = [&](int t, float s) {
+                    if (p.layout == 0) {
+                        acc = acc + s;
+                    } else {
+                        const int k8 = t & 7;
+                        if (k8 == 0) a0 = s;
+                        else if (k8 == 1) a1 = s;
+                        else if (k8 == 2) a2 = s;
+                        else if (k8 == 3) a3 = s;
+                        else if (k8 == 4) a0 = a0 + s;
+                        else if (k8 == 5) a1 = a1 + s;
+                        else if (k8 == 6) a2 = a2 + s;
+                        else {
+                            const float g = (a0 + a2) + (a1 + (a3 + s));
+                            acc = have_acc ? acc + g : g;
+                            have_acc = true;
+                        }
+                    }
+                };
                 for (int j = 0; j < my_n; ++j) {
+                    if (!((my_live >> j) & 1)) {  // every block of the chunk sums to +0 for every row of the warpgroup
+#pragma unroll
+                        for (int bl = 0; bl < 4; ++bl) add_block(4 * j + bl, 0.0f);
+                        continue;
+                    }
 #pragma unroll 1
                     for (int hf = 0; hf < 2; ++hf) {
                         uint32_t v[64];
@@ -292,23 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                                 scores_of(&v[32 * blk], t, vis, x);
                                 if (!sm::block_dead(vis, sm::block_max_only(x), row_max)) s = sm::exp_sum(x, row_max);
                             }
-                            if (p.layout == 0) {
-                                acc = acc + s;
-                            } else {
-                                const int k8 = t & 7;
-                                if (k8 == 0) a0 = s;
-                                else if (k8 == 1) a1 = s;
-                                else if (k8 == 2) a2 = s;
-                                else if (k8 == 3) a3 = s;
-                                else if (k8 == 4) a0 = a0 + s;
-                                else if (k8 == 5) a1 = a1 + s;
-                                else if (k8 == 6) a2 = a2 + s;
-                                else {
-                                    const float g = (a0 + a2) + (a1 + (a3 + s));
-                                    acc = have_acc ? acc + g : g;
-                                    have_acc = true;
-                                }
-                            }
+                            add_block(t, s);
                         }
                     }
                 }
@@ -320,7 +371,19 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             }
             // ---- pass C: the codes and scales of P, into the operand tile of the second contraction
             uint32_t sf_word = 0;
+            bool p_started = false;
             for (int j = 0; j < my_n; ++j) {
+                if (!((my_live >> j) & 1)) {  // +0 codes for the whole chunk: nothing for the tensor core to add
+                    if (dump_codes != nullptr) {
+                        const int sc = sm::dead_block_scale<ELEM>(row_max, row_sum);
+                        for (int t = 4 * j; t < 4 * j + 4; ++t) {
+                            if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(0, 0, 0, 0);
+                            else { *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(0, 0, 0, 0); }
+                            dump_scales[t] = (uint8_t)sc;
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[64];
@@ -365,10 +428,11 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                         if (dump_scales != nullptr) dump_scales[t] = (uint8_t)sc;
                         if (bl == 0) {
                             sf_word = 0;
-                            if (j > 0) {  // the tensor core must be done with the previous chunk's codes before they are overwritten
+                            if (p_started) {  // the tensor core must be done with the previous chunk's codes before they are overwritten
                                 mbar_wait(&p_free[wg], pfree_par);
                                 pfree_par ^= 1;
                             }
+                            p_started = true;
                         }
                         sf_word |= (uint32_t)sc << (8 * bl);
                         // K-major 128B-swizzled operand tile: 16-byte chunk cc of row r lives at chunk cc ^ (r & 7)
@@ -423,8 +487,15 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             tma_load_3d(&map_q, q_full, smem + Smem::OFF_Q, 0, qt * 2 * QT, bh);  // rows past q_len read as zero
             if (active[1]) tma_load_3d(&map_q, q_full, smem + Smem::OFF_Q + TILE_BYTES, 0, qt * 2 * QT + QT, bh);
             uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
-            for (int pass = 0; pass < 3; ++pass)
+            uint64_t need = ~0ull;
+            for (int pass = 0; pass < 3; ++pass) {
+                if (pass == 1) {
+                    uint64_t live[2];
+                    live_chunks(live);
+                    need = live[0] | live[1];
+                }
                 for (int j = 0; j < n_cta; ++j) {
+                    if (!((need >> j) & 1)) continue;
                     mbar_wait(&k_empty[ks], kph ^ 1);
                     mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
                     tma_load_3d(&map_k, &k_full[ks], smem + Smem::OFF_K + ks * TILE_BYTES, 0, j * KC, bhk);
@@ -436,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                         if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
                     }
                 }
+            }
         }
     } else if (warp == 9) {
         // ================= MMA issuer =================
@@ -452,16 +524,20 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         }
         __syncwarp();
         // O[wg] += P[wg] (chunk jj) x V (chunk jj)
+        uint64_t live[2] = {~0ull, ~0ull};
+        int last_live[2] = {-1, -1};
+        bool o_started[2] = {false, false};
+        uint32_t kcnt = 0, vcnt = 0;
         auto pv = [&](int jj) {
             mbar_wait(&v_full[vs], vph);
             mbar_wait(&vsf_full[vs], vph);
             tc_fence_after();
-            const uint32_t tm_sfv = tmem_base + TM_SFV + 4 * (jj & 1);
+            const uint32_t tm_sfv = tmem_base + TM_SFV + 4 * (vcnt++ & 1);
             if (elect_one()) tc_copy_sf(tm_sfv, smem_desc(smem_u32(smem + Smem::OFF_SFV + vs * 512), 128, kLayoutNone));
             __syncwarp();
 #pragma unroll
             for (int wg = 0; wg < 2; ++wg) {
-                if (!active[wg] || jj >= nv[wg]) continue;
+                if (!active[wg] || jj >= nv[wg] || !((live[wg] >> jj) & 1)) continue;
                 mbar_wait(&p_full[wg], pfull_par[wg]);
                 pfull_par[wg] ^= 1;
                 tc_fence_after();
@@ -472,11 +548,12 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                     for (int k = 0; k < KC / UMMA_K; ++k) {
                         const uint64_t da = smem_desc(p_addr + wg * TILE_BYTES + k * UMMA_K, 1024, kLayoutSw128);
                         const uint64_t db = smem_desc(v_addr0 + vs * TILE_BYTES + k * UMMA_K, 1024, kLayoutSw128);
-                        tc_mma_mx(tmem_base + TM_O + wg * 128, da, db, idesc_with_sf(p.idesc_pv, k, k), (jj | k) != 0, tm_sfp, tm_sfv);
+                        tc_mma_mx(tmem_base + TM_O + wg * 128, da, db, idesc_with_sf(p.idesc_pv, k, k), (o_started[wg] || k != 0) ? 1u : 0u, tm_sfp, tm_sfv);
                     }
                     tc_commit(&p_free[wg]);
-                    if (jj == nv[wg] - 1) tc_commit(&o_full[wg]);
+                    if (jj == last_live[wg]) tc_commit(&o_full[wg]);
                 }
+                o_started[wg] = true;
                 __syncwarp();
             }
             if (elect_one()) tc_commit(&v_empty[vs]);
@@ -484,12 +561,22 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
         };
         uint32_t ab_item[2] = {0, 0}, cfree_par[2] = {0, 0};
+        int prev = -1;  // pass C: the last chunk whose P @ V has not been issued yet
         for (int pass = 0; pass < 3; ++pass) {
+            if (pass == 1) {
+                live_chunks(live);
+#pragma unroll
+                for (int wg = 0; wg < 2; ++wg) {
+                    const uint64_t m = live[wg] & (nv[wg] >= 64 ? ~0ull : ((1ull << nv[wg]) - 1));
+                    last_live[wg] = m ? 63 - __clzll((long long)m) : -1;
+                }
+            }
             for (int j = 0; j < n_cta; ++j) {
+                if (pass > 0 && !(((live[0] | live[1]) >> j) & 1)) continue;
                 mbar_wait(&k_full[ks], kph);
                 mbar_wait(&ksf_full[ks], kph);
                 tc_fence_after();
-                const uint32_t tm_sfk = tmem_base + TM_SFK + 8 * (j & 1);
+                const uint32_t tm_sfk = tmem_base + TM_SFK + 8 * (kcnt++ & 1);
                 if (elect_one()) {
                     tc_copy_sf(tm_sfk, smem_desc(smem_u32(smem + Smem::OFF_SFK + ks * 1024), 128, kLayoutNone));
                     tc_copy_sf(tm_sfk + 4, smem_desc(smem_u32(smem + Smem::OFF_SFK + ks * 1024 + 512), 128, kLayoutNone));
@@ -499,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                 for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
                     for (int wg = 0; wg < 2; ++wg) {
-                        if (!active[wg] || j >= nv[wg]) continue;
+                        if (!active[wg] || j >= nv[wg] || (pass > 0 && !((live[wg] >> j) & 1))) continue;
                         uint32_t tm_s;
                         uint64_t* full_bar;
                         if (pass < 2) {  // two tiles per warpgroup inside its output accumulator: run one tile ahead of the softmax threads
@@ -528,13 +615,14 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                     }
                     // software pipeline of pass C: the P @ V of the previous chunk goes behind the first score tile of this one,
                     // so the softmax threads never wait for a score tile behind their own P @ V
-                    if (pass == 2 && hf == 0 && j >= 1) pv(j - 1);
+                    if (pass == 2 && hf == 0 && prev >= 0) pv(prev);
                 }
+                if (pass == 2) prev = j;
                 if (elect_one()) tc_commit(&k_empty[ks]);
                 __syncwarp();
                 if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
             }
-            if (pass == 2) pv(n_cta - 1);
+            if (pass == 2 && prev >= 0) pv(prev);
         }
         tc_fence_before();
     } else {
@@ -564,30 +652,33 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             for (int i = 0; i < 4; ++i) w[i] = __ldg(ksrc + j * KC + i * 32 + lane);
         };
         uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
-        uint32_t kw[4], kn[4];
-        const int total = 3 * n_cta;
-        if (total > 0) load_k(0, kw);
-        for (int it = 0; it < total; ++it) {
-            const int pass = it / n_cta, j = it - pass * n_cta;
-            if (it + 1 < total) load_k((it + 1) % n_cta, kn);
-            uint32_t vw[4];
-            if (pass == 2) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) vw[i] = __ldg(reinterpret_cast<const uint32_t*>(vsrc + (int64_t)(i * 32 + lane) * vld + 4 * j));
+        uint64_t need = ~0ull;
+        for (int pass = 0; pass < 3; ++pass) {
+            if (pass == 1) {
+                uint64_t live[2];
+                live_chunks(live);
+                need = live[0] | live[1];
             }
-            mbar_wait(&k_empty[ks], kph ^ 1);
-            *reinterpret_cast<uint4*>(smem + Smem::OFF_SFK + ks * 1024 + 16 * lane) = make_uint4(kw[0], kw[1], 0u, 0u);        // keys 0..63 of the chunk
-            *reinterpret_cast<uint4*>(smem + Smem::OFF_SFK + ks * 1024 + 512 + 16 * lane) = make_uint4(kw[2], kw[3], 0u, 0u);  // keys 64..127
-            publish(&ksf_full[ks]);
-            if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
-            if (pass == 2) {
-                mbar_wait(&v_empty[vs], vph ^ 1);
-                *reinterpret_cast<uint4*>(smem + Smem::OFF_SFV + vs * 512 + 16 * lane) = make_uint4(vw[0], vw[1], vw[2], vw[3]);
-                publish(&vsf_full[vs]);
-                if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
-            }
+            for (int j = 0; j < n_cta; ++j) {
+                if (!((need >> j) & 1)) continue;
+                uint32_t kw[4], vw[4];
+                load_k(j, kw);
+                if (pass == 2) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) kw[i] = kn[i];
+                    for (int i = 0; i < 4; ++i) vw[i] = __ldg(reinterpret_cast<const uint32_t*>(vsrc + (int64_t)(i * 32 + lane) * vld + 4 * j));
+                }
+                mbar_wait(&k_empty[ks], kph ^ 1);
+                *reinterpret_cast<uint4*>(smem + Smem::OFF_SFK + ks * 1024 + 16 * lane) = make_uint4(kw[0], kw[1], 0u, 0u);        // keys 0..63 of the chunk
+                *reinterpret_cast<uint4*>(smem + Smem::OFF_SFK + ks * 1024 + 512 + 16 * lane) = make_uint4(kw[2], kw[3], 0u, 0u);  // keys 64..127
+                publish(&ksf_full[ks]);
+                if (++ks == K_STAGES) { ks = 0; kph ^= 1; }
+                if (pass == 2) {
+                    mbar_wait(&v_empty[vs], vph ^ 1);
+                    *reinterpret_cast<uint4*>(smem + Smem::OFF_SFV + vs * 512 + 16 * lane) = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+                    publish(&vsf_full[vs]);
+                    if (++vs == V_STAGES) { vs = 0; vph ^= 1; }
+                }
+            }
         }
     }
     __syncthreads();
@@ -653,18 +744,22 @@ int launch_flash_attention(const mxq_attention_args_t* a, int device, cudaStream
     p.flags = a->flags;
     p.q_tiles = (int)q_tiles;
     const unsigned grid = (unsigned)(bh * q_tiles);
-#define MXQ_FA_CASE(E)                                                                                                              \
-    case E: {                                                                                                                       \
-        cudaError_t e = ensure_smem_attr((const void*)mx_flash_attention_kernel<E>, Smem::DYN_BYTES, device);                        \
+#define MXQ_FA_LAUNCH(E, T)                                                                                                         \
+    {                                                                                                                               \
+        cudaError_t e = ensure_smem_attr((const void*)mx_flash_attention_kernel<E, T>, Smem::DYN_BYTES, device);                     \
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }   \
-        mx_flash_attention_kernel<E><<<grid, fa::kThreads, Smem::DYN_BYTES, stream>>>(map_q, map_k, map_v, p);                          \
-        break;                                                                                                                      \
+        mx_flash_attention_kernel<E, T><<<grid, fa::kThreads, Smem::DYN_BYTES, stream>>>(map_q, map_k, map_v, p);                    \
     }
+#define MXQ_FA_CASE(E)                                                                                                              \
+    case E:                                                                                                                         \
+        if (a->mask != nullptr) MXQ_FA_LAUNCH(E, true) else MXQ_FA_LAUNCH(E, false)                                                  \
+        break;
     switch (a->p_elem) {
         MXQ_FA_CASE(MXQ_ELEM_E4M3) MXQ_FA_CASE(MXQ_ELEM_E3M2) MXQ_FA_CASE(MXQ_ELEM_E2M3) MXQ_FA_CASE(MXQ_ELEM_E2M1) MXQ_FA_CASE(MXQ_ELEM_E5M2)
     default: snprintf(msg, msg_len, "unknown element type %d", a->p_elem); return MXQ_ERR_INVALID;
     }
 #undef MXQ_FA_CASE
+#undef MXQ_FA_LAUNCH
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (flash attention): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;
