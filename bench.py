@@ -277,7 +277,17 @@ def mx_matmul_extras(dev):
     _, us4 = timed(lambda: m4.to_dtype(torch.float32), n=4, rounds=3)
     out["to_dtype_fp32_16384x16384"] = {"float8_e4m3": {"us": round(us8, 1), "GB/s": round(n_el * (5 + 1 / 32) / us8 / 1e3, 1)},
                                         "float4_e2m1": {"us": round(us4, 1), "GB/s": round(n_el * (4.5 + 1 / 32) / us4 / 1e3, 1)}}
+    # secondary K2 / K1 paths: the transposing dequantize (`MXTensor.t().to_dtype()`: blocked axis physically innermost, logically
+    # second-to-last) and float32 input to `to_mx` (labelled extension)
+    _, us8t = timed(lambda: m8.t().to_dtype(torch.bfloat16), n=4, rounds=3)
+    _, us4t = timed(lambda: m4.t().to_dtype(torch.bfloat16), n=4, rounds=3)
+    out["t_to_dtype_bf16_16384x16384"] = {"float8_e4m3": {"us": round(us8t, 1), "GB/s": round(n_el * (3 + 1 / 32) / us8t / 1e3, 1)},
+                                          "float4_e2m1": {"us": round(us4t, 1), "GB/s": round(n_el * (2.5 + 1 / 32) / us4t / 1e3, 1)}}
     del m8, m4
+    x32 = x0.float()
+    _, us32 = timed(lambda: MXTensor.to_mx(x32, dtypes.float8_e4m3, BLOCK), n=4, rounds=3)
+    out["to_mx_float32_input_extension_16384x16384"] = {"us": round(us32, 1), "GB/s": round(n_el * (5 + 1 / 32) / us32 / 1e3, 1), "parity": "unpinned (the reference asserts bf16 input)"}
+    del x32
     _, us5 = timed(lambda: MXTensor.to_mx(x0, dtypes.float8_e5m2, BLOCK), n=4, rounds=3)
     out["to_mx_float8_e5m2_extension_16384x16384"] = {"us": round(us5, 1), "GB/s": round(n_el * (3 + 1 / 32) / us5 / 1e3, 1), "parity": "unpinned (element type absent from the reference)"}
     del x0

@@ -140,6 +140,27 @@ def test_dequantize_strided_views(mx, oracle, elem, target):
         assert_bits_equal(bits_of(out), want, f"{shape} perm {perm}")
 
 
+@pytest.mark.parametrize("target", ["bf16", "f32"])
+@pytest.mark.parametrize("elem", ELEMS)
+def test_dequantize_transposed_vector_kernel_every_scale(mx, oracle, elem, target):
+    """the vectorised transposing kernel (block 32, blocked axis physically innermost, logically second-to-last -- what aten.t of a
+    quantized weight gives): every scale byte incl. 0, 254 and 255 (NaN), every code, ragged logical columns, batches"""
+    rng = np.random.default_rng(17)
+    td = torch.bfloat16 if target == "bf16" else torch.float32
+    per = 2 if elem == "float4_e2m1" else 1
+    hi = 64 if elem.startswith("float6") else 256
+    for shape, perm in (((257, 512), (1, 0)), ((3, 70, 256), (0, 2, 1))):
+        codes = rng.integers(0, hi, size=shape[:-1] + (shape[-1] // per,), dtype=np.uint8)
+        scales = rng.integers(0, 256, size=shape[:-1] + (shape[-1] // 32,), dtype=np.uint8)
+        if elem == "int8":
+            codes = codes.view(np.int8)
+        bd = perm.index(len(shape) - 1)
+        out = torch.ops.torchmx.dequantize_mx(torch.from_numpy(codes).to(DEV).permute(perm), torch.from_numpy(scales).to(DEV).permute(perm), elem, 32, td, bd)
+        want = oracle.dequantize(np.transpose(codes, perm), np.transpose(scales, perm), elem, 32, target, bd)
+        want = want.view(np.uint32) if target == "f32" else want
+        assert_bits_equal(bits_of(out), want, f"{shape} perm {perm}")
+
+
 # ---- MXTensor level (user API) against reference fixtures --------------------------------------------------
 @pytest.mark.parametrize("elem", ELEMS)
 def test_readme_example(mx, fixtures, elem):

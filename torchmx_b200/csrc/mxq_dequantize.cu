@@ -12,6 +12,8 @@
 // Fast path (block 32, blocked axis innermost and contiguous): flat run of blocks, a thread owns
 // 16 codes (one 128-bit load; fp4: 16 bytes = one whole block) and writes 32/64 B (bf16) or
 // 64/128 B (fp32) with 256-bit stores.
+#include <type_traits>
+
 #include "mxq_common.cuh"
 
 namespace mxq {
@@ -196,6 +198,91 @@ __global__ void __launch_bounds__(256) dequantize_transposed_kernel(const uint8_
     }
 }
 
+// ---- transposing path, block size 32, vectorised --------------------------------------------------------------------------
+// The same mapping as dequantize_transposed_kernel with 128-bit accesses on both sides: a CTA owns 64 physical rows (logical
+// columns n) x KT logical rows k (KT = 64 elements; 128 for fp4, whose 16-byte load holds a whole block).  Thread (row, q) loads
+// 16 code bytes of its row, decodes them with the block's scale (K2's arithmetic: exact decode, exact fp32 product, one
+// rounding) and scatters the values into a shared-memory tile laid out [k][n]; thread (k, q) then stores 16 consecutive n
+// of one k: 32 B (bf16) / 64 B (fp32) per thread, 128 / 256 B contiguous per k row.
+// Algorithmic traffic = the flat kernel's (1 + 1/32 B in, 2 / 4 B out per element).
+template <int ELEM, bool F32>
+__global__ void __launch_bounds__(256) dequantize_transposed_b32_kernel(const uint8_t* __restrict__ codes, const uint8_t* __restrict__ scales,
+                                                                        void* __restrict__ dst, int64_t K, int64_t N, int64_t code_batch_stride,
+                                                                        int64_t code_row_stride, int64_t scale_batch_stride, int64_t scale_row_stride) {
+    constexpr bool FP4 = ELEM == MXQ_ELEM_E2M1;
+    constexpr int EPL = FP4 ? 32 : 16;        // elements per 16-byte load
+    constexpr int KT = 128;                   // logical rows k per CTA: a whole 128-byte line of every physical row (fp4: 64 bytes)
+    constexpr int LOADS = KT / (4 * EPL);     // 16-byte loads per thread
+    constexpr int PITCH = 64 + (F32 ? 4 : 8); // elements per tile row: 16-byte aligned rows, consecutive rows 4 banks apart
+    constexpr int CH = F32 ? 4 : 8;           // elements per 16-byte chunk
+    using T = typename std::conditional<F32, float, uint16_t>::type;
+    __shared__ __align__(16) T tile[KT][PITCH];
+    const int64_t b = blockIdx.z;
+    // consecutive CTAs walk the logical columns n: their 128-byte output segments of one k row are neighbours in DRAM (the
+    // output is twice the bytes of the input, so the stores get the locality)
+    const int64_t n0 = (int64_t)blockIdx.x * 64, k0 = (int64_t)blockIdx.y * KT;
+#pragma unroll
+    for (int h = 0; h < LOADS; ++h) {
+        const int row = threadIdx.x >> 2, q = threadIdx.x & 3, grp = 4 * h + q;  // grp: which EPL-wide slice of the tile's k range
+        const int64_t n = n0 + row, k = k0 + grp * EPL;
+        float f[EPL];
+        if (n < N && k < K) {  // (K is a multiple of 32 and of EPL: a load never straddles the end of a row)
+            const uint8_t* src = codes + b * code_batch_stride + n * code_row_stride + (FP4 ? (k >> 1) : k);
+            const uint4 v = ldg128_stream(src);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const float sc = scale_f32(__ldg(scales + b * scale_batch_stride + n * scale_row_stride + (k >> 5)));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if constexpr (FP4) {
+                    float t[8];
+                    decode8_e2m1(w[i], sc, t);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[8 * i + j] = t[j];
+                } else {
+                    float t[4];
+                    decode4<ELEM>(w[i], sc, t);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) f[4 * i + j] = t[j];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) f[i] = 0.0f;
+        }
+        // 16-byte chunks of a tile row are XOR-permuted with the row's load group (mod 4 = q of the thread that writes it), so the
+        // four q lanes of a warp, whose rows lie a multiple of 32 banks apart, hit different banks
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const int col = (((row / CH) ^ (F32 ? 2 * q : q)) * CH) + (row % CH);
+            if constexpr (F32) tile[grp * EPL + i][col] = f[i];
+            else tile[grp * EPL + i][col] = (uint16_t)pack_bf16x2(f[i], 0.0f);
+        }
+    }
+    __syncthreads();
+    constexpr int PER = 16;  // n per thread and k row
+#pragma unroll
+    for (int it = 0; it < KT / 64; ++it) {
+        const int kk = it * 64 + (threadIdx.x >> 2), q = threadIdx.x & 3;
+        const int g = (kk / EPL) & 3;
+        const int64_t k = k0 + kk, n = n0 + q * PER;
+        if (k >= K || n >= N) continue;
+        T* out = reinterpret_cast<T*>(dst) + (b * K + k) * N + n;
+        const bool vec_out = n + PER <= N && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+#pragma unroll
+        for (int j = 0; j < PER / CH; ++j) {
+            const int chunk = ((q * PER) / CH + j) ^ (F32 ? 2 * g : g);
+            const uint4 v = *reinterpret_cast<const uint4*>(&tile[kk][chunk * CH]);
+            if (vec_out) {
+                stg128_stream(out + j * CH, v);
+            } else {
+                const T* e = reinterpret_cast<const T*>(&v);
+                for (int u = 0; u < CH; ++u)
+                    if (n + j * CH + u < N) out[j * CH + u] = e[u];
+            }
+        }
+    }
+}
+
 // ---- launchers -----------------------------------------------------------------------------------
 template <int ELEM, bool F32>
 static cudaError_t launch_flat(const void* codes, const uint8_t* scales, int64_t n_blocks, int block_size, void* dst, int sm_count, int cb,
@@ -248,6 +335,14 @@ static cudaError_t launch_strided(const void* codes, const uint8_t* scales, int 
             batch *= sizes[d];
         }
         const int64_t K = sizes[ndim - 2], N = sizes[ndim - 1];
+        constexpr int KT = 128;
+        const bool vec = block_size == 32 && K % 32 == 0 && ((uintptr_t)codes % 16) == 0 && cs[ndim - 1] % 16 == 0 && cbs % 16 == 0 &&
+                         (ELEM != MXQ_ELEM_E2M1 || K % 64 == 0);
+        if (ok && vec && batch <= 65535 && (K + KT - 1) / KT <= 65535) {
+            dim3 grid((unsigned)((N + 63) / 64), (unsigned)((K + KT - 1) / KT), (unsigned)batch);
+            dequantize_transposed_b32_kernel<ELEM, F32><<<grid, 256, 0, stream>>>((const uint8_t*)codes, scales, dst, K, N, cbs, cs[ndim - 1], sbs, ss[ndim - 1]);
+            return cudaGetLastError();
+        }
         if (ok && batch <= 65535 && (N + 63) / 64 <= 65535) {
             dim3 grid((unsigned)((K + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)batch);
             dequantize_transposed_kernel<ELEM, F32><<<grid, 256, 0, stream>>>((const uint8_t*)codes, scales, dst, batch, K, N, cbs, cs[ndim - 1], sbs,
