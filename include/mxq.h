@@ -329,6 +329,16 @@ typedef struct {
 } mxq_rope_args_t;
 MXQ_API int mxq_rope(const mxq_rope_args_t *args, int device, void *stream);
 
+/*
+ * the attention output as o_proj's MX activation  <->  `attn_output.transpose(1, 2).contiguous().reshape(b, q, h * d)`
+ * (torchmx/layers/mx_llama_attention.py:245-247) followed by the quantization on entry to o_proj (torchmx/layers/mx_linear.py:63-66):
+ *     codes, scales = quantize_mx(transpose(src), elem, 32)     with the transposed bf16 tensor never written
+ *   src    : bf16 [batch, heads, tokens, head_dim] contiguous (what the attention kernel leaves), head_dim % 32 == 0
+ *   codes  : [batch, tokens, heads * head_dim] (float4_e2m1: half), scales [batch, tokens, heads * head_dim / 32]
+ */
+MXQ_API int mxq_quantize_heads(const void *src, int64_t batch, int64_t heads, int64_t tokens, int64_t head_dim, int elem /* mxq_elem_t */,
+                       unsigned flags /* MXQ_FLAG_* */, void *codes, uint8_t *scales, int device, void *stream);
+
 #define MXQ_OK 0
 #define MXQ_ERR_INVALID 1
 #define MXQ_ERR_UNSUPPORTED_SHAPE 2

@@ -93,6 +93,26 @@ def test_rope_is_bit_identical_to_apply_rotary_pos_emb(b, t, hq, hk, d, stacked)
         assert_bits_equal(bits_of(got[1]), bits_of(want[1]), "k")
 
 
+@pytest.mark.parametrize("elem", ELEMS + ["float8_e5m2"])
+@pytest.mark.parametrize("shape", [(1, 32, 2048, 128), (32, 8, 1, 128), (2, 3, 77, 64), (1, 2, 5, 32)])
+def test_quantize_heads_is_k1_of_the_transposed_tensor(elem, shape):
+    import torchmx  # noqa: F401
+    from torchmx_b200 import dtypes, glue_ops
+    from torchmx_b200.mx_tensor import MXTensor
+    b, h, t, d = shape
+    g = torch.Generator(device=DEV).manual_seed(t)
+    x = torch.randn(*shape, device=DEV, dtype=torch.bfloat16, generator=g)
+    x *= torch.exp2(torch.randint(-20, 20, (b, h, t, d // 32), device=DEV, generator=g).float()).repeat_interleave(32, -1).to(torch.bfloat16)
+    x[0, 0, 0, 3] = float("nan")
+    x[-1, -1, -1, -1] = float("inf")
+    dt = dtypes.STR_TO_ELEM_DTYPE[elem]
+    got = glue_ops.quantize_heads(x, dt)
+    want = MXTensor.to_mx(x.transpose(1, 2).reshape(b, t, h * d).contiguous(), dt, 32)
+    assert got.shape == want.shape
+    assert_bits_equal(bits_of(got._scale_e8m0), bits_of(want._scale_e8m0), "scales")
+    assert_bits_equal(bits_of(got._data), bits_of(want._data), "codes")
+
+
 def test_glue_kernels_decline_what_they_cannot_take():
     import torchmx  # noqa: F401
     from torchmx_b200 import glue_ops

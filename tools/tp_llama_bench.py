@@ -131,7 +131,8 @@ class TPDecoderLayer(torch.nn.Module):
             a = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True)
         else:      # decode: attend to the first cache_len + 1 cache positions
             a = F.scaled_dot_product_attention(q, kc[:, :, : cache_len + 1], vc[:, :, : cache_len + 1], enable_gqa=True)
-        o = self.o(a.transpose(1, 2).reshape(B, T, self.nh_local * self.hd))
+        a_mx = glue_ops.quantize_heads(a, self.act)  # o's activation, quantized straight from the [B, H, T, D] attention output (K5c)
+        o = self.o(a_mx if a_mx is not None else a.transpose(1, 2).reshape(B, T, self.nh_local * self.hd))
         r = glue_ops.rmsnorm(o, self.n2, 1e-5, residual=h, to_mx=to_mx, want_y=to_mx is None)
         assert r is not None
         y, y_mx, h = r

@@ -17,7 +17,7 @@ ABI_VERSION = 2
 MAX_DIMS = 6
 
 EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_gemm_dequant", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
-           "mxq_softmax_quantize", "mxq_flash_attention", "mxq_silu_mul_quantize", "mxq_rmsnorm", "mxq_rope", "mxq_last_error", "mxq_version", "mxq_arch")
+           "mxq_softmax_quantize", "mxq_flash_attention", "mxq_silu_mul_quantize", "mxq_rmsnorm", "mxq_rope", "mxq_quantize_heads", "mxq_last_error", "mxq_version", "mxq_arch")
 
 
 class GemmArgs(ctypes.Structure):
@@ -150,6 +150,8 @@ def lib() -> ctypes.CDLL:
         L.mxq_flash_attention.argtypes = [ctypes.POINTER(AttentionArgs), i32, vp]
         L.mxq_rmsnorm.restype = i32
         L.mxq_rmsnorm.argtypes = [ctypes.POINTER(RmsNormArgs), i32, vp]
+        L.mxq_quantize_heads.restype = i32
+        L.mxq_quantize_heads.argtypes = [vp, i64, i64, i64, i64, i32, u32, vp, vp, i32, vp]
         L.mxq_rope.restype = i32
         L.mxq_rope.argtypes = [ctypes.POINTER(RopeArgs), i32, vp]
         if L.mxq_version() != ABI_VERSION:

@@ -22,6 +22,7 @@ cudaError_t launch_silu_mul_quantize(const void*, const void*, int64_t, int64_t,
 int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size_t);
 int launch_rmsnorm(const mxq_rmsnorm_args_t*, cudaStream_t, char*, size_t);
 int launch_rope(const mxq_rope_args_t*, int, cudaStream_t, char*, size_t);
+int launch_heads_quantize(const void*, int64_t, int64_t, int64_t, int64_t, int, unsigned, void*, uint8_t*, cudaStream_t, char*, size_t);
 }  // namespace mxq
 
 namespace {
@@ -234,6 +235,19 @@ int mxq_rmsnorm(const mxq_rmsnorm_args_t* a, int device, void* stream) {
     char msg[400] = "";
     const int rc = mxq::launch_rmsnorm(a, (cudaStream_t)stream, msg, sizeof(msg));
     return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_rmsnorm: %s", msg);
+}
+
+int mxq_quantize_heads(const void* src, int64_t batch, int64_t heads, int64_t tokens, int64_t head_dim, int elem, unsigned flags, void* codes,
+                       uint8_t* scales, int device, void* stream) {
+    if (!valid_elem(elem)) return fail(MXQ_ERR_INVALID, "mxq_quantize_heads: unknown element type %d", elem);
+    if (batch < 0 || heads < 0 || tokens < 0 || head_dim < 0) return fail(MXQ_ERR_INVALID, "mxq_quantize_heads: negative extent");
+    if (batch == 0 || heads == 0 || tokens == 0 || head_dim == 0) return MXQ_OK;
+    if (!src || !codes || !scales) return fail(MXQ_ERR_INVALID, "mxq_quantize_heads: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_quantize_heads: selecting device");
+    char msg[400] = "";
+    const int rc = mxq::launch_heads_quantize(src, batch, heads, tokens, head_dim, elem, flags, codes, scales, (cudaStream_t)stream, msg, sizeof(msg));
+    return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_quantize_heads: %s", msg);
 }
 
 int mxq_rope(const mxq_rope_args_t* a, int device, void* stream) {

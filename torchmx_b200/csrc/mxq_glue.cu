@@ -173,7 +173,64 @@ __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
     }
 }
 
+// K5c heads_quantize_kernel: the attention output as the MX activation of o_proj.  The attention kernel leaves [batch, heads, tokens,
+// head_dim]; the reference transposes to [batch, tokens, heads * head_dim] (a copy, torchmx/layers/mx_llama_attention.py:245-247) and
+// o_proj quantizes on entry (mx_linear.py:63-66).  An MX block (32 consecutive channels) lies inside one head, so the codes can be
+// produced straight from the [b, h, t, d] layout: one thread per block, K1's arithmetic, stores in [b, t, h * d] order.
+template <int ELEM>
+__global__ void __launch_bounds__(256) heads_quantize_kernel(const uint16_t* __restrict__ src, uint8_t* __restrict__ codes, uint8_t* __restrict__ scales,
+                                                             int64_t n_blocks, int heads, int64_t tokens, int dblocks, uint32_t flags) {
+    pdl_launch_dependents();
+    const int64_t o = (int64_t)blockIdx.x * 256 + threadIdx.x;  // block index in output order: ((b * T + t) * H + h) * dblocks + db
+    if (o >= n_blocks) return;
+    const int db = (int)(o % dblocks);
+    int64_t r = o / dblocks;
+    const int h = (int)(r % heads); r /= heads;
+    const int64_t t = r % tokens, b = r / tokens;
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(src) + ((((b * heads + h) * tokens + t) * dblocks + db) * 64);
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const u32x8 v = ldg256_stream(p + 32 * j);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[8 * j + k] = v.v[k];
+    }
+    constexpr int NO = (ELEM == MXQ_ELEM_E2M1) ? 4 : 8;
+    uint32_t out[NO];
+    const int sc = quantize_block32<ELEM>(w, (flags & MXQ_FLAG_HW_EXACT) != 0, out);
+    uint8_t* dst = codes + o * (NO * 4);
+    if constexpr (NO == 4) stg128_stream(dst, make_uint4(out[0], out[1], out[2], out[3]));
+    else {
+        u32x8 q;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q.v[k] = out[k];
+        stg256_stream(dst, q);
+    }
+    scales[o] = (uint8_t)sc;
+}
+
 }  // namespace glue
+
+int launch_heads_quantize(const void* src, int64_t batch, int64_t heads, int64_t tokens, int64_t head_dim, int elem, unsigned flags, void* codes,
+                          uint8_t* scales, cudaStream_t stream, char* msg, size_t msg_len) {
+    using namespace glue;
+    if (head_dim % 32 || ((uintptr_t)src % 32) || ((uintptr_t)codes % 32) || heads > 0x7FFFFFFF) {
+        snprintf(msg, msg_len, "needs head_dim %% 32 == 0 and 32-byte aligned tensors");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    const int64_t n_blocks = batch * heads * tokens * (head_dim / 32);
+    const int64_t grid = (n_blocks + 255) / 256;
+    if (grid > 0x7FFFFFFF) { snprintf(msg, msg_len, "too many blocks"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+#define MXQ_HQ_CASE(E) case E: heads_quantize_kernel<E><<<(unsigned)grid, 256, 0, stream>>>((const uint16_t*)src, (uint8_t*)codes, scales, n_blocks, (int)heads, tokens, (int)(head_dim / 32), flags); break;
+    switch (elem) {
+        MXQ_HQ_CASE(MXQ_ELEM_E4M3) MXQ_HQ_CASE(MXQ_ELEM_E3M2) MXQ_HQ_CASE(MXQ_ELEM_E2M3) MXQ_HQ_CASE(MXQ_ELEM_E2M1) MXQ_HQ_CASE(MXQ_ELEM_INT8) MXQ_HQ_CASE(MXQ_ELEM_E5M2)
+    default: snprintf(msg, msg_len, "unknown element type %d", elem); return MXQ_ERR_INVALID;
+    }
+#undef MXQ_HQ_CASE
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "launch: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    return MXQ_OK;
+}
 
 int launch_rmsnorm(const mxq_rmsnorm_args_t* a, cudaStream_t stream, char* msg, size_t msg_len) {
     using namespace glue;

@@ -22,7 +22,7 @@ from . import env_variables as env
 from .mlp_ops import _rows_view
 from .mx_tensor import MXTensor, _stream_ptr
 
-stats = {"rmsnorm": 0, "rmsnorm_to_mx": 0, "rope": 0}
+stats = {"rmsnorm": 0, "rmsnorm_to_mx": 0, "rope": 0, "quantize_heads": 0}
 _ENABLED = os.environ.get("MXQ_FUSED_GLUE", "1") != "0"
 MAX_HIDDEN = 16384
 
@@ -125,3 +125,25 @@ def rope(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor)
     _C.check(rc, "mxq_rope")
     stats["rope"] += 1
     return q_out, k_out
+
+
+def quantize_heads(x: torch.Tensor, elem_dtype: dtypes.DType, block_size: int = 32) -> Optional[MXTensor]:
+    """x: bf16 [batch, heads, tokens, head_dim] contiguous (an attention kernel's output) -> the MXTensor
+    `MXTensor.to_mx(x.transpose(1, 2).reshape(batch, tokens, heads * head_dim), elem_dtype, 32)` without writing the transposed
+    tensor (K5c); None when the kernel does not apply"""
+    if not _ENABLED or block_size != 32 or not _plain_bf16(x) or x.dim() != 4 or not x.is_contiguous() or x.numel() == 0:
+        return None
+    b, h, t, d = x.shape
+    if d % 32 or x.data_ptr() % 32:
+        return None
+    is_fp4 = elem_dtype == dtypes.float4_e2m1
+    codes = torch.empty((b, t, h * d // 2 if is_fp4 else h * d), dtype=torch.int8 if elem_dtype == dtypes.int8 else torch.uint8, device=x.device)
+    scales = torch.empty((b, t, h * d // 32), dtype=torch.uint8, device=x.device)
+    flags = _C.FLAG_HW_EXACT if (elem_dtype in dtypes.SUPPORTED_FP_ELEM_DTYPES and env.MX_EXACT_QUANTIZATION == "True") else 0
+    rc = _C.lib().mxq_quantize_heads(x.data_ptr(), b, h, t, d, dtypes.ELEM_ID[elem_dtype.name], flags, codes.data_ptr(), scales.data_ptr(),
+                                     x.device.index, _stream_ptr(x))
+    if rc == _C.ERR_UNSUPPORTED_SHAPE:
+        return None
+    _C.check(rc, "mxq_quantize_heads")
+    stats["quantize_heads"] += 1
+    return MXTensor(scales, codes, elem_dtype, 32, torch.bfloat16)

@@ -95,7 +95,7 @@ def _fuse_linears(mods) -> Optional[MXInferenceLinear]:
 
 
 GROUPED_DECODE_SDPA = os.environ.get("MXQ_GROUPED_DECODE_SDPA", "1") != "0"  # decode under sdpa: no repeat_kv copies (see forward)
-STACKED_MAX_ROWS = 128  # measured on Llama-8B: decode 10.1 -> 9.8 ms/step stacked, but prefill 27.1 -> 29.3 ms (the column
+STACKED_MAX_ROWS = int(os.environ.get("MXQ_STACKED_MAX_ROWS", 128))  # measured on Llama-8B: decode 10.1 -> 9.8 ms/step stacked, but prefill 27.1 -> 29.3 ms (the column
 #                         slices of a stacked output make every following elementwise kernel and copy strided), so prefill keeps
 #                         one launch per projection
 
@@ -321,6 +321,20 @@ class _MXAttentionMixin:
             out = nn.functional.scaled_dot_product_attention(query_states.reshape(b, hk, h // hk, d), key_states, value_states, attn_mask=mask,
                                                              dropout_p=0.0, scale=self.scaling, is_causal=False)
             attn_output, attn_weights = out.reshape(b, 1, h, d), None
+        elif (GROUPED_DECODE_SDPA and attention_mask is None and getattr(self.config, "_attn_implementation", "eager") == "sdpa" and not self.training
+              and query_states.is_cuda and isinstance(self.o_proj, MXInferenceLinear) and self.o_proj.qconfig.activations_config.block_size == 32
+              and self.head_dim % 32 == 0 and not torch.compiler.is_compiling()):
+            # Prefill under sdpa without a mask tensor (transformers leaves the causal rule to the kernel): the same SDPA call, but
+            # its [b, h, q, d] output is quantized for o_proj straight from that layout (K5c) instead of being transposed into a
+            # contiguous [b, q, h * d] copy first (sdpa_attention_forward ends with .transpose(1, 2).contiguous()) and quantized
+            # by o_proj on entry -- the codes are the same bit for bit
+            causal = query_states.shape[2] > 1 and getattr(self, "is_causal", True)
+            out = nn.functional.scaled_dot_product_attention(query_states, key_states, value_states, attn_mask=None, dropout_p=0.0, scale=self.scaling,
+                                                             is_causal=causal, enable_gqa=self.num_key_value_groups > 1)
+            x_mx = glue_ops.quantize_heads(out, self.o_proj.qconfig.activations_config.elem_dtype)
+            if x_mx is not None:
+                return self.o_proj(x_mx), None
+            attn_output, attn_weights = out.transpose(1, 2), None
         else:
             fn = mod_llama.eager_attention_forward
             impl = getattr(self.config, "_attn_implementation", "eager")
