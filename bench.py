@@ -55,6 +55,39 @@ def measured_peak_gbs():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Run this process on the CPUs of the NUMA node its GPU hangs off (sysfs; best effort, None when unknown): with one rank per
+    GPU the pinned host buffers of the e2e leg are then spread over the nodes instead of all landing on the node the launcher
+    happened to start on (round 1: 131 GB/s aggregate at 8 GPUs against 82 GB/s at 1)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bus is None:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def ncu_traffic(kernel_key: str):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -507,6 +540,7 @@ def run_b200(args):
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e_steps = max(1, min(args.steps, 5))
+    numa = bind_to_gpu_numa_node(local)  # the pinned buffers below are first-touched on the GPU's own NUMA node (N > 1: no shared DRAM channel)
     xh = torch.empty(ROWS, COLS, dtype=torch.bfloat16).pin_memory()
     xh.copy_(xs[0])
 
@@ -604,12 +638,14 @@ def run_b200(args):
                        "parallelism": f"independent tensors per GPU x{world}, no collective"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": round(1e3 * e2e_s / max(e2e_steps, 1), 2), "note": "pinned host buffers, PCIe copies in the timed region; four pipelined streams (H2D / D2H overlap, full-duplex PCIe)"},
+                    "steps": e2e_steps, "ms_per_step": round(1e3 * e2e_s / max(e2e_steps, 1), 2), "note": "pinned host buffers, PCIe copies in the timed region; four pipelined streams (H2D / D2H overlap, full-duplex PCIe)",
+                    "host_numa_node_of_rank0": numa},
             "gpu_launches": args.steps * 2 * len(ELEMS),
             "roofline": roofline,
             "cpu_baseline": None if cpu_value is None else {
                 "value": round(cpu_value, 3), "unit": "GB/s", "cores": cpu_threads, "kind": "port",
-                "sample": f"{cpu_rows}x{COLS} rows of the workload (1/8), all 5 elem dtypes, quantize+dequantize, best of 2, {cpu_dt:.2f} s"},
+                "sample": f"{cpu_rows}x{COLS} rows of the workload (1/8), all 5 elem dtypes, quantize+dequantize, best of 2, {cpu_dt:.2f} s",
+                "python_reference_context": "the unmodified Python reference (torch CPU ops) measured 0.04-1.8 GB/s on 8 cores on this workload (BASELINE.md section 4); it cannot travel to the GPU box, the C port (validated against it bit for bit) is what is timed here"},
             "kernels": {k: {"us": round(v["ms"] * 1e3, 2), "GB/s": round(v["GB/s"], 1)} for k, v in kernels.items()},
             "mx_matmul": extras,
             "llama8b": llama,
