@@ -56,9 +56,10 @@ def measured_peak_gbs():
 
 
 def bind_to_gpu_numa_node(local_rank: int):
-    """Run this process on the CPUs of the NUMA node its GPU hangs off (sysfs; best effort, None when unknown): with one rank per
-    GPU the pinned host buffers of the e2e leg are then spread over the nodes instead of all landing on the node the launcher
-    happened to start on (round 1: 131 GB/s aggregate at 8 GPUs against 82 GB/s at 1)."""
+    """Run this process on the CPUs of the NUMA node its GPU hangs off (sysfs; best effort, None when unknown), so that with one rank
+    per GPU the pinned host buffers of the e2e leg are first-touched next to their GPU.  On this pool's boxes it is a no-op: they
+    expose ONE NUMA node (nvidia-smi topo: every GPU "NUMA affinity 0", numa_node = -1 in sysfs), and the e2e leg saturates at
+    ~130 GB/s aggregate from 2 GPUs on (82 GB/s at 1): the host side of the copies, not the kernels, is the limit there."""
     try:
         import torch
         pr = torch.cuda.get_device_properties(local_rank)
