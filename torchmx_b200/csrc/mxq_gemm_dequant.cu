@@ -24,7 +24,11 @@ constexpr int TILE = 128;       // output tile: 128 x 128
 constexpr int BK = 64;          // bf16 elements per stage and row = one 128-byte swizzle row
 constexpr int STAGES = 3;       // bf16 operand stages (what the tensor core reads)
 constexpr int RAW_STAGES = 6;   // raw code stages (what TMA writes): the deep ring that covers the DRAM / L2 latency
-constexpr int kProducerThreads = 256;
+constexpr int kProducerThreads = 512;             // 8 warps per operand: the dequantization is latency-bound per warp (one chunk chain at
+                                                  // a time), so twice the warps of the first version is nearly twice the rate
+constexpr int kPerOperand = kProducerThreads / 2;
+constexpr int CHUNKS = TILE * 4 / kPerOperand;    // 16-element chunks per thread and stage (fast path)
+constexpr int kMmaWarp = kProducerThreads / 32, kTmaWarp = kMmaWarp + 1;
 constexpr int kThreads = kProducerThreads + 64;  // + MMA warp + TMA warp
 constexpr int STAGE_BYTES = TILE * BK * 2;  // 16 KB per operand
 constexpr int RAW_BYTES = TILE * BK;        // 8 KB per operand (fp4 uses half of it)
@@ -236,7 +240,8 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
         lut[threadIdx.x] = lut_entry(p.a.elem, threadIdx.x);
         lut[256 + threadIdx.x] = lut_entry(p.b.elem, threadIdx.x);
     }
-    if (warp == 8) {
+    static_assert(kPerOperand == 256 || kPerOperand == 128, "thread <-> (row, chunk) maps assume 128 or 256 producer threads per operand");
+    if (warp == kMmaWarp) {
         if (elect_one()) {
             for (int i = 0; i < STAGES; ++i) {
                 mbar_init(&full[i], kProducerThreads);
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
             }
             for (int i = 0; i < RAW_STAGES; ++i) {
                 mbar_init(&raw_full[i], 1);
-                mbar_init(&raw_empty[i], 4 * (n_fast > 0 ? n_fast : 1));
+                mbar_init(&raw_empty[i], (kPerOperand / 32) * (n_fast > 0 ? n_fast : 1));
             }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
         __syncwarp();
         tmem_alloc<128>(tmem_ptr);
     }
-    if (warp == 9 && elect_one()) {
+    if (warp == kTmaWarp && elect_one()) {
         if (p.a.fast) tma_prefetch_desc(&map_a);
         if (p.b.fast) tma_prefetch_desc(&map_b);
     }
@@ -261,11 +266,11 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp < 8) {
-        // ================= producers: warps 0..3 build the A tile, warps 4..7 the B tile =================
-        const bool is_b = threadIdx.x >= 128;
+    if (warp < kMmaWarp) {
+        // ================= producers: warps 0..7 build the A tile, warps 8..15 the B tile =================
+        const bool is_b = threadIdx.x >= kPerOperand;
         const Operand& op = is_b ? p.b : p.a;
-        const int tidx = threadIdx.x & 127;
+        const int tidx = threadIdx.x & (kPerOperand - 1);
         const int row0 = (is_b ? nb : mb) * TILE;
         const uint8_t* codes = op.codes + (int64_t)b * op.batch_stride;
         const uint8_t* scales = op.scales + (int64_t)b * op.sbatch_stride;
@@ -278,30 +283,30 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
             // reads 512 (256) contiguous raw bytes per instruction.  item = i * 128 + tidx -> row = item >> 2, q = item & 3.
             const bool fp4 = op.elem == MXQ_ELEM_E2M1;
             const int q = tidx & 3;
-            int rows_i[4];
-            const uint8_t* sc_ptr[4];
+            int rows_i[CHUNKS];
+            const uint8_t* sc_ptr[CHUNKS];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                rows_i[i] = (i * 128 + tidx) >> 2;
+            for (int i = 0; i < CHUNKS; ++i) {
+                rows_i[i] = (i * kPerOperand + tidx) >> 2;
                 const int r = min(row0 + rows_i[i], op.rows - 1);  // rows past the edge carry zero codes; any in-range scale will do
                 sc_ptr[i] = scales + (int64_t)r * op.srow_stride;
             }
-            auto load_scales = [&](int ks, int (&sb)[4]) {
+            auto load_scales = [&](int ks, int (&sb)[CHUNKS]) {
                 const int kq = ks * BK + 16 * q;
                 const bool live = ks < k_steps && kq < p.K;
                 const int64_t off = (int64_t)(kq >> op.bs_shift) * op.sk_stride;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) sb[i] = live ? (int)__ldg(sc_ptr[i] + off) : 127;
+                for (int i = 0; i < CHUNKS; ++i) sb[i] = live ? (int)__ldg(sc_ptr[i] + off) : 127;
             };
-            int sb_cur[4], sb_nxt[4];
+            int sb_cur[CHUNKS], sb_nxt[CHUNKS];
             load_scales(0, sb_cur);
             for (int ks = 0; ks < k_steps; ++ks) {
                 load_scales(ks + 1, sb_nxt);
                 mbar_wait(&raw_full[rs], rphase);
                 const uint8_t* raw = raw_base + rs * RAW_BYTES;
-                uint32_t rw[4][4];
+                uint32_t rw[CHUNKS][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < CHUNKS; ++i) {
                     if (fp4) {
                         const uint2 v = *reinterpret_cast<const uint2*>(raw + rows_i[i] * 32 + q * 8);
                         rw[i][0] = v.x; rw[i][1] = v.y; rw[i][2] = 0; rw[i][3] = 0;
@@ -318,9 +323,9 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* dst = tile_base + stage * STAGE_BYTES;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < CHUNKS; ++i) {
                     uint32_t o[8];
-                    if (dead) {
+                    if (dead || row0 + rows_i[i] >= op.rows) {  // past K / past the last row (decode: most of the 128-token tile): zeros
 #pragma unroll
                         for (int j = 0; j < 8; ++j) o[j] = 0u;
                     } else {
@@ -335,25 +340,26 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
                 mbar_arrive(&full[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) sb_cur[i] = sb_nxt[i];
+                for (int i = 0; i < CHUNKS; ++i) sb_cur[i] = sb_nxt[i];
             }
         } else {
-            // generic: thread = one row of the tile, element-wise addressing through the operand's strides
-            const int row = tidx;
+            // generic: two threads per row of the tile (four 8-element chunks each), element-wise addressing through the operand's strides
+            constexpr int TPR = kPerOperand / TILE;
+            const int row = tidx / TPR, c0 = (tidx % TPR) * (8 / TPR);
             const int r = row0 + row;
             for (int ks = 0; ks < k_steps; ++ks) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* dst = tile_base + stage * STAGE_BYTES + row * 128;
 #pragma unroll 4
-                for (int c = 0; c < 8; ++c)  // 16-byte chunk c of the row lives at chunk c ^ (row & 7) (SWIZZLE_128B)
+                for (int c = c0; c < c0 + 8 / TPR; ++c)  // 16-byte chunk c of the row lives at chunk c ^ (row & 7) (SWIZZLE_128B)
                     *reinterpret_cast<uint4*>(dst + ((c ^ (row & 7)) << 4)) = dequant_chunk(op, codes, scales, my_lut, r, ks * BK + c * 8, p.K);
                 fence_proxy_async_smem();
                 mbar_arrive(&full[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-        // ================= epilogue: warp (quadrant, column half) drains 32 rows x 64 columns =================
-        const int quad = warp & 3, half = warp >> 2;
+        // ================= epilogue: warp (quadrant, column group) drains 32 rows x 32 columns =================
+        const int quad = warp & 3, cgrp = warp >> 2;
         if (k_steps > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
@@ -361,16 +367,16 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
         const int m = mb * TILE + quad * 32 + lane;
         uint16_t* drow = p.d + (int64_t)b * p.d_batch + (int64_t)m * p.ldd;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < TILE / 32 / (kMmaWarp / 4); ++c) {
             uint32_t v[32];
             if (k_steps > 0) {
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + half * 64 + c * 32, v);
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (cgrp * (TILE / 32 / (kMmaWarp / 4)) + c) * 32, v);
                 tmem_ld_wait();
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0u;
             }
-            const int col0 = nb * TILE + half * 64 + c * 32;
+            const int col0 = nb * TILE + (cgrp * (TILE / 32 / (kMmaWarp / 4)) + c) * 32;
             if (m < p.M && col0 < p.N) {
                 float f[32];
 #pragma unroll
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
             }
         }
         tc_fence_before();
-    } else if (warp == 8) {
+    } else if (warp == kMmaWarp) {
         // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
         // kind::f16 descriptor: fp32 accumulator (bit 4), bf16 A and B (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
         }
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc<128>(tmem_base);
     }
