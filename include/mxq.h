@@ -246,6 +246,19 @@ typedef struct {
 MXQ_API int mxq_softmax_quantize(const mxq_softmax_args_t *args, int device, void *stream);
 
 /*
+ * bf16 GEMM on the tensor cores (tcgen05 kind::f16), D[b] = A[b] B[b]^T (+ bias): the second half of the reference's own recipe --
+ * dequantize both operands, then a bf16 matmul (torchmx/ops.py:29-41, 60-68, 99-119) -- for LARGE contractions of operand pairs the
+ * block-scaled MMA cannot take.  mxq_gemm_dequant dequantizes inside the GEMM, i.e. once per output tile; above a few hundred
+ * rows and columns it is cheaper to dequantize each operand once (mxq_dequantize / mxq_dequantize_strided into scratch) and multiply
+ * the bf16 matrices with the same MMA loop and epilogue fed by TMA.  No library GEMM is involved.
+ *   a : bf16 [batch, M, K], K contiguous, row stride lda and batch stride in ELEMENTS (multiples of 8), 16-byte aligned
+ *   b : bf16 [batch, N, K] likewise;  bias: NULL or N bf16;  d: bf16 [batch, M, N], ldd / d_batch_stride in elements
+ *   K % 8 == 0, else MXQ_ERR_UNSUPPORTED_SHAPE (the caller uses mxq_gemm_dequant)
+ */
+MXQ_API int mxq_gemm_bf16(const void *a, int64_t lda, int64_t a_batch_stride, const void *b, int64_t ldb, int64_t b_batch_stride, const void *bias,
+                  void *d, int64_t ldd, int64_t d_batch_stride, int64_t batch, int64_t M, int64_t N, int64_t K, int device, void *stream);
+
+/*
  * MX attention as one kernel  <->  the attention of the reference's MX blocks (torchmx/layers/mx_llama_attention.py:195-243,
  * mx_qwen2_attention.py): scores = Q_mx K_mx^T, P = quantize_mx(softmax(scores * scaling + mask)), out = P_mx V_mx -- with
  * neither the scores nor the codes of P written to device memory.  Both contractions run as tcgen05 block-scaled MMAs; every

@@ -16,7 +16,7 @@ GEMM_B_STATIC, GEMM_WIDE_TILES, GEMM_NO_PDL, GEMM_NO_MXF4 = 1, 2, 4, 8
 ABI_VERSION = 2
 MAX_DIMS = 6
 
-EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_gemm_dequant", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
+EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_gemm_dequant", "mxq_gemm_bf16", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
            "mxq_softmax_quantize", "mxq_flash_attention", "mxq_silu_mul_quantize", "mxq_rmsnorm", "mxq_rope", "mxq_quantize_heads", "mxq_last_error", "mxq_version", "mxq_arch")
 
 
@@ -136,6 +136,8 @@ def lib() -> ctypes.CDLL:
         L.mxq_gemm.argtypes = [ctypes.POINTER(GemmArgs), i32, vp]
         L.mxq_gemm_dequant.restype = i32
         L.mxq_gemm_dequant.argtypes = [ctypes.POINTER(GemmDequantArgs), i32, vp]
+        L.mxq_gemm_bf16.restype = i32
+        L.mxq_gemm_bf16.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp, i64, i64, i64, i64, i64, i64, i32, vp]
         L.mxq_transcode_to_e4m3.restype = i32
         L.mxq_transcode_to_e4m3.argtypes = [vp, i32, i64, vp, i32, vp]
         L.mxq_pack_operand.restype = i32

@@ -17,6 +17,8 @@ cudaError_t launch_pack_operand(const void*, int, int64_t, void*, int, cudaStrea
 cudaError_t launch_unpack_operand(const void*, int, int64_t, void*, int, cudaStream_t);
 int launch_gemm(const mxq_gemm_args_t*, int, int, cudaStream_t, char*, size_t);
 namespace gemm { int launch_gemm_dequant(const mxq_gemm_dequant_args_t*, int, cudaStream_t, char*, size_t); }
+namespace gemm { int launch_gemm_bf16(const void*, int64_t, int64_t, const void*, int64_t, int64_t, const void*, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int,
+                                       cudaStream_t, char*, size_t); }
 namespace gemm { int launch_flash_attention(const mxq_attention_args_t*, int, cudaStream_t, char*, size_t); }
 cudaError_t launch_silu_mul_quantize(const void*, const void*, int64_t, int64_t, int64_t, int64_t, int, unsigned, void*, uint8_t*, int, cudaStream_t);
 int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size_t);
@@ -260,6 +262,19 @@ int mxq_rope(const mxq_rope_args_t* a, int device, void* stream) {
     char msg[400] = "";
     const int rc = mxq::launch_rope(a, sm_count_of(scope.cur), (cudaStream_t)stream, msg, sizeof(msg));
     return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_rope: %s", msg);
+}
+
+int mxq_gemm_bf16(const void* a, int64_t lda, int64_t a_batch_stride, const void* b, int64_t ldb, int64_t b_batch_stride, const void* bias, void* d,
+                  int64_t ldd, int64_t d_batch_stride, int64_t batch, int64_t M, int64_t N, int64_t K, int device, void* stream) {
+    if (batch < 0 || M < 0 || N < 0 || K < 0) return fail(MXQ_ERR_INVALID, "mxq_gemm_bf16: negative extent");
+    if (batch == 0 || M == 0 || N == 0) return MXQ_OK;
+    if (!a || !b || !d) return fail(MXQ_ERR_INVALID, "mxq_gemm_bf16: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_gemm_bf16: selecting device");
+    char msg[400] = "";
+    const int rc = mxq::gemm::launch_gemm_bf16(a, lda, a_batch_stride, b, ldb, b_batch_stride, bias, d, ldd, d_batch_stride, batch, M, N, K, scope.cur,
+                                               (cudaStream_t)stream, msg, sizeof(msg));
+    return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_gemm_bf16: %s", msg);
 }
 
 int mxq_flash_attention(const mxq_attention_args_t* a, int device, void* stream) {

@@ -45,6 +45,7 @@ struct Smem {
     static constexpr int TOTAL = OFF_TMEM_PTR + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
     static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(RAW_STAGES * 2 * STAGE_BYTES <= OFF_LUT, "direct mode lays its operand ring over the operand + raw area");
 };
 
 struct Operand {
@@ -62,6 +63,7 @@ struct Params {
     const uint16_t* bias; uint16_t* d;
     int64_t ldd, d_batch;
     int M, N, K, m_blocks, n_blocks;
+    int direct;  // the operands ARE bf16 K-major matrices (dequantized once by K2): their tiles arrive by TMA, nobody dequantizes
 };
 
 __device__ __forceinline__ float lut_entry(int elem, uint32_t code) {
@@ -249,7 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
             }
             for (int i = 0; i < RAW_STAGES; ++i) {
                 mbar_init(&raw_full[i], 1);
-                mbar_init(&raw_empty[i], (kPerOperand / 32) * (n_fast > 0 ? n_fast : 1));
+                // (direct mode: the raw ring's barriers and shared memory serve as a 6-deep ring of bf16 operand stages)
+                mbar_init(&raw_empty[i], p.direct ? 1 : (kPerOperand / 32) * (n_fast > 0 ? n_fast : 1));
             }
             mbar_init(tmem_full, 1);
             fence_barrier_init();
@@ -258,8 +261,8 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
         tmem_alloc<128>(tmem_ptr);
     }
     if (warp == kTmaWarp && elect_one()) {
-        if (p.a.fast) tma_prefetch_desc(&map_a);
-        if (p.b.fast) tma_prefetch_desc(&map_b);
+        if (p.a.fast || p.direct) tma_prefetch_desc(&map_a);
+        if (p.b.fast || p.direct) tma_prefetch_desc(&map_b);
     }
     tc_fence_before();
     __syncthreads();
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
             constexpr int TPR = kPerOperand / TILE;
             const int row = tidx / TPR, c0 = (tidx % TPR) * (8 / TPR);
             const int r = row0 + row;
-            for (int ks = 0; ks < k_steps; ++ks) {
+            for (int ks = 0; ks < (p.direct ? 0 : k_steps); ++ks) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* dst = tile_base + stage * STAGE_BYTES + row * 128;
 #pragma unroll 4
@@ -409,26 +412,43 @@ __global__ void __launch_bounds__(kThreads, 1) mx_gemm_dequant_kernel(const __gr
         // kind::f16 descriptor: fp32 accumulator (bit 4), bf16 A and B (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
         constexpr uint64_t HI_OPERAND = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayoutSw128 << 61);
-        const uint32_t a_lo0 = smem_u32(smem + Smem::OFF_A) >> 4, b_lo0 = smem_u32(smem + Smem::OFF_B) >> 4;
+        // direct mode: RAW_STAGES stages of [A tile | B tile] laid over the whole operand + raw area (nobody dequantizes, so the TMA
+        // ring is all there is between DRAM latency and the tensor core: 6 x 32 KB in flight instead of 3)
+        const uint32_t a_lo0 = smem_u32(smem + Smem::OFF_A) >> 4, b_lo0 = (p.direct ? smem_u32(smem + STAGE_BYTES) : smem_u32(smem + Smem::OFF_B)) >> 4;
+        const uint32_t stage_step = (p.direct ? 2 * STAGE_BYTES : STAGE_BYTES) >> 4;
+        const uint32_t n_stages = p.direct ? RAW_STAGES : STAGES;
+        uint64_t* const full_b = p.direct ? raw_full : full;
+        uint64_t* const empty_b = p.direct ? raw_empty : empty;
         uint32_t stage = 0, phase = 0;
         for (int ks = 0; ks < k_steps; ++ks) {
-            mbar_wait(&full[stage], phase);
+            mbar_wait(&full_b[stage], phase);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4), b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
+                const uint32_t a_lo = a_lo0 + stage * stage_step, b_lo = b_lo0 + stage * stage_step;
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)  // 16 bf16 = 32 bytes further along the swizzle row
                     tc_mma_f16(tmem_base, HI_OPERAND | (a_lo + k * 2), HI_OPERAND | (b_lo + k * 2), idesc, (ks | k) != 0);
-                tc_commit(&empty[stage]);
+                tc_commit(&empty_b[stage]);
                 if (ks == k_steps - 1) tc_commit(tmem_full);
             }
             __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         tc_fence_before();
     } else {
-        // ================= TMA producer of the raw code tiles (operands in the fast form only) =================
-        if (n_fast > 0 && elect_one()) {
+        // ================= TMA producer: bf16 operand tiles (direct mode), or the raw code tiles of operands in the fast form =================
+        if (p.direct) {
+            if (elect_one()) {
+                uint32_t stage = 0, phase = 0;
+                for (int ks = 0; ks < k_steps; ++ks) {
+                    mbar_wait(&raw_empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&raw_full[stage], 2 * STAGE_BYTES);
+                    tma_load_3d(&map_a, &raw_full[stage], smem + stage * 2 * STAGE_BYTES, ks * BK, mb * TILE, b);
+                    tma_load_3d(&map_b, &raw_full[stage], smem + stage * 2 * STAGE_BYTES + STAGE_BYTES, ks * BK, nb * TILE, b);
+                    if (++stage == RAW_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (n_fast > 0 && elect_one()) {
             const uint32_t a_bytes = p.a.fast ? (p.a.elem == MXQ_ELEM_E2M1 ? TILE * 32 : TILE * 64) : 0;
             const uint32_t b_bytes = p.b.fast ? (p.b.elem == MXQ_ELEM_E2M1 ? TILE * 32 : TILE * 64) : 0;
             uint32_t rs = 0, rphase = 0;
@@ -469,6 +489,39 @@ static void fill_operand(Operand& o, const mxq_operand_t& s, int64_t rows, int64
 
 }  // namespace dq
 
+// D[b] = A[b] B[b]^T (+ bias) on bf16 operands that were dequantized ONCE (K2): the same MMA loop and epilogue with the operand
+// tiles arriving by TMA.  For large M x N this beats dequantizing inside the GEMM, which repeats the work for every output tile.
+int launch_gemm_bf16(const void* a, int64_t lda, int64_t a_bs, const void* b, int64_t ldb, int64_t b_bs, const void* bias, void* d, int64_t ldd, int64_t d_bs,
+                     int64_t batch, int64_t M, int64_t N, int64_t K, int device, cudaStream_t stream, char* msg, size_t msg_len) {
+    using namespace dq;
+    if (M > 0x7FFFFFFF || N > 0x7FFFFFFF || K > 0x7FFFFFFF || K % 8 || lda % 8 || ldb % 8 || a_bs % 8 || b_bs % 8 || ((uintptr_t)a % 16) || ((uintptr_t)b % 16)) {
+        snprintf(msg, msg_len, "bf16 operands need K %% 8 == 0 and 16-byte aligned rows");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    dq::Params p;
+    memset(&p, 0, sizeof(p));
+    p.a.rows = (int)M; p.b.rows = (int)N;
+    p.bias = (const uint16_t*)bias; p.d = (uint16_t*)d;
+    p.ldd = ldd; p.d_batch = d_bs;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.m_blocks = (int)((M + TILE - 1) / TILE);
+    p.n_blocks = (int)((N + TILE - 1) / TILE);
+    p.direct = 1;
+    const int64_t ctas = (int64_t)p.m_blocks * p.n_blocks * batch;
+    if (ctas > 0x7FFFFFFF) { snprintf(msg, msg_len, "too many output tiles"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+    CUtensorMap maps[2];
+    if (!cached_bf16_operand_map(&maps[0], a, K, M, batch, lda, a_bs, TILE, device) || !cached_bf16_operand_map(&maps[1], b, K, N, batch, ldb, b_bs, TILE, device)) {
+        snprintf(msg, msg_len, "cuTensorMapEncodeTiled failed");
+        return MXQ_ERR_CUDA;
+    }
+    cudaError_t e = ensure_smem_attr((const void*)mx_gemm_dequant_kernel, Smem::DYN_BYTES, device);
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    mx_gemm_dequant_kernel<<<(unsigned)ctas, dq::kThreads, Smem::DYN_BYTES, stream>>>(maps[0], maps[1], p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "launch (bf16 gemm): %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    return MXQ_OK;
+}
+
 int launch_gemm_dequant(const mxq_gemm_dequant_args_t* a, int device, cudaStream_t stream, char* msg, size_t msg_len) {
     using namespace dq;
     if (a->M > 0x7FFFFFFF || a->N > 0x7FFFFFFF || a->K > 0x7FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
@@ -480,6 +533,7 @@ int launch_gemm_dequant(const mxq_gemm_dequant_args_t* a, int device, cudaStream
     p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
     p.m_blocks = (int)((a->M + TILE - 1) / TILE);
     p.n_blocks = (int)((a->N + TILE - 1) / TILE);
+    p.direct = 0;
     const int64_t ctas = (int64_t)p.m_blocks * p.n_blocks * a->batch;
     if (ctas > 0x7FFFFFFF) { snprintf(msg, msg_len, "too many output tiles"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
     CUtensorMap maps[2];

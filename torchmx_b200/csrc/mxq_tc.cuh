@@ -448,6 +448,9 @@ bool cached_scale_map(CUtensorMap* map, const void* base, int64_t scale_bytes_pe
 // raw code bytes [batch][rows][k_bytes] (K3d): box = box_bytes x box_rows, no swizzle, bytes / rows past the edge read as zero
 bool cached_raw_map(CUtensorMap* map, const void* base, int64_t k_bytes, int64_t rows, int64_t batch, int64_t ld, int64_t batch_stride, int box_bytes,
                     int box_rows, int device);
+// bf16 operand [batch][rows][K], K contiguous: box = 64 elements (one 128-byte swizzle row) x box_rows, OOB reads as zero
+bool cached_bf16_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows, int64_t batch, int64_t ld, int64_t batch_stride, int box_rows,
+                             int device);
 // D: [batch][M][N] bf16, box = 64 columns x 32 rows, 128B swizzle (one epilogue warp's staging buffer)
 bool cached_d_map(CUtensorMap* map, void* base, int64_t N, int64_t M, int64_t batch, int64_t ldd, int64_t batch_stride, int device);
 // The dynamic shared-memory opt-in is a per-(kernel, device) attribute: set the first time a kernel is launched on a device,

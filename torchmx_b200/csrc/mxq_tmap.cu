@@ -150,6 +150,27 @@ bool cached_d_map(CUtensorMap* map, void* base, int64_t N, int64_t M, int64_t ba
     });
 }
 
+bool cached_bf16_operand_map(CUtensorMap* map, const void* base, int64_t K, int64_t rows, int64_t batch, int64_t ld, int64_t batch_stride, int box_rows,
+                             int device) {
+    (void)device;
+    if (batch <= 1) batch_stride = ld * rows;
+    Key key;
+    memset(&key, 0, sizeof(key));
+    key.kind = 4; key.base = (uint64_t)(uintptr_t)base;
+    key.v[0] = K; key.v[1] = rows; key.v[2] = batch; key.v[3] = ld; key.v[4] = batch_stride;
+    key.box_rows = box_rows;
+    return lookup_or_encode(key, map, [&](CUtensorMap* m) {
+        EncodeTiledFn fn = encode_fn();
+        if (!fn) return false;
+        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+        cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)batch_stride * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    });
+}
+
 cudaError_t ensure_smem_attr(const void* kernel, int bytes, int device) {
     struct Seen { const void* kernel; uint64_t devices; };
     static Seen seen[128];

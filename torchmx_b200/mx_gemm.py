@@ -241,6 +241,9 @@ def _fill_operand(o: "_C.Operand", t: MXTensor, rows_dim: int, k_dim: int, batch
     return d, s
 
 
+DIRECT_MIN_ROWS = int(os.environ.get("MXQ_DEQUANT_ONCE_MIN_ROWS", 512))  # M and N from which operands are dequantized once (see try_dequant_gemm)
+
+
 def try_dequant_gemm(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back) -> Optional[torch.Tensor]:
     """The contraction of two MXTensors of ANY element type / block size / block orientation / padding / strides as one
     kernel (`mxq_gemm_dequant`): what the reference computes as dequantize + bf16 matmul (torchmx/ops.py:29-41, 60-68,
@@ -279,6 +282,20 @@ def try_dequant_gemm(aten_op, a: MXTensor, b: MXTensor, extra_front, extra_back)
             return None
         if bias.dtype != torch.bfloat16 or not bias.is_contiguous():
             return None
+    if M >= DIRECT_MIN_ROWS and N >= DIRECT_MIN_ROWS and K % 8 == 0 and a.dim() >= 2:
+        # large outputs: the fused kernel dequantizes every operand element once per 128 x 128 output tile it touches (N / 128 resp.
+        # M / 128 times); dequantizing each operand ONCE (K2, any layout / block size / padding) and running the same tensor-core
+        # loop on the bf16 matrices is what the reference's recipe does, and is ~4x faster at 8192^3 -- still no library GEMM
+        a_hp = a.to_dtype(torch.bfloat16).reshape(batch, M, K)
+        b_hp = (b if b_k == -1 else b.transpose(-1, -2)).to_dtype(torch.bfloat16).reshape(batch, N, K)
+        out = torch.empty(lead + (N,), dtype=torch.bfloat16, device=a._data.device)
+        rc = _C.lib().mxq_gemm_bf16(a_hp.data_ptr(), K, M * K, b_hp.data_ptr(), K, N * K, bias.data_ptr() if bias is not None else None, out.data_ptr(), N, M * N,
+                                    batch, M, N, K, out.device.index, _stream_ptr(out))
+        if rc != _C.ERR_UNSUPPORTED_SHAPE:
+            _C.check(rc, "mxq_gemm_bf16")
+            stats["dequant_gemm"] += 1
+            stats["dequant_once_gemm"] = stats.get("dequant_once_gemm", 0) + 1
+            return out
     g = _C.GemmDequantArgs()
     keep_a = _fill_operand(g.a, a, -2, -1, batched, collapse=aten_op is aten.linear.default)
     keep_b = _fill_operand(g.b, b, b_rows, b_k, batched, False)
