@@ -37,7 +37,9 @@ constexpr int QT = 128;     // query rows per warpgroup
 constexpr int KC = 128;     // keys per chunk: four MX blocks of P = one 32-bit scale word per row
 constexpr int HD = 128;     // head_dim
 constexpr int K_STAGES = 3, V_STAGES = 2;
-constexpr int kThreads = 256 + 96;
+constexpr int kSoftmaxWarps = 16;
+constexpr int kThreads = kSoftmaxWarps * 32 + 96;
+constexpr int kWgThreads = 256;  // softmax threads per query tile: two per row
 constexpr int TILE_BYTES = 128 * 128;
 
 struct Smem {
@@ -51,7 +53,9 @@ struct Smem {
     static constexpr int OFF_SFP = OFF_SFV + V_STAGES * 512;
     static constexpr int OFF_CMAX = OFF_SFP + 2 * 512;            // [wg][chunk <= 64][row] bf16: largest score of the chunk, from pass A
     static constexpr int OFF_LIVE = OFF_CMAX + 2 * 64 * 128 * 2;  // [wg][2] words: chunks with a row that still counts after the row maximum is known
-    static constexpr int OFF_BAR = OFF_LIVE + 16;
+    static constexpr int OFF_XCH = OFF_LIVE + 16;                 // [wg][parity 2][sub 2][value 2][row 128] fp32: what a row's two threads exchange per chunk
+    static constexpr int OFF_XMAX = OFF_XCH + 2 * 1024 * 4;       // [wg][sub][row] fp32: partial row maxima
+    static constexpr int OFF_BAR = OFF_XMAX + 2 * 256 * 4;
     // q_full, qsf_full, k_full/ksf_full/k_empty[K_STAGES], v_full/vsf_full/v_empty[V_STAGES], sa_full/sa_free[2][2],
     // sc_full/sc_free/p_full/p_free/o_full[2]
     static constexpr int NUM_BARS = 2 + 3 * K_STAGES + 3 * V_STAGES + 18 + 2;
@@ -157,25 +161,25 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     }
     const int n_cta = max(nv[0], nv[1]);
 
-    if (warp == 8 && elect_one()) {
+    if (warp == kSoftmaxWarps && elect_one()) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_k);
         tma_prefetch_desc(&map_v);
     }
-    if (warp == 9 && elect_one()) {
+    if (warp == kSoftmaxWarps + 1 && elect_one()) {
         mbar_init(q_full, 1);
         mbar_init(qsf_full, 1);
         for (int i = 0; i < K_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&ksf_full[i], 1); mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < V_STAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&vsf_full[i], 1); mbar_init(&v_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&sa_full[i], 1); mbar_init(&sa_free[i], QT); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&sa_full[i], 1); mbar_init(&sa_free[i], kWgThreads); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&sc_full[i], 1); mbar_init(&sc_free[i], QT); mbar_init(&p_full[i], QT); mbar_init(&p_free[i], 1); mbar_init(&o_full[i], 1);
-            mbar_init(&scan_done[i], QT);
+            mbar_init(&sc_full[i], 1); mbar_init(&sc_free[i], kWgThreads); mbar_init(&p_full[i], kWgThreads); mbar_init(&p_free[i], 1); mbar_init(&o_full[i], 1);
+            mbar_init(&scan_done[i], kWgThreads);
         }
         for (int i = 0; i < 4; ++i) live_words[i] = 0;
         fence_barrier_init();
     }
-    if (warp == 10) tmem_alloc<512>(tmem_ptr);
+    if (warp == kSoftmaxWarps + 2) tmem_alloc<512>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -198,9 +202,14 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         }
     };
 
-    if (warp < 8) {
+    if (warp < kSoftmaxWarps) {
         // ================= softmax warpgroups =================
-        const int wg = warp >> 2, quad = warp & 3;
+        // 16 warps: query tile wg (0 / 1) x sub (0 / 1) x TMEM lane quadrant.  Thread = (query row, sub): of every 64-column score
+        // tile the sub-0 thread of a row owns the first MX block (columns 0..31), the sub-1 thread the second -- four softmax warps
+        // per scheduler instead of two (the arithmetic is latency-bound per warp).  What a row's two threads must agree on -- the
+        // row maximum, the per-block sums in K4a's order, the chunk maxima -- goes through a few KB of shared memory and a named
+        // barrier of the 256 threads of the query tile.
+        const int wg = warp >> 3, sub = (warp >> 2) & 1, quad = warp & 3;
         const int r = quad * 32 + lane;                 // row inside the warpgroup's tile = TMEM lane
         const int q = qt * 2 * QT + wg * QT + r;        // query row
         const bool row_live = active[wg] && q < p.q_len;
@@ -210,29 +219,32 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         const int tpr = p.kv_len / 32;
         const bool hw_exact = (p.flags & MXQ_FLAG_HW_EXACT) != 0;
         uint8_t* p_tile = smem + Smem::OFF_P + wg * TILE_BYTES + r * 128;
-        uint32_t* sfp_word = reinterpret_cast<uint32_t*>(smem + Smem::OFF_SFP + wg * 512 + 16 * (r & 31) + 4 * (r >> 5));
+        uint8_t* sfp_bytes = smem + Smem::OFF_SFP + wg * 512 + 16 * (r & 31) + 4 * (r >> 5);
         constexpr int NO = (ELEM == MXQ_ELEM_E2M1) ? 4 : 8;
         uint8_t* dump_codes = (p.p_codes != nullptr && row_live) ? p.p_codes + ((int64_t)bh * p.q_len + q) * tpr * (NO * 4) : nullptr;
         uint8_t* dump_scales = (p.p_codes != nullptr && row_live) ? p.p_scales + ((int64_t)bh * p.q_len + q) * tpr : nullptr;
+        float* xch = reinterpret_cast<float*>(smem + Smem::OFF_XCH) + wg * 1024;  // [parity 2][sub 2][value 2][row 128]
+        auto wg_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory"); };
+        auto dump_zero = [&](int t, int sc) {
+            if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(0, 0, 0, 0);
+            else { *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(0, 0, 0, 0); }
+            dump_scales[t] = (uint8_t)sc;
+        };
 
         float row_max = -INFINITY, row_sum = 0.0f;
         // passes A and B keep TWO 64-column score tiles per warpgroup inside its (still unused) output accumulator, so the tensor
         // core works one tile ahead of the softmax threads; pass C has the accumulator in use and a single tile
-        const uint32_t tm_sa = tm_lane + TM_O + wg * 128, tm_sc = tm_lane + TM_S + wg * 64;
+        const uint32_t tm_sa = tm_lane + TM_O + wg * 128 + sub * 32, tm_sc = tm_lane + TM_S + wg * 64 + sub * 32;
         uint32_t ab_item = 0, c_par = 0, pfree_par = 0;
-        auto take_tile = [&](uint32_t taddr, uint64_t* full, uint32_t parity, uint64_t* free_bar, uint32_t (&v)[64]) {
+        auto take_tile = [&](uint32_t taddr, uint64_t* full, uint32_t parity, uint64_t* free_bar, uint32_t (&v)[32]) {
             mbar_wait(full, parity);
             tc_fence_after();
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32b_x32(taddr, v0);
-            tmem_ld_32x32b_x32(taddr + 32, v1);
+            tmem_ld_32x32b_x32(taddr, v);
             tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = v0[i]; v[32 + i] = v1[i]; }
             tc_fence_before();
             mbar_arrive(free_bar);  // the tensor core may overwrite the tile while we compute
         };
-        auto take_ab = [&](uint32_t (&v)[64]) {
+        auto take_ab = [&](uint32_t (&v)[32]) {
             const uint32_t buf = ab_item & 1;
             take_tile(tm_sa + buf * 64, &sa_full[wg * 2 + buf], (ab_item >> 1) & 1, &sa_free[wg * 2 + buf], v);
             ++ab_item;
@@ -243,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             return vis;
         };
         // the 32 scores of a block as the softmax sees them: bf16 matmul result, * scaling, + mask, causal rule (mxq_softmax_core.cuh)
-        auto scores_of = [&](const uint32_t* raw, int t, int vis, float (&x)[32]) {
+        auto scores_of = [&](const uint32_t (&raw)[32], int t, int vis, float (&x)[32]) {
             uint32_t w[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]));
@@ -259,46 +271,53 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             // ---- pass A: row maximum.  Without an additive mask the map score -> bf16(bf16(score) * scaling) is monotone
             // (scaling > 0), so the maximum of the mapped scores is the map of the maximum raw score: one max per element.
             const bool fast_max = !TABLE && p.scaling > 0.0f;
-            float raw_max = -INFINITY, chunk_max = -INFINITY;
+            float part_max = -INFINITY, chunk_max = -INFINITY;
             uint16_t* cmax = reinterpret_cast<uint16_t*>(smem + Smem::OFF_CMAX) + wg * 64 * 128 + r;
             for (int j = 0; j < my_n; ++j) {
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v[64];
+                    uint32_t v[32];
                     take_ab(v);
-#pragma unroll
-                    for (int blk = 0; blk < 2; ++blk) {
-                        const int t = 4 * j + 2 * hf + blk;
-                        const int vis = visible(t);
-                        if (vis == 0) continue;
+                    const int t = 4 * j + 2 * hf + sub;
+                    const int vis = visible(t);
+                    if (vis > 0) {
+                        float m;
                         if (fast_max) {
-                            float m = -INFINITY;
                             if (vis == 32) {
-                                m = __uint_as_float(v[32 * blk]);
+                                m = __uint_as_float(v[0]);
 #pragma unroll
-                                for (int i = 1; i < 31; i += 2) m = sm::max_nan3(m, __uint_as_float(v[32 * blk + i]), __uint_as_float(v[32 * blk + i + 1]));
-                                m = sm::max_nan(m, __uint_as_float(v[32 * blk + 31]));
+                                for (int i = 1; i < 31; i += 2) m = sm::max_nan3(m, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                                m = sm::max_nan(m, __uint_as_float(v[31]));
                             } else {
+                                m = -INFINITY;
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) m = sm::max_nan(m, i < vis ? __uint_as_float(v[32 * blk + i]) : -INFINITY);
+                                for (int i = 0; i < 32; ++i) m = sm::max_nan(m, i < vis ? __uint_as_float(v[i]) : -INFINITY);
                             }
-                            raw_max = sm::max_nan(raw_max, m);
                         } else {
                             float x[32];
-                            scores_of(&v[32 * blk], t, vis, x);
-                            const float m = sm::block_max_only(x);
-                            row_max = sm::max_nan(row_max, m);
-                            chunk_max = sm::max_nan(chunk_max, m);
+                            scores_of(v, t, vis, x);
+                            m = sm::block_max_only(x);
                         }
+                        part_max = sm::max_nan(part_max, m);
+                        chunk_max = sm::max_nan(chunk_max, m);
                     }
-                    if (use_table && hf == 1) {
-                        cmax[j * 128] = (uint16_t)pack_bf16x2(chunk_max, 0.0f);  // (the scores are bf16 values: exact)
+                    if (use_table && hf == 1) {  // the chunk's largest score over both threads of the row (the scores are bf16 values: exact)
+                        float* slot = xch + (j & 1) * 512;
+                        slot[sub * 256 + r] = chunk_max;
+                        wg_sync();
+                        if (sub == 0) cmax[j * 128] = (uint16_t)pack_bf16x2(sm::max_nan(chunk_max, slot[256 + r]), 0.0f);
                         chunk_max = -INFINITY;
                     }
                 }
             }
+            {
+                float* slot = reinterpret_cast<float*>(smem + Smem::OFF_XMAX) + wg * 256;
+                slot[sub * 128 + r] = part_max;
+                wg_sync();  // (also: every chunk maximum of this query tile is in the table)
+                row_max = sm::max_nan(part_max, slot[(sub ^ 1) * 128 + r]);
+            }
             if (fast_max) {
-                const uint32_t r1 = pack_bf16x2(raw_max, 0.0f);
+                const uint32_t r1 = pack_bf16x2(row_max, 0.0f);
                 const uint32_t r2 = pack_bf16x2(__uint_as_float(r1 << 16) * p.scaling, 0.0f);
                 row_max = __uint_as_float(r2 << 16);
             }
@@ -316,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                 my_live = (uint64_t)live_words[2 * wg] | ((uint64_t)live_words[2 * wg + 1] << 32);
             }
             // ---- pass B: row sum of expf(x - max), the per-block sums added in K4a's order (sm::sum_layout): blocks in order, or
-            // butterfly-reduced groups of 8 added in order
+            // butterfly-reduced groups of 8 added in order.  Both threads of a row add all four sums of a chunk, in the same order.
             {
                 float acc = 0.0f, a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
                 bool have_acc = false;
@@ -345,23 +364,30 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                         for (int bl = 0; bl < 4; ++bl) add_block(4 * j + bl, 0.0f);
                         continue;
                     }
+                    float mine[2];
 #pragma unroll 1
                     for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t v[64];
+                        uint32_t v[32];
                         take_ab(v);
-#pragma unroll
-                        for (int blk = 0; blk < 2; ++blk) {
-                            const int t = 4 * j + 2 * hf + blk;
-                            const int vis = visible(t);
-                            float s = 0.0f;
-                            if (vis > 0) {
-                                float x[32];
-                                scores_of(&v[32 * blk], t, vis, x);
-                                if (!sm::block_dead(vis, sm::block_max_only(x), row_max)) s = sm::exp_sum(x, row_max);
-                            }
-                            add_block(t, s);
+                        const int t = 4 * j + 2 * hf + sub;
+                        const int vis = visible(t);
+                        float s = 0.0f;
+                        if (vis > 0) {
+                            float x[32];
+                            scores_of(v, t, vis, x);
+                            if (!sm::block_dead(vis, sm::block_max_only(x), row_max)) s = sm::exp_sum(x, row_max);
                         }
+                        mine[hf] = s;
                     }
+                    float* slot = xch + (j & 1) * 512;
+                    slot[sub * 256 + r] = mine[0];
+                    slot[sub * 256 + 128 + r] = mine[1];
+                    wg_sync();
+                    const float o0 = slot[(sub ^ 1) * 256 + r], o1 = slot[(sub ^ 1) * 256 + 128 + r];
+                    add_block(4 * j + 0, sub ? o0 : mine[0]);
+                    add_block(4 * j + 1, sub ? mine[0] : o0);
+                    add_block(4 * j + 2, sub ? o1 : mine[1]);
+                    add_block(4 * j + 3, sub ? mine[1] : o1);
                 }
                 if (p.layout != 0 && ((4 * my_n) & 7) != 0) {  // a half-filled last group (the rest of it: hidden blocks, sum 0)
                     const float g = ((a0 + 0.0f) + (a2 + 0.0f)) + ((a1 + 0.0f) + (a3 + 0.0f));
@@ -370,79 +396,68 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                 row_sum = acc;
             }
             // ---- pass C: the codes and scales of P, into the operand tile of the second contraction
-            uint32_t sf_word = 0;
             bool p_started = false;
             for (int j = 0; j < my_n; ++j) {
                 if (!((my_live >> j) & 1)) {  // +0 codes for the whole chunk: nothing for the tensor core to add
                     if (dump_codes != nullptr) {
                         const int sc = sm::dead_block_scale<ELEM>(row_max, row_sum);
-                        for (int t = 4 * j; t < 4 * j + 4; ++t) {
-                            if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(0, 0, 0, 0);
-                            else { *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(0, 0, 0, 0); }
-                            dump_scales[t] = (uint8_t)sc;
-                        }
+                        dump_zero(4 * j + sub, sc);
+                        dump_zero(4 * j + 2 + sub, sc);
                     }
                     continue;
                 }
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v[64];
+                    uint32_t v[32];
                     take_tile(tm_sc, &sc_full[wg], c_par, &sc_free[wg], v);
                     c_par ^= 1;
+                    const int bl = 2 * hf + sub;   // block inside the chunk
+                    const int t = 4 * j + bl;      // block inside the row
+                    const int vis = visible(t);
+                    float x[32];
+                    float m = -INFINITY, lo = INFINITY;
+                    if (vis > 0) {
+                        scores_of(v, t, vis, x);
+                        sm::block_max(x, m, lo);
+                    }
+                    uint32_t c[8];
+                    int sc;
+                    if (sm::block_dead(vis, m, row_max)) {
 #pragma unroll
-                    for (int blk = 0; blk < 2; ++blk) {
-                        const int bl = 2 * hf + blk;   // block inside the chunk
-                        const int t = 4 * j + bl;      // block inside the row
-                        const int vis = visible(t);
-                        float x[32];
-                        float m = -INFINITY, lo = INFINITY;
-                        if (vis > 0) {
-                            scores_of(&v[32 * blk], t, vis, x);
-                            sm::block_max(x, m, lo);
-                        }
-                        uint32_t c[8];
-                        int sc;
-                        if (sm::block_dead(vis, m, row_max)) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) c[i] = 0;
-                            sc = row_live ? sm::dead_block_scale<ELEM>(row_max, row_sum) : 127;
-                            if (dump_codes != nullptr) {
-                                if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(0, 0, 0, 0);
-                                else { *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(0, 0, 0, 0); }
+                        for (int i = 0; i < 8; ++i) c[i] = 0;
+                        sc = row_live ? sm::dead_block_scale<ELEM>(row_max, row_sum) : 127;
+                        if (dump_codes != nullptr) dump_zero(t, sc);
+                    } else {
+                        sm::exp_sum(x, row_max);
+                        uint32_t w[16];
+                        sm::normalize(x, lo, row_max, row_sum, w);
+                        uint32_t out[NO];
+                        sc = quantize_block32<ELEM>(w, hw_exact, out);
+                        if (dump_codes != nullptr) {
+                            if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+                            else {
+                                *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(out[0], out[1], out[2], out[3]);
+                                *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(out[4], out[5], out[6], out[7]);
                             }
-                        } else {
-                            sm::exp_sum(x, row_max);
-                            uint32_t w[16];
-                            sm::normalize(x, lo, row_max, row_sum, w);
-                            uint32_t out[NO];
-                            sc = quantize_block32<ELEM>(w, hw_exact, out);
-                            if (dump_codes != nullptr) {
-                                if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(out[0], out[1], out[2], out[3]);
-                                else {
-                                    *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(out[0], out[1], out[2], out[3]);
-                                    *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(out[4], out[5], out[6], out[7]);
-                                }
-                            }
-                            container_bytes<ELEM>(out, c);
+                            dump_scales[t] = (uint8_t)sc;
                         }
-                        if (dump_scales != nullptr) dump_scales[t] = (uint8_t)sc;
-                        if (bl == 0) {
-                            sf_word = 0;
-                            if (p_started) {  // the tensor core must be done with the previous chunk's codes before they are overwritten
-                                mbar_wait(&p_free[wg], pfree_par);
-                                pfree_par ^= 1;
-                            }
-                            p_started = true;
+                        container_bytes<ELEM>(out, c);
+                    }
+                    if (hf == 0) {
+                        if (p_started) {  // the tensor core must be done with the previous chunk's codes before they are overwritten
+                            mbar_wait(&p_free[wg], pfree_par);
+                            pfree_par ^= 1;
                         }
-                        sf_word |= (uint32_t)sc << (8 * bl);
-                        // K-major 128B-swizzled operand tile: 16-byte chunk cc of row r lives at chunk cc ^ (r & 7)
-                        *reinterpret_cast<uint4*>(p_tile + (((2 * bl) ^ (r & 7)) << 4)) = make_uint4(c[0], c[1], c[2], c[3]);
-                        *reinterpret_cast<uint4*>(p_tile + (((2 * bl + 1) ^ (r & 7)) << 4)) = make_uint4(c[4], c[5], c[6], c[7]);
-                        if (bl == 3) {
-                            *sfp_word = sf_word;
-                            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-                            mbar_arrive(&p_full[wg]);
-                        }
+                        p_started = true;
+                    }
+                    // K-major 128B-swizzled operand tile: 16-byte chunk cc of row r lives at chunk cc ^ (r & 7); the block's scale is
+                    // byte bl of the row's 32-bit scale word in the tcgen05.cp layout
+                    *reinterpret_cast<uint4*>(p_tile + (((2 * bl) ^ (r & 7)) << 4)) = make_uint4(c[0], c[1], c[2], c[3]);
+                    *reinterpret_cast<uint4*>(p_tile + (((2 * bl + 1) ^ (r & 7)) << 4)) = make_uint4(c[4], c[5], c[6], c[7]);
+                    sfp_bytes[bl] = (uint8_t)sc;
+                    if (hf == 1) {
+                        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                        mbar_arrive(&p_full[wg]);
                     }
                 }
             }
@@ -451,20 +466,16 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             // chunks this warpgroup skipped (hidden by the causal rule): their codes are +0 and the scale is that of a zero block
             if (dump_codes != nullptr) {
                 const int sc = sm::dead_block_scale<ELEM>(row_max, row_sum);
-                for (int t = 4 * my_n; t < tpr; ++t) {
-                    if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(0, 0, 0, 0);
-                    else { *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(0, 0, 0, 0); }
-                    dump_scales[t] = (uint8_t)sc;
-                }
+                for (int t = 4 * my_n + sub; t < tpr; t += 2) dump_zero(t, sc);
             }
-            // ---- drain the output accumulator: thread = row, 128 bf16 = 256 contiguous bytes ----
+            // ---- drain the output accumulator: thread = (row, column half), 64 bf16 = 128 contiguous bytes ----
             mbar_wait(&o_full[wg], 0);
             tc_fence_after();
-            uint16_t* orow = p.out + (int64_t)b * p.out_sb + (int64_t)h * p.out_sh + (int64_t)q * p.out_sq;
+            uint16_t* orow = p.out + (int64_t)b * p.out_sb + (int64_t)h * p.out_sh + (int64_t)q * p.out_sq + sub * 64;
 #pragma unroll 1
-            for (int cg = 0; cg < 4; ++cg) {
+            for (int cg = 0; cg < 2; ++cg) {
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(tm_lane + TM_O + wg * 128 + cg * 32, v);
+                tmem_ld_32x32b_x32(tm_lane + TM_O + wg * 128 + sub * 64 + cg * 32, v);
                 tmem_ld_wait();
                 if (row_live) {
 #pragma unroll
@@ -480,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             }
             tc_fence_before();
         }
-    } else if (warp == 8) {
+    } else if (warp == kSoftmaxWarps) {
         // ================= TMA producer =================
         if (elect_one()) {
             mbar_arrive_expect_tx(q_full, (active[1] ? 2 : 1) * TILE_BYTES);
@@ -509,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kSoftmaxWarps + 1) {
         // ================= MMA issuer =================
         uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
         uint32_t pfull_par[2] = {0, 0};
@@ -682,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         }
     }
     __syncthreads();
-    if (warp == 10) {
+    if (warp == kSoftmaxWarps + 2) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
