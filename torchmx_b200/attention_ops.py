@@ -100,7 +100,7 @@ def flash_attention(q_mx: MXTensor, k_mx: MXTensor, vt_mx: MXTensor, scaling: fl
         return None
     b, h, q_len, d = q_mx.shape
     hk, kv_len = k_mx.shape[1], k_mx.shape[2]
-    if d != 128 or k_mx.shape != (b, hk, kv_len, d) or vt_mx.shape != (b, hk, d, kv_len) or h % hk or kv_len % 128 or kv_len < q_len or q_len == 0:
+    if d != 128 or k_mx.shape != (b, hk, kv_len, d) or vt_mx.shape != (b, hk, d, kv_len) or h % hk or kv_len % 32 or kv_len < q_len or q_len == 0:
         return None
     masked = causal or mask is not None
     if kv_len > (8192 if masked else 1024):  # (rows whose block sums K4a adds in an order K4b does not reproduce)

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     const int bh = (int)(blockIdx.x % bh_count);
     const int b = bh / p.heads, h = bh - b * p.heads;
     const int bhk = b * p.kv_heads + h / (p.heads / p.kv_heads);  // grouped-query attention: the key / value head of this query head
-    const int n_total = p.kv_len / KC;
+    const int n_total = (p.kv_len + KC - 1) / KC;  // (kv_len % 32 == 0; the last chunk may hold 1..3 blocks: the rest reads as zero and is hidden)
     int nv[2];
     bool active[2];
 #pragma unroll
@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         float* xch = reinterpret_cast<float*>(smem + Smem::OFF_XCH) + wg * 1024;  // [parity 2][sub 2][value 2][row 128]
         auto wg_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory"); };
         auto dump_zero = [&](int t, int sc) {
+            if (t >= tpr) return;  // (a block past the end of a ragged last chunk)
             if constexpr (NO == 4) *reinterpret_cast<uint4*>(dump_codes + t * 16) = make_uint4(0, 0, 0, 0);
             else { *reinterpret_cast<uint4*>(dump_codes + t * 32) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(dump_codes + t * 32 + 16) = make_uint4(0, 0, 0, 0); }
             dump_scales[t] = (uint8_t)sc;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             ++ab_item;
         };
         auto visible = [&](int t) {  // how many of block t's 32 keys this query row may see
-            int vis = row_live ? 32 : 0;
+            int vis = (row_live && t < tpr) ? 32 : 0;
             if (p.causal && row_live) vis = min(32, max(0, q + p.causal_offset + 1 - t * 32));
             return vis;
         };
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                     if (sm::block_dead(vis, m, row_max)) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) c[i] = 0;
-                        sc = row_live ? sm::dead_block_scale<ELEM>(row_max, row_sum) : 127;
+                        sc = (row_live && t < tpr) ? sm::dead_block_scale<ELEM>(row_max, row_sum) : 127;
                         if (dump_codes != nullptr) dump_zero(t, sc);
                     } else {
                         sm::exp_sum(x, row_max);
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         const uint8_t* vsrc = p.v_sf + (int64_t)bhk * HD * vld;
         auto load_k = [&](int j, uint32_t (&w)[4]) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) w[i] = __ldg(ksrc + j * KC + i * 32 + lane);
+            for (int i = 0; i < 4; ++i) w[i] = __ldg(ksrc + min(j * KC + i * 32 + lane, p.kv_len - 1));  // (keys past kv_len: zero codes, hidden)
         };
         uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
         uint64_t need = ~0ull;
@@ -675,8 +676,19 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
                 uint32_t kw[4], vw[4];
                 load_k(j, kw);
                 if (pass == 2) {
+                    if ((vld & 3) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) vw[i] = __ldg(reinterpret_cast<const uint32_t*>(vsrc + (int64_t)(i * 32 + lane) * vld + 4 * j));
+                        for (int i = 0; i < 4; ++i) vw[i] = __ldg(reinterpret_cast<const uint32_t*>(vsrc + (int64_t)(i * 32 + lane) * vld + 4 * j));
+                    } else {  // ragged kv_len: a channel's scale row is not a whole number of words
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint8_t* row = vsrc + (int64_t)(i * 32 + lane) * vld;
+                            uint32_t w = 0;
+#pragma unroll
+                            for (int bb = 0; bb < 4; ++bb) w |= (uint32_t)(4 * j + bb < vld ? __ldg(row + 4 * j + bb) : 127) << (8 * bb);
+                            vw[i] = w;
+                        }
+                    }
                 }
                 mbar_wait(&k_empty[ks], kph ^ 1);
                 *reinterpret_cast<uint4*>(smem + Smem::OFF_SFK + ks * 1024 + 16 * lane) = make_uint4(kw[0], kw[1], 0u, 0u);        // keys 0..63 of the chunk
@@ -704,8 +716,8 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
 int launch_flash_attention(const mxq_attention_args_t* a, int device, cudaStream_t stream, char* msg, size_t msg_len) {
     using namespace fa;
     auto fmt_ok = [](int f) { return f == MXQ_OPERAND_E4M3_BYTES || f == MXQ_OPERAND_E5M2_BYTES; };
-    if (a->head_dim != HD || a->kv_len % KC || a->kv_len < KC || a->q_len < 1 || a->kv_len < a->q_len || a->heads % a->kv_heads) {
-        snprintf(msg, msg_len, "needs head_dim == 128, kv_len %% 128 == 0, kv_len >= q_len, heads %% kv_heads == 0");
+    if (a->head_dim != HD || a->kv_len % 32 || a->kv_len < 32 || a->q_len < 1 || a->kv_len < a->q_len || a->heads % a->kv_heads) {
+        snprintf(msg, msg_len, "needs head_dim == 128, kv_len %% 32 == 0, kv_len >= q_len, heads %% kv_heads == 0");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
     if (!fmt_ok(a->q_format) || !fmt_ok(a->k_format) || !fmt_ok(a->v_format) || a->p_elem == MXQ_ELEM_INT8) {
@@ -720,7 +732,8 @@ int launch_flash_attention(const mxq_attention_args_t* a, int device, cudaStream
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
     auto al16 = [](const void* ptr) { return ((uintptr_t)ptr % 16) == 0; };
-    if (!al16(a->q_codes) || !al16(a->k_codes) || !al16(a->vt_codes) || ((uintptr_t)a->q_scales % 4) || ((uintptr_t)a->k_scales % 4) || ((uintptr_t)a->vt_scales % 4) ||
+    if (!al16(a->q_codes) || !al16(a->k_codes) || !al16(a->vt_codes) || ((uintptr_t)a->q_scales % 4) || ((uintptr_t)a->k_scales % 4) ||
+        ((a->kv_len % KC) == 0 && ((uintptr_t)a->vt_scales % 4)) ||
         !al16(a->out) || (a->out_batch_stride % 8) || (a->out_head_stride % 8) || (a->out_row_stride % 8) || (a->p_codes && !al16(a->p_codes))) {
         snprintf(msg, msg_len, "misaligned operand");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
