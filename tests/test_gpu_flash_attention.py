@@ -77,7 +77,8 @@ CASES = [
     (1, 2, 2, 256, 640, "mask+pad"),    # + padded keys at the end
     (1, 1, 1, 512, 512, "mask+causal"),
     # kv_len a multiple of 32 but not of 128: the last chunk holds 1..3 blocks
-    (4, 4, 2, 1, 160, "mask"),          # a decode step against a 160-slot cache, additive mask
+    (4, 4, 2, 1, 160, "mask"),          # a decode step against a 160-slot cache, additive mask (grouped-query heads as tile rows)
+    (3, 8, 2, 1, 256, "none"),          # a decode step, four query heads per key / value head, no mask
     (2, 4, 2, 200, 224, "causal"),
     (1, 2, 1, 96, 96, "causal"),        # less than one chunk
     (1, 2, 2, 300, 416, "mask+pad"),

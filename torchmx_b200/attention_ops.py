@@ -122,10 +122,18 @@ def flash_attention(q_mx: MXTensor, k_mx: MXTensor, vt_mx: MXTensor, scaling: fl
         [(c.data_ptr(), f, s.data_ptr()) for c, f, s in ops]
     a.batch, a.heads, a.kv_heads, a.q_len, a.kv_len, a.head_dim = b, h, hk, q_len, kv_len, d
     a.scaling, a.causal = float(scaling), 1 if causal else 0
+    # One query position (decode) with grouped-query heads: the query heads that share a key / value head become the ROWS of one
+    # query tile ([b, h, 1, d] is [b, h_kv, groups, d] in memory), so a CTA works on `groups` live rows instead of one and the grid
+    # shrinks by that factor.  Same rows, same keys, same arithmetic per row; the mask row is shared by the group.
+    grouped = q_len == 1 and h > hk and not causal and (mask is None or mask.shape[1] == 1)
+    if grouped:
+        a.heads, a.q_len, a.mask_stride_q = hk, h // hk, 0
     a.p_elem = dtypes.ELEM_ID[p_elem_dtype.name]
     a.flags = _C.FLAG_HW_EXACT if (p_elem_dtype in dtypes.SUPPORTED_FP_ELEM_DTYPES and env.MX_EXACT_QUANTIZATION == "True") else 0
     out = torch.empty((b, q_len, h, d), dtype=torch.bfloat16, device=dev)
     a.out, a.out_batch_stride, a.out_row_stride, a.out_head_stride = out.data_ptr(), out.stride(0), out.stride(1), out.stride(2)
+    if grouped:  # element (batch, key head, group row g, channel) of the kernel's view is head (key head * groups + g) of the one token
+        a.out_row_stride, a.out_head_stride = out.stride(2), (h // hk) * out.stride(2)
     probs = None
     if return_probs:
         is_fp4 = p_elem_dtype == dtypes.float4_e2m1
