@@ -15,15 +15,20 @@
 // recomputes Q K^T in each (the tensor core has the time: the kernel is bound by the fp32 softmax arithmetic).  Every rounding
 // step is K4a's (mxq_softmax_core.cuh), and the per-block sums are added in K4a's order, so the codes of P are K4a's bit for bit.
 //
-// CTA = 256 query rows of one (batch, head): two warpgroups of 128 softmax threads (thread = query row = TMEM lane), each with
-// its own 128 x 64 score tile and 128 x 128 output accumulator in TMEM, sharing the K / V tiles the TMA warp streams in.
-//   warps 0..3 / 4..7  softmax warpgroup 0 / 1: tcgen05.ld two MX blocks of scores, K4a arithmetic, P codes -> swizzled shared
-//                      memory tile + scale words in the tcgen05.cp layout; finally drain the output accumulator
-//   warp 8             TMA producer: Q tiles once, then per pass the K tiles (128 keys x 128 B) and, in pass C, the V^T tiles
-//                      (128 channels x 128 keys)
-//   warp 9             MMA issuer (one elected lane): S = Q K^T as two N = 64 halves per 128-key chunk, O += P V per chunk
-//   warp 10            scale-factor loader: Q / K / V E8M0 scales from their reference layout into the tcgen05.cp chunk layout
-// Causal attention without an explicit mask skips the key chunks a warpgroup's rows cannot see.
+// CTA = 256 query rows of one (batch, head) = two query tiles of 128 rows, each with its own 128 x 64 score tile and 128 x 128
+// output accumulator in TMEM, sharing the K / V tiles the TMA warp streams in.
+//   warps 0..15  softmax: query tile (warp >> 3) x MX block of the score tile (sub = (warp >> 2) & 1) x TMEM lane quadrant.  TWO
+//                threads per query row, one per 32-column block of every 64-column score tile: tcgen05.ld the block, K4a's
+//                arithmetic, P codes -> swizzled shared-memory tile + scale bytes in the tcgen05.cp layout; finally drain half
+//                of the row's output accumulator each.  What the two threads of a row must agree on goes through shared memory
+//                behind a 256-thread named barrier per query tile.
+//   warp 16      TMA producer: Q tiles once, then per pass the K tiles (128 keys x 128 B) and, in pass C, the V^T tiles
+//                (128 channels x 128 keys)
+//   warp 17      MMA issuer (one elected lane): S = Q K^T as two N = 64 halves per 128-key chunk, O += P V per chunk
+//   warp 18      scale-factor loader: Q / K / V E8M0 scales from their reference layout into the tcgen05.cp chunk layout
+// Causal attention without an explicit mask skips the key chunks a query tile's rows cannot see; with an explicit additive mask
+// pass A records the largest score of every (row, chunk) and passes B / C skip the chunks that are dead for a whole tile.
+// The key axis may be any multiple of 32 (a ragged last chunk is zero-filled by TMA and hidden).
 #include <cstring>
 
 #include "mxq_softmax_core.cuh"
