@@ -251,6 +251,45 @@ def test_silu_mul_to_mx_is_bit_identical_to_the_chain(elem, shape):
     assert torch.equal(got._scale_e8m0, want._scale_e8m0) and torch.equal(got._data, want._data)
 
 
+@pytest.mark.parametrize("elem", ["int8", "float8_e4m3"])
+def test_silu_mul_to_mx_every_bf16_gate_value(elem):
+    """K1b evaluates silu by a five-instruction sequence (csrc/mxq_silu.cuh); the gate has only 65536 possible values, all of them
+    go through here -- each alone in its block beside zeros (so that it sets the block scale and keeps as many of its bits as the
+    element type has) and among random neighbours, with up = 1, a power of two and random multipliers."""
+    import torchmx  # noqa: F401
+    from torchmx import dtypes, mlp_ops
+    from torchmx.mx_tensor import MXTensor
+    et = dtypes.STR_TO_ELEM_DTYPE[elem]
+    every = torch.arange(65536, device=DEV, dtype=torch.int32).to(torch.int16).view(torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(13)
+    alone = torch.zeros(65536, 32, device=DEV, dtype=torch.bfloat16)
+    alone[:, 5] = every
+    among = (torch.randn(65536, 32, device=DEV, generator=g) * 3).to(torch.bfloat16)
+    among[:, 17] = every
+    gate = torch.cat([alone, among], dim=1).reshape(512, 128 * 64).contiguous()
+    for up in (torch.ones_like(gate), torch.full_like(gate, -0.125), (torch.randn(gate.shape, device=DEV, generator=g) * 2).to(torch.bfloat16)):
+        got = mlp_ops.silu_mul_to_mx(gate, up, et, 32)
+        want = MXTensor.to_mx(torch.nn.functional.silu(gate) * up, et, 32)
+        assert torch.equal(got._scale_e8m0, want._scale_e8m0) and torch.equal(got._data, want._data)
+
+
+def test_silu_sequence_equals_the_plain_formula_for_every_bf16_input(tmp_path):
+    """tools/silu_check.cu compares the bf16 rounding of the shipped sequence with that of g / (1 + expf(-g)) for all 65536 inputs
+    on this GPU and exits non-zero on any difference (recorded run: profiles/r2_k1b_silu_check.json)"""
+    import json, os, shutil, subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "silu_check")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-I", os.path.join(root, "torchmx_b200", "csrc"),
+                    os.path.join(root, "tools", "silu_check.cu"), "-o", exe], check=True, timeout=300)
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    report = json.loads(run.stdout)
+    assert report["cuda"] == "no error" and report["inputs"] == 65536
+    assert report["mismatches"]["shipped"]["count"] == 0 and run.returncode == 0
+
+
 def test_silu_mul_to_mx_on_column_slices_nan_blocks_and_refusals():
     import torchmx  # noqa: F401
     from torchmx import dtypes, mlp_ops

@@ -4,12 +4,15 @@
 // 19-59, with transformers' LlamaMLP / Qwen2MLP forward), and MXInferenceLinear.forward quantizes the product on entry
 // (torchmx/layers/mx_linear.py:63-66): three launches -- silu, mul, K1 -- that write and re-read a [tokens, intermediate] bf16
 // tensor twice.  This kernel reads gate and up once and writes the codes + scales down_proj consumes:
-//     h = bf16( g / (1 + exp(-g)) )        (aten silu: fp32 arithmetic on the bf16 input, one rounding)
+//     h = bf16( g / (1 + exp(-g)) )        (aten silu: fp32 arithmetic on the bf16 input, one rounding; evaluated by the five-
+//                                           instruction sequence of mxq_silu.cuh, checked against the plain formula for all
+//                                           65536 bf16 inputs on the hardware: tools/silu_check.cu)
 //     y = bf16( h * u )                    (aten mul)
 //     codes, scales = quantize_mx(y)       (K1's arithmetic, mxq_quant_core.cuh)
 // bit-identical to the three-launch chain.  Algorithmic traffic 2 + 2 + 1 + 1/32 B per element.  gate / up may be column
 // slices of one stacked projection output (row strides given), so a single gate+up GEMM can feed it without a copy.
 #include "mxq_quant_core.cuh"
+#include "mxq_silu.cuh"
 
 #include <cmath>
 
@@ -37,7 +40,7 @@ __global__ void __launch_bounds__(256) silu_mul_quantize_kernel(const uint16_t* 
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float g0 = __uint_as_float(g[i] << 16), g1 = __uint_as_float(g[i] & 0xFFFF0000u);
-            const uint32_t h = pack_bf16x2(g0 / (1.0f + expf(-g0)), g1 / (1.0f + expf(-g1)));
+            const uint32_t h = pack_bf16x2(silu_bf16_input(g0), silu_bf16_input(g1));
             w[i] = pack_bf16x2(__uint_as_float(h << 16) * __uint_as_float(u[i] << 16), __uint_as_float(h & 0xFFFF0000u) * __uint_as_float(u[i] & 0xFFFF0000u));
         }
         uint32_t out[NO];
