@@ -36,8 +36,13 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libmxq.so cannot be built (there is no CPU fallback)")
 
 
+FLAGS_STAMP = os.path.join(HERE, "lib", "nvcc_flags.txt")  # a developer build must not be mistaken for a fresh release build
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB):
+        return True
+    if not os.path.exists(FLAGS_STAMP) or open(FLAGS_STAMP).read() != " ".join(NVCC_FLAGS):
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(HERE), "include", "mxq.h"), __file__]
@@ -73,6 +78,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs,
                            "-Xcompiler", "-fPIC", "-lcudart_static", "-lcuda"])
     os.replace(tmp, LIB)
+    with open(FLAGS_STAMP, "w") as f:
+        f.write(" ".join(NVCC_FLAGS))
     return LIB
 
 
