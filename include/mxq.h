@@ -57,6 +57,12 @@ typedef enum {
 #define MXQ_FLAG_HW_EXACT 1u /* env MX_HARDWARE_EXACT_QUANTIZATION == "True"
                                 (torchmx/env_variables.py:16, mx_tensor.py:80-90).  Only
                                 observable in NaN-scale blocks: see DESIGN.md "hw_exact quirk" */
+#define MXQ_FLAG_OPERAND_LAYOUT 2u /* mxq_quantize only; float4_e2m1 / float6_* elements, block 32, bf16 source, 32-byte aligned
+                                      pointers (else MXQ_ERR_UNSUPPORTED_SHAPE): `codes` receives the packed tensor-core operand
+                                      stream (MXQ_OPERAND_E2M1_PACKED / MXQ_OPERAND_E3M2_PACKED / MXQ_OPERAND_E2M3_PACKED, what
+                                      mxq_pack_operand makes of the reference-layout codes: n/2 or 3n/4 bytes) -- the form
+                                      mxq_gemm consumes -- so an activation quantized on entry to a linear
+                                      (torchmx/layers/mx_linear.py:63-66) needs no second launch */
 
 /*
  * quantize  <->  torchmx::quantize_mx  (torchmx/mx_tensor.py:36-96)

@@ -326,6 +326,63 @@ def test_fused_activation_quantization_is_bit_identical(mx, rows, N, K, wdt, bia
     assert torch.isnan(y_fused[0]).all() and torch.isnan(y_fused[-1]).all() and (rows < 3 or not torch.isnan(y_fused[1]).any())
 
 
+@pytest.mark.parametrize("adt", ["float6_e3m2", "float6_e2m3", "float4_e2m1"])
+@pytest.mark.parametrize("mode", ["False", "True"])
+def test_quantize_straight_into_the_operand_layout(mx, adt, mode):
+    """mxq_quantize with MXQ_FLAG_OPERAND_LAYOUT == mxq_quantize followed by mxq_pack_operand, bit for bit (codes and scales),
+    NaN / Inf blocks included, under both values of the hw_exact toggle; refused for one-byte element types"""
+    from torchmx import dtypes
+    from torchmx import env_variables as env
+    from torchmx.mx_tensor import MXTensor
+    from torchmx_b200 import _C, mx_gemm
+    from torchmx_b200.mx_tensor import _stream_ptr
+    env.MX_EXACT_QUANTIZATION = mode
+    et = dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[adt]
+    g = torch.Generator(device=DEV).manual_seed(77)
+    rows, K = 333, 1024
+    x = torch.randn(rows, K, device=DEV, dtype=torch.bfloat16, generator=g)
+    x *= torch.exp2(torch.randint(-30, 30, (rows, K // 32), device=DEV, generator=g).float()).repeat_interleave(32, -1).to(torch.bfloat16)
+    x[3, 40] = float("inf"); x[7, 999] = float("nan"); x[9, :64] = 0
+    ref = MXTensor.to_mx(x, et, 32)
+    want, fmt = mx_gemm._operand_rows(ref._data, et, None, packed=True)
+    bits = mx_gemm._PACKED_BITS[fmt]
+    got = torch.empty(rows, K * bits // 8, device=DEV, dtype=torch.uint8)
+    sc = torch.empty(rows, K // 32, device=DEV, dtype=torch.uint8)
+    flags = _C.FLAG_OPERAND_LAYOUT | (_C.FLAG_HW_EXACT if mode == "True" else 0)
+    _C.check(_C.lib().mxq_quantize(x.data_ptr(), _C.HP_BF16, rows * K // 32, 32, dtypes.ELEM_ID[adt], flags, got.data_ptr(), sc.data_ptr(), 0, _stream_ptr(x)), "quantize")
+    assert torch.equal(sc, ref._scale_e8m0) and torch.equal(got, want.view(rows, -1))
+    rc = _C.lib().mxq_quantize(x.data_ptr(), _C.HP_BF16, rows * K // 32, 32, dtypes.ELEM_ID["float8_e4m3"], flags, got.data_ptr(), sc.data_ptr(), 0, _stream_ptr(x))
+    assert rc == _C.ERR_UNSUPPORTED_SHAPE
+
+
+@pytest.mark.parametrize("adt", ["float6_e3m2", "float6_e2m3", "float4_e2m1"])
+@pytest.mark.parametrize("wdt", ["float8_e4m3", "float6_e3m2", "float4_e2m1"])
+@pytest.mark.parametrize("rows,N,K,bias", [(300, 520, 640, True), (2048, 1024, 512, False), (40, 384, 256, True)])
+def test_linear_with_4_and_6_bit_activations_is_two_launches_and_bit_identical(mx, adt, wdt, rows, N, K, bias):
+    """MXInferenceLinear.forward with a 4 / 6-bit activation config (the reference's GEMM_COMBINATIONS, tests/layers/conftest.py:
+    56-65): K1 writes the packed operand stream, the GEMM reads it -- no mxq_pack_operand launch for the activation -- and the
+    result equals quantize -> pack -> GEMM bit for bit"""
+    from torchmx.config import MXConfig, QLinearConfig
+    from torchmx.layers.mx_linear import MXInferenceLinear
+    from torchmx_b200 import mx_gemm
+    g = torch.Generator(device=DEV).manual_seed(rows + N)
+    lin = torch.nn.Linear(K, N, bias=bias).to(DEV, torch.bfloat16)
+    layer = MXInferenceLinear.from_float(lin, QLinearConfig(weights_config=MXConfig(wdt, 32), activations_config=MXConfig(adt, 32)))
+    x = torch.randn(2, rows // 2, K, device=DEV, dtype=torch.bfloat16, generator=g) * 3
+    layer(x)  # (the weight's operand shadow is made on first use)
+    n0, t0 = mx_gemm.stats.get("packed_act_quant", 0), mx_gemm.stats["transcode"]
+    y = layer(x)
+    assert mx_gemm.stats.get("packed_act_quant", 0) == n0 + 1 and mx_gemm.stats["transcode"] == t0, "expected K1 -> GEMM without a pack launch"
+    real = mx_gemm.linear_packed_act_quant
+    mx_gemm.linear_packed_act_quant = lambda *a, **k: None
+    try:
+        y3 = layer(x)
+    finally:
+        mx_gemm.linear_packed_act_quant = real
+    assert mx_gemm.stats["transcode"] == t0 + 1  # the three-launch path packs the activation
+    assert y.shape == (2, rows // 2, N) and torch.equal(y, y3)
+
+
 # ---- packed-only weights (SURVEY §8f-3): PackedMXLinear / pack_linear_ / mxq_unpack_operand -----------------------------------
 @pytest.mark.parametrize("wdt", ["float6_e3m2", "float6_e2m3", "float4_e2m1", "float8_e4m3"])
 @pytest.mark.parametrize("rows", [8, 300])

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmxq.so")
 OK, ERR_INVALID, ERR_UNSUPPORTED_SHAPE, ERR_CUDA = 0, 1, 2, 3
 HP_BF16, HP_F32 = 0, 1
 FLAG_HW_EXACT = 1
+FLAG_OPERAND_LAYOUT = 2
 GEMM_B_STATIC, GEMM_WIDE_TILES, GEMM_NO_PDL, GEMM_NO_MXF4 = 1, 2, 4, 8
 ABI_VERSION = 2
 MAX_DIMS = 6

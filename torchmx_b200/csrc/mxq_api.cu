@@ -102,6 +102,8 @@ int mxq_quantize(const void* src, int src_dtype, int64_t n_blocks, int block_siz
     if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_quantize: selecting device");
     const cudaError_t e = mxq::launch_quantize(src, src_dtype, n_blocks, block_size, elem, flags, codes, scales, sm_count_of(scope.cur),
                                                quant_ept_override(), waves_override(), (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported && (flags & MXQ_FLAG_OPERAND_LAYOUT))
+        return fail(MXQ_ERR_UNSUPPORTED_SHAPE, "mxq_quantize: MXQ_FLAG_OPERAND_LAYOUT needs a 4 / 6-bit element type, block 32, bf16 source and 32-byte aligned pointers");
     return e == cudaSuccess ? MXQ_OK : fail_cuda(e, "mxq_quantize: launch");
 }
 

@@ -18,7 +18,10 @@ constexpr int kQuantThreads = 256;
 
 // BS = block size: 32 (the MX block; EPT 8 / 16 / 32), or 8 / 16 (EPT = BS: a thread owns a whole block) and 64 / 128 (EPT 32, two /
 // four lanes per block) -- same arithmetic, only the number of lanes that share a block maximum changes.
-template <int ELEM, int EPT, int BS = 32>
+// OPERAND (fp4 / fp6, EPT 16 / 32): the codes leave in the packed tensor-core operand format (include/mxq.h MXQ_OPERAND_*_PACKED:
+// fp4 low nibble first, fp6 four codes in three bytes) instead of the reference layout -- what mxq_pack_operand would make of
+// them, without the extra launch and round trip; the codes themselves are the same.
+template <int ELEM, int EPT, int BS = 32, bool OPERAND = false>
 __global__ void __launch_bounds__(kQuantThreads) quantize_b32_bf16_kernel(const uint16_t* __restrict__ src, uint8_t* __restrict__ codes,
                                                                            uint8_t* __restrict__ scales, int64_t n_blocks, uint32_t flags) {
     pdl_launch_dependents();       // a dependent MX GEMM may start streaming its weights while the activation is quantized
@@ -58,7 +61,28 @@ __global__ void __launch_bounds__(kQuantThreads) quantize_b32_bf16_kernel(const 
         uint32_t out[NO];
         if (s != 255) convert_words<ELEM, NW>(w, s, out);
         else nanblock_words<ELEM, NW>(w, (flags & MXQ_FLAG_HW_EXACT) != 0, out);
-        if (live) {
+        if constexpr (OPERAND && ELEM == MXQ_ELEM_E2M1) {
+#pragma unroll
+            for (int i = 0; i < NO; ++i) out[i] = ((out[i] & 0x0F0F0F0Fu) << 4) | ((out[i] >> 4) & 0x0F0F0F0Fu);
+        }
+        if constexpr (OPERAND && (ELEM == MXQ_ELEM_E3M2 || ELEM == MXQ_ELEM_E2M3)) {
+            if (live) {
+                uint32_t* q = reinterpret_cast<uint32_t*>(codes + c * (EPT * 3 / 4));  // 12 bytes per 16 codes
+#pragma unroll
+                for (int g = 0; g < EPT / 16; ++g) {
+                    uint32_t t[4];  // 24 packed bits per word of four codes
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t v = out[4 * g + j];
+                        t[j] = (v & 0x3F) | ((v >> 2) & 0xFC0) | ((v >> 4) & 0x3F000) | ((v >> 6) & 0xFC0000);
+                    }
+                    q[3 * g + 0] = t[0] | (t[1] << 24);
+                    q[3 * g + 1] = (t[1] >> 8) | (t[2] << 16);
+                    q[3 * g + 2] = (t[2] >> 16) | (t[3] << 8);
+                }
+                if ((threadIdx.x & (LPB - 1)) == 0) scales[c / LPB] = (uint8_t)s;
+            }
+        } else if (live) {
             constexpr int OB = NO * 4;  // output bytes per thread
             uint8_t* q = codes + c * OB;
             if constexpr (OB == 4) *reinterpret_cast<uint32_t*>(q) = out[0];
@@ -203,6 +227,17 @@ static cudaError_t launch_quantize_elem(const void* src, int src_dtype, int64_t 
                                         uint8_t* scales, int sm_count, int ept_override, int waves, cudaStream_t stream) {
     if (n_blocks == 0) return cudaSuccess;
     const uintptr_t a_src = (uintptr_t)src, a_codes = (uintptr_t)codes;
+    if (flags & MXQ_FLAG_OPERAND_LAYOUT) {
+        if constexpr (ELEM == MXQ_ELEM_E2M1 || ELEM == MXQ_ELEM_E3M2 || ELEM == MXQ_ELEM_E2M3) {
+            if (block_size != 32 || src_dtype != MXQ_HP_BF16 || (a_src % 32) || (a_codes % 32)) return cudaErrorNotSupported;
+            const int64_t want = (n_blocks + kQuantThreads - 1) / kQuantThreads;
+            const int grid = (int)(want < 0x7FFFFFFF ? want : 0x7FFFFFFF);
+            quantize_b32_bf16_kernel<ELEM, 32, 32, true><<<grid, kQuantThreads, 0, stream>>>((const uint16_t*)src, (uint8_t*)codes, scales, n_blocks, flags);
+            return cudaGetLastError();
+        } else {
+            return cudaErrorNotSupported;
+        }
+    }
     if (block_size == 32 && src_dtype == MXQ_HP_BF16 && (a_src % 32) == 0 && (a_codes % 32) == 0) {
         int ept = ept_override ? ept_override : 32;
         const int lpb = 32 / ept;

@@ -95,6 +95,11 @@ class MXInferenceLinear(torch.nn.Linear):
             out = mx_gemm.linear_fused_act_quant(x, w_mx, bias, env.MX_EXACT_QUANTIZATION == "True", fused=_fused)
             if out is not None:
                 return out
+        elif ac.block_size == 32 and ac.elem_dtype_name in ("float6_e3m2", "float6_e2m3", "float4_e2m1"):
+            # 4 / 6-bit activations: K1 writes the packed operand stream the GEMM reads (no mxq_pack_operand launch in between)
+            out = mx_gemm.linear_packed_act_quant(x, w_mx, bias, ac.elem_dtype, env.MX_EXACT_QUANTIZATION == "True", fused=_fused)
+            if out is not None:
+                return out
         x_mx = MXTensor.to_mx(x, ac.elem_dtype, ac.block_size)
         # F.linear(x_mx, w_mx, bias) reaches the same kernel through the dispatcher (aten.t + aten.mm / addmm on MXTensor
         # views, ~50 us of host time per layer); hand the operands to the tensor-core path directly when they qualify

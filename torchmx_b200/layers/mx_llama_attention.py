@@ -95,9 +95,11 @@ def _fuse_linears(mods) -> Optional[MXInferenceLinear]:
 
 
 GROUPED_DECODE_SDPA = os.environ.get("MXQ_GROUPED_DECODE_SDPA", "1") != "0"  # decode under sdpa: no repeat_kv copies (see forward)
-STACKED_MAX_ROWS = int(os.environ.get("MXQ_STACKED_MAX_ROWS", 128))  # measured on Llama-8B: decode 10.1 -> 9.8 ms/step stacked, but prefill 27.1 -> 29.3 ms (the column
-#                         slices of a stacked output make every following elementwise kernel and copy strided), so prefill keeps
-#                         one launch per projection
+# q/k/v as ONE launch on the row-stacked weights at every size.  Round 1 stacked only decode-sized activations: the column slices
+# of a stacked output made every following elementwise kernel and copy strided (prefill 27.1 -> 29.3 ms).  Since K5b (rotary)
+# reads the projection outputs in place through their strides, stacking wins at prefill too: Llama-8B 22.4 -> 21.2 ms (with MX
+# attention 25.1 -> 24.7 ms).  MXQ_STACKED_MAX_ROWS caps the activation rows it applies to.
+STACKED_MAX_ROWS = int(os.environ.get("MXQ_STACKED_MAX_ROWS", 1 << 30))
 
 
 # gate/up feed K1b, which reads the two column slices in place: no strided follow-up kernels, so the MLP stacks at every size

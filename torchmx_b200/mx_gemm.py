@@ -451,6 +451,59 @@ def linear_fused_act_quant(x: torch.Tensor, w: MXTensor, bias, hw_exact: bool, f
     return out
 
 
+def linear_packed_act_quant(x: torch.Tensor, w: MXTensor, bias, act_elem: dtypes.DType, hw_exact: bool,
+                            fused: Optional[FusedOutput] = None) -> Optional[torch.Tensor]:
+    """MXInferenceLinear.forward with a 4 / 6-bit ACTIVATION config (reference: torchmx/layers/mx_linear.py:63-94 with
+    `activations_config` float6_* / float4_e2m1): K1 writes the packed tensor-core operand stream itself (MXQ_FLAG_OPERAND_LAYOUT)
+    and the GEMM reads it -- two launches, where quantize -> mxq_pack_operand -> GEMM were three and the codes made one more round
+    trip through HBM.  Same codes, same scales, same GEMM: bit-identical to the three-launch path.  None when the operands do
+    not qualify (the caller takes that path)."""
+    if (_DISABLED or not _USE_PACKED or torch.compiler.is_compiling() or type(x) is not torch.Tensor or not x.is_cuda or x.dtype != torch.bfloat16
+            or act_elem.name not in _PACKED_FORMAT or not _qualifies(w)):
+        return None
+    K = x.shape[-1]
+    if w._data.dim() != 2 or w._block_dim != 1 or K % 128 != 0 or w.shape[-1] != K or not x.is_contiguous() or x.data_ptr() % 32:
+        return None
+    rows = x.numel() // K
+    if rows == 0:
+        return None
+    wk = _rows_k(w, 1)
+    if wk is None:
+        return None
+    if bias is not None and (isinstance(bias, MXTensor) or bias.dtype != torch.bfloat16 or bias.dim() != 1 or not bias.is_contiguous()):
+        return None
+    a_fmt = _PACKED_FORMAT[act_elem.name]
+    a_e = torch.empty((rows, K * _PACKED_BITS[a_fmt] // 8), dtype=torch.uint8, device=x.device)
+    sfa = torch.empty((rows, K // 32), dtype=torch.uint8, device=x.device)
+    rc = _C.lib().mxq_quantize(x.data_ptr(), _C.HP_BF16, rows * (K // 32), 32, dtypes.ELEM_ID[act_elem.name],
+                               _C.FLAG_OPERAND_LAYOUT | (_C.FLAG_HW_EXACT if hw_exact else 0), a_e.data_ptr(), sfa.data_ptr(), x.device.index, _stream_ptr(x))
+    if rc == _C.ERR_UNSUPPORTED_SHAPE:
+        return None
+    _C.check(rc, "mxq_quantize")
+    w_origin = getattr(w, "_mxq_origin", w)
+    b_e, b_fmt = _operand_rows(wk[0], w._elem_dtype, w_origin)
+    N = w.shape[0]
+    if fused is not None and fused.view.shape == (rows, N) and fused.view.is_contiguous():
+        out, d_mc = fused.view, fused.multicast_ptr
+    else:
+        fused, d_mc = None, 0
+        out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.bfloat16, device=x.device)
+    ok = _launch(a_e, sfa, b_e, wk[1], bias, 1, rows, N, K, 0, 0, 0, 0, out, a_fmt, b_fmt, d_mc, static_b=_static_b(w_origin))
+    if not ok and fused is not None:
+        fused, d_mc = None, 0
+        out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.bfloat16, device=x.device)
+        ok = _launch(a_e, sfa, b_e, wk[1], bias, 1, rows, N, K, 0, 0, 0, 0, out, a_fmt, b_fmt, 0, static_b=_static_b(w_origin))
+    if not ok:
+        return None
+    stats["tensor_core"] += 1
+    stats["packed_act_quant"] = stats.get("packed_act_quant", 0) + 1
+    if fused is not None:
+        fused.taken = True
+        stats["fused_allreduce"] += 1
+        return out.view(tuple(x.shape[:-1]) + (N,))
+    return out
+
+
 def pack_weight(w: MXTensor):
     """MXTensor weight [N, K] (blocks along K) -> (operand tensor, MXQ_OPERAND_* format) in the form the tensor-core kernels
     consume: the dense 4 / 6-bit stream for fp4 / fp6, the code bytes themselves for fp8.  None if the weight cannot run on
