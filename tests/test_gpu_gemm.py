@@ -110,6 +110,31 @@ def test_tensor_core_matmul(mx, monkeypatch, M, N, K, ea, eb, bias, batch, sprea
     _tol_check(out, A, B, bias_t, f"{M}x{N}x{K} {ea}x{eb}")
 
 
+@pytest.mark.parametrize("M,N,K,ea,eb", [(64, 96, 256, "float8_e4m3", "float6_e3m2"), (200, 136, 384, "float8_e4m3", "float4_e2m1"),
+                                         (16, 520, 1024, "float6_e2m3", "float8_e4m3"), (130, 260, 128, "float4_e2m1", "float4_e2m1")])
+def test_mx_linear_against_the_oracle_end_to_end(mx, oracle, M, N, K, ea, eb):
+    """The whole MX linear through the GPU path (K1 on both operands, tensor-core GEMM) against the CPU oracle end to end: the
+    oracle quantizes the same bf16 bits, dequantizes them and contracts with double accumulation (oracle/mx_oracle.c
+    mxo_gemm_nt_bf16) -- no GPU kernel of this repository on the checker's side."""
+    from torchmx import dtypes
+    from torchmx.mx_tensor import MXTensor
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV, dtype=torch.bfloat16, generator=g) * 2
+    w = torch.randn(N, K, device=DEV, dtype=torch.bfloat16, generator=g)
+    w *= torch.exp2(torch.randint(-6, 6, (N, K // 32), device=DEV, generator=g).float()).repeat_interleave(32, -1).to(torch.bfloat16)
+    out = torch.nn.functional.linear(MXTensor.to_mx(x, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[ea], 32), MXTensor.to_mx(w, dtypes.STR_TO_SUPPORTED_ELEM_DTYPE[eb], 32))
+    bits = lambda t: t.view(torch.int16).cpu().numpy().view(np.uint16)
+    deq = {}
+    for name, t, el in (("a", x, ea), ("b", w, eb)):
+        scales, codes = oracle.quantize(bits(t), el, 32)
+        deq[name] = oracle.dequantize(codes, scales, el, 32, target="bf16")
+    ref = oracle.gemm_nt(deq["a"], deq["b"]).astype(np.float64)
+    S = np.abs(oracle.bf16_bits_to_f32(deq["a"]).astype(np.float64)) @ np.abs(oracle.bf16_bits_to_f32(deq["b"]).astype(np.float64)).T
+    err = np.abs(out.double().cpu().numpy() - ref)
+    tol = 2.0 ** -8 * np.abs(ref) + 2.0 ** -18 * S + 1e-30  # bf16 rounding of the output + fp32 accumulation order
+    assert (err <= tol).all(), f"{int((err > tol).sum())} of {err.size} outside tolerance"
+
+
 def test_matmul_entry_points_agree(mx):
     """mm, addmm, linear (2-D and 3-D input, inference_mode and no_grad) and 4-D matmul all reach the
     same kernel and must agree bit-for-bit with each other."""
