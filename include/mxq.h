@@ -358,6 +358,23 @@ MXQ_API int mxq_rope(const mxq_rope_args_t *args, int device, void *stream);
 MXQ_API int mxq_quantize_heads(const void *src, int64_t batch, int64_t heads, int64_t tokens, int64_t head_dim, int elem /* mxq_elem_t */,
                        unsigned flags /* MXQ_FLAG_* */, void *codes, uint8_t *scales, int device, void *stream);
 
+/*
+ * the value heads as the MX operand of P.V  <->  `MXTensor.to_mx(value_states.transpose(-2, -1), elem, 32)`
+ * (torchmx/layers/mx_llama_attention.py:205-212: V is quantized along the SEQUENCE axis, 32 consecutive key positions of one
+ * (head, channel) per block) without the strided copy that materialises the transposed bf16 tensor:
+ *     codes, scales = quantize_mx(transpose(x, -2, -1), elem, 32)
+ *   x      : bf16 [n0, n1, rows, cols], element (i0, i1, r, c) at x + i0 * s0 + i1 * s1 + r * row_stride + c (strides in elements,
+ *            multiples of 8; base 16-byte aligned; cols contiguous): a [batch, heads, keys, head_dim] value tensor or cache slice
+ *   codes  : [n0, n1, cols, rows] contiguous (float4_e2m1: rows / 2 bytes per channel), scales [n0, n1, cols, rows / 32]
+ *   rows % 32 == 0, cols % 8 == 0, n0 * n1 <= 65535, else MXQ_ERR_UNSUPPORTED_SHAPE (the caller transposes and calls mxq_quantize)
+ */
+typedef struct {
+    const void *x; int64_t n0, n1, rows, cols, s0, s1, row_stride;
+    int elem /* mxq_elem_t */; unsigned flags /* MXQ_FLAG_HW_EXACT */;
+    void *codes; uint8_t *scales;
+} mxq_transposed_quantize_args_t;
+MXQ_API int mxq_quantize_transposed(const mxq_transposed_quantize_args_t *args, int device, void *stream);
+
 #define MXQ_OK 0
 #define MXQ_ERR_INVALID 1
 #define MXQ_ERR_UNSUPPORTED_SHAPE 2

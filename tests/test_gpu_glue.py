@@ -113,6 +113,35 @@ def test_quantize_heads_is_k1_of_the_transposed_tensor(elem, shape):
     assert_bits_equal(bits_of(got._data), bits_of(want._data), "codes")
 
 
+@pytest.mark.parametrize("elem", ELEMS + ["float8_e5m2"])
+@pytest.mark.parametrize("shape,cache_len", [((32, 8, 256, 128), 0), ((1, 8, 2048, 128), 0), ((2, 3, 96, 64), 160), ((1, 2, 32, 40), 0), ((3, 1, 416, 72), 512)])
+@pytest.mark.parametrize("mode", ["False", "True"])
+def test_quantize_transposed_is_k1_of_the_transposed_tensor(elem, shape, cache_len, mode):
+    """K5d: V quantized along the sequence axis straight from [b, h, kv, d] (also from a slice of a longer cache) == the strided
+    copy + K1 of the reference's recipe (torchmx/layers/mx_llama_attention.py:205-212), bit for bit"""
+    import torchmx  # noqa: F401
+    from torchmx_b200 import dtypes, glue_ops
+    from torchmx_b200 import env_variables as env
+    from torchmx_b200.mx_tensor import MXTensor
+    env.MX_EXACT_QUANTIZATION = mode
+    b, h, kv, d = shape
+    g = torch.Generator(device=DEV).manual_seed(kv + d)
+    full = torch.randn(b, h, max(cache_len, kv), d, device=DEV, dtype=torch.bfloat16, generator=g)
+    full *= torch.exp2(torch.randint(-20, 20, (b, h, full.shape[2] // 32, 1, d), device=DEV, generator=g).float()).expand(-1, -1, -1, 32, -1).reshape(full.shape).to(torch.bfloat16)
+    x = full[:, :, :kv]  # (a view with the cache's strides when cache_len > kv)
+    x[0, 0, 3, 1] = float("nan")
+    x[-1, -1, -1, -1] = float("inf")
+    x[0, -1, :32, 2] = 0
+    dt = dtypes.STR_TO_ELEM_DTYPE[elem]
+    n0 = glue_ops.stats["quantize_transposed"]
+    got = glue_ops.quantize_transposed(x, dt)
+    assert got is not None and glue_ops.stats["quantize_transposed"] == n0 + 1
+    want = MXTensor.to_mx(x.transpose(2, 3).contiguous(), dt, 32)
+    assert got.shape == want.shape == (b, h, d, kv)
+    assert_bits_equal(bits_of(got._scale_e8m0), bits_of(want._scale_e8m0), "scales")
+    assert_bits_equal(bits_of(got._data), bits_of(want._data), "codes")
+
+
 def test_glue_kernels_decline_what_they_cannot_take():
     import torchmx  # noqa: F401
     from torchmx_b200 import glue_ops
@@ -123,6 +152,9 @@ def test_glue_kernels_decline_what_they_cannot_take():
     q = torch.randn(1, 2, 4, 24, device=DEV, dtype=torch.bfloat16)
     cs = torch.randn(1, 4, 24, device=DEV, dtype=torch.bfloat16)
     assert glue_ops.rope(q, q, cs, cs) is None                                                      # head_dim % 16
+    from torchmx_b200 import dtypes
+    assert glue_ops.quantize_transposed(torch.randn(1, 2, 48, 64, device=DEV, dtype=torch.bfloat16), dtypes.float8_e4m3) is None   # rows % 32
+    assert glue_ops.quantize_transposed(torch.randn(1, 2, 64, 64, device=DEV, dtype=torch.bfloat16).transpose(2, 3), dtypes.float8_e4m3) is None  # cols strided
 
 
 def test_quantize_llm_with_fused_norms_matches_the_unfused_model():

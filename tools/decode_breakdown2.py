@@ -6,9 +6,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import llama_bench as lb
 from transformers.cache_utils import StaticCache
 with torch.no_grad():
-    model, cfg, info = lb.build("8b", 2, "float6_e3m2", "float8_e4m3", llm_api=True, fuse_norm=True)
+    model, cfg, info = lb.build("8b", 2, "float6_e3m2", "float8_e4m3", llm_api=True, fuse_norm=True, mx_attention=os.environ.get("DB_MX_ATTENTION", "0") == "1")
     B, ctx = 32, 128
-    cache = StaticCache(config=cfg, max_cache_len=ctx + 16)
+    cache = StaticCache(config=cfg, max_cache_len=256 if os.environ.get("DB_MX_ATTENTION", "0") == "1" else ctx + 16)
     model(input_ids=torch.randint(0, cfg.vocab_size, (B, ctx), device="cuda"), past_key_values=cache, use_cache=True)
     tok = torch.randint(0, cfg.vocab_size, (B, 1), device="cuda")
     for i in range(3):

@@ -18,7 +18,7 @@ ABI_VERSION = 2
 MAX_DIMS = 6
 
 EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_gemm_dequant", "mxq_gemm_bf16", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
-           "mxq_softmax_quantize", "mxq_flash_attention", "mxq_silu_mul_quantize", "mxq_rmsnorm", "mxq_rope", "mxq_quantize_heads", "mxq_last_error", "mxq_version", "mxq_arch")
+           "mxq_softmax_quantize", "mxq_flash_attention", "mxq_silu_mul_quantize", "mxq_rmsnorm", "mxq_rope", "mxq_quantize_heads", "mxq_quantize_transposed", "mxq_last_error", "mxq_version", "mxq_arch")
 
 
 class GemmArgs(ctypes.Structure):
@@ -105,6 +105,15 @@ class RopeArgs(ctypes.Structure):
     ]
 
 
+class TransposedQuantArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("n0", ctypes.c_int64), ("n1", ctypes.c_int64), ("rows", ctypes.c_int64), ("cols", ctypes.c_int64),
+        ("s0", ctypes.c_int64), ("s1", ctypes.c_int64), ("row_stride", ctypes.c_int64),
+        ("elem", ctypes.c_int), ("flags", ctypes.c_uint),
+        ("codes", ctypes.c_void_p), ("scales", ctypes.c_void_p),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -157,6 +166,8 @@ def lib() -> ctypes.CDLL:
         L.mxq_quantize_heads.argtypes = [vp, i64, i64, i64, i64, i32, u32, vp, vp, i32, vp]
         L.mxq_rope.restype = i32
         L.mxq_rope.argtypes = [ctypes.POINTER(RopeArgs), i32, vp]
+        L.mxq_quantize_transposed.restype = i32
+        L.mxq_quantize_transposed.argtypes = [ctypes.POINTER(TransposedQuantArgs), i32, vp]
         if L.mxq_version() != ABI_VERSION:
             raise RuntimeError(f"torchmx_b200: libmxq.so has ABI v{L.mxq_version()}, this package needs v{ABI_VERSION}: rebuild with `python -m torchmx_b200.build --force`")
         if L.mxq_arch() != 1000:

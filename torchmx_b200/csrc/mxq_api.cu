@@ -25,6 +25,7 @@ int launch_softmax_quantize(const mxq_softmax_args_t*, cudaStream_t, char*, size
 int launch_rmsnorm(const mxq_rmsnorm_args_t*, cudaStream_t, char*, size_t);
 int launch_rope(const mxq_rope_args_t*, int, cudaStream_t, char*, size_t);
 int launch_heads_quantize(const void*, int64_t, int64_t, int64_t, int64_t, int, unsigned, void*, uint8_t*, cudaStream_t, char*, size_t);
+int launch_transposed_quantize(const mxq_transposed_quantize_args_t*, cudaStream_t, char*, size_t);
 }  // namespace mxq
 
 namespace {
@@ -252,6 +253,19 @@ int mxq_quantize_heads(const void* src, int64_t batch, int64_t heads, int64_t to
     char msg[400] = "";
     const int rc = mxq::launch_heads_quantize(src, batch, heads, tokens, head_dim, elem, flags, codes, scales, (cudaStream_t)stream, msg, sizeof(msg));
     return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_quantize_heads: %s", msg);
+}
+
+int mxq_quantize_transposed(const mxq_transposed_quantize_args_t* a, int device, void* stream) {
+    if (!a) return fail(MXQ_ERR_INVALID, "mxq_quantize_transposed: null args");
+    if (!valid_elem(a->elem)) return fail(MXQ_ERR_INVALID, "mxq_quantize_transposed: unknown element type %d", a->elem);
+    if (a->n0 < 0 || a->n1 < 0 || a->rows < 0 || a->cols < 0) return fail(MXQ_ERR_INVALID, "mxq_quantize_transposed: negative extent");
+    if (a->n0 == 0 || a->n1 == 0 || a->rows == 0 || a->cols == 0) return MXQ_OK;
+    if (!a->x || !a->codes || !a->scales) return fail(MXQ_ERR_INVALID, "mxq_quantize_transposed: null pointer");
+    DeviceScope scope(device);
+    if (scope.err != cudaSuccess) return fail_cuda(scope.err, "mxq_quantize_transposed: selecting device");
+    char msg[400] = "";
+    const int rc = mxq::launch_transposed_quantize(a, (cudaStream_t)stream, msg, sizeof(msg));
+    return rc == MXQ_OK ? MXQ_OK : fail(rc, "mxq_quantize_transposed: %s", msg);
 }
 
 int mxq_rope(const mxq_rope_args_t* a, int device, void* stream) {

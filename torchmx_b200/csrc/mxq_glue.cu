@@ -209,6 +209,55 @@ __global__ void __launch_bounds__(256) heads_quantize_kernel(const uint16_t* __r
     scales[o] = (uint8_t)sc;
 }
 
+// K5d transposed_quantize_kernel: the value heads as the MX operand of P.V.  The reference quantizes V along the SEQUENCE axis
+// (torchmx/layers/mx_llama_attention.py:205-212: value_states.transpose(-2, -1) -> to_mx -> transpose back), i.e. an MX block is
+// 32 consecutive key positions of one (head, channel); as aten ops that is a strided copy of the whole value cache
+// ([b, h, kv, d] -> [b, h, d, kv], 38 us per layer at batch 32 x 256 keys) followed by K1.  Here a CTA loads a 128-key x 64-channel
+// tile with coalesced 16-byte loads, and each thread then quantizes ONE block -- 32 keys of one channel, gathered from shared
+// memory -- with K1's arithmetic and stores its 32 codes contiguously in the [b, h, d, kv] layout: the transposed bf16 tensor is
+// never written.  Same codes and scales as the two-step path, bit for bit.
+struct TransposedQuantParams {
+    const uint16_t* x; int64_t s0, s1, sr;  // x[i0][i1][r][c] at x + i0 * s0 + i1 * s1 + r * sr + c (elements)
+    int64_t n1, rows, cols;
+    uint8_t* codes; uint8_t* scales; unsigned flags;
+};
+
+template <int ELEM>
+__global__ void __launch_bounds__(256) transposed_quantize_kernel(const TransposedQuantParams p) {
+    pdl_launch_dependents();
+    constexpr int TR = 128, TC = 64;
+    __shared__ __align__(16) uint16_t tile[TR][TC + 8];  // (+8: rows stay 16-byte aligned, column reads of a warp hit 16 distinct words)
+    const int64_t slice = blockIdx.z;
+    const int64_t i0 = slice / p.n1, i1 = slice % p.n1;
+    const int64_t r0 = (int64_t)blockIdx.y * TR, c0 = (int64_t)blockIdx.x * TC;
+    const uint16_t* src = p.x + i0 * p.s0 + i1 * p.s1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int v = threadIdx.x + i * 256;  // 16-byte vector: row v / 8, columns 8 * (v % 8) ..
+        const int r = v >> 3, c8 = (v & 7) * 8;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (r0 + r < p.rows && c0 + c8 < p.cols) val = *reinterpret_cast<const uint4*>(src + (r0 + r) * p.sr + c0 + c8);
+        *reinterpret_cast<uint4*>(&tile[r][c8]) = val;
+    }
+    __syncthreads();
+    const int c = threadIdx.x & (TC - 1), rb = threadIdx.x >> 6;  // channel, 32-key block within the tile
+    if (c0 + c >= p.cols || r0 + rb * 32 >= p.rows) return;
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = (uint32_t)tile[rb * 32 + 2 * i][c] | ((uint32_t)tile[rb * 32 + 2 * i + 1][c] << 16);
+    constexpr int NO = (ELEM == MXQ_ELEM_E2M1) ? 4 : 8;
+    uint32_t out[NO];
+    const int sc = quantize_block32<ELEM>(w, (p.flags & MXQ_FLAG_HW_EXACT) != 0, out);
+    const int64_t blk = (slice * p.cols + c0 + c) * (p.rows / 32) + (r0 / 32 + rb);  // block index in [.., channel, key block] order
+    uint8_t* dst = p.codes + blk * (NO * 4);
+    if constexpr (NO == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+    else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<uint4*>(dst + 16) = make_uint4(out[4], out[5], out[6], out[7]);
+    }
+    p.scales[blk] = (uint8_t)sc;
+}
+
 }  // namespace glue
 
 int launch_heads_quantize(const void* src, int64_t batch, int64_t heads, int64_t tokens, int64_t head_dim, int elem, unsigned flags, void* codes,
@@ -287,6 +336,31 @@ int launch_rope(const mxq_rope_args_t* a, int sm_count, cudaStream_t stream, cha
     const int64_t n = a->batch * a->tokens * (int64_t)(a->q_heads + a->k_heads) * (a->head_dim / 16);
     const int64_t want = (n + 255) / 256, cap = (int64_t)sm_count * 16;
     rope_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(msg, msg_len, "launch: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
+    return MXQ_OK;
+}
+
+int launch_transposed_quantize(const mxq_transposed_quantize_args_t* a, cudaStream_t stream, char* msg, size_t msg_len) {
+    using namespace glue;
+    if (a->rows % 32 || a->cols % 8 || ((uintptr_t)a->x % 16) || (a->s0 % 8) || (a->s1 % 8) || (a->row_stride % 8) || ((uintptr_t)a->codes % 16)) {
+        snprintf(msg, msg_len, "needs rows %% 32 == 0, cols %% 8 == 0 and 16-byte aligned rows");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
+    const int64_t slices = a->n0 * a->n1, gy = (a->rows + 127) / 128, gx = (a->cols + 63) / 64;
+    if (slices == 0 || a->rows == 0 || a->cols == 0) return MXQ_OK;
+    if (slices > 65535 || gy > 65535 || gx > 0x7FFFFFFF) { snprintf(msg, msg_len, "too many slices / rows"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+    TransposedQuantParams p;
+    p.x = (const uint16_t*)a->x; p.s0 = a->s0; p.s1 = a->s1; p.sr = a->row_stride;
+    p.n1 = a->n1; p.rows = a->rows; p.cols = a->cols;
+    p.codes = (uint8_t*)a->codes; p.scales = a->scales; p.flags = a->flags;
+    const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)slices);
+#define MXQ_TQ_CASE(E) case E: transposed_quantize_kernel<E><<<grid, 256, 0, stream>>>(p); break;
+    switch (a->elem) {
+        MXQ_TQ_CASE(MXQ_ELEM_E4M3) MXQ_TQ_CASE(MXQ_ELEM_E3M2) MXQ_TQ_CASE(MXQ_ELEM_E2M3) MXQ_TQ_CASE(MXQ_ELEM_E2M1) MXQ_TQ_CASE(MXQ_ELEM_INT8) MXQ_TQ_CASE(MXQ_ELEM_E5M2)
+    default: snprintf(msg, msg_len, "unknown element type %d", a->elem); return MXQ_ERR_INVALID;
+    }
+#undef MXQ_TQ_CASE
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;

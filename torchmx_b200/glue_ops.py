@@ -22,7 +22,7 @@ from . import env_variables as env
 from .mlp_ops import _rows_view
 from .mx_tensor import MXTensor, _stream_ptr
 
-stats = {"rmsnorm": 0, "rmsnorm_to_mx": 0, "rope": 0, "quantize_heads": 0}
+stats = {"rmsnorm": 0, "rmsnorm_to_mx": 0, "rope": 0, "quantize_heads": 0, "quantize_transposed": 0}
 _ENABLED = os.environ.get("MXQ_FUSED_GLUE", "1") != "0"
 MAX_HIDDEN = 16384
 
@@ -146,4 +146,30 @@ def quantize_heads(x: torch.Tensor, elem_dtype: dtypes.DType, block_size: int = 
         return None
     _C.check(rc, "mxq_quantize_heads")
     stats["quantize_heads"] += 1
+    return MXTensor(scales, codes, elem_dtype, 32, torch.bfloat16)
+
+
+def quantize_transposed(x: torch.Tensor, elem_dtype: dtypes.DType, block_size: int = 32) -> Optional[MXTensor]:
+    """x: bf16 [n0, n1, rows, cols] (any strides over the first three dims, cols contiguous: a value tensor or a slice of a value
+    cache) -> the MXTensor `MXTensor.to_mx(x.transpose(-2, -1), elem_dtype, 32)` -- shape [n0, n1, cols, rows], blocks along the
+    rows (key positions) -- without materialising the transposed bf16 tensor (K5d); None when the kernel does not apply"""
+    if not _ENABLED or block_size != 32 or not _plain_bf16(x) or x.dim() != 4 or x.numel() == 0 or x.stride(3) != 1:
+        return None
+    n0, n1, rows, cols = x.shape
+    if rows % 32 or cols % 8 or n0 * n1 > 65535 or x.data_ptr() % 16 or any(st % 8 for st in x.stride()[:3]):
+        return None
+    is_fp4 = elem_dtype == dtypes.float4_e2m1
+    codes = torch.empty((n0, n1, cols, rows // 2 if is_fp4 else rows), dtype=torch.int8 if elem_dtype == dtypes.int8 else torch.uint8, device=x.device)
+    scales = torch.empty((n0, n1, cols, rows // 32), dtype=torch.uint8, device=x.device)
+    a = _C.TransposedQuantArgs()
+    a.x, a.n0, a.n1, a.rows, a.cols = x.data_ptr(), n0, n1, rows, cols
+    a.s0, a.s1, a.row_stride = x.stride(0), x.stride(1), x.stride(2)
+    a.elem = dtypes.ELEM_ID[elem_dtype.name]
+    a.flags = _C.FLAG_HW_EXACT if (elem_dtype in dtypes.SUPPORTED_FP_ELEM_DTYPES and env.MX_EXACT_QUANTIZATION == "True") else 0
+    a.codes, a.scales = codes.data_ptr(), scales.data_ptr()
+    rc = _C.lib().mxq_quantize_transposed(a, x.device.index, _stream_ptr(x))
+    if rc == _C.ERR_UNSUPPORTED_SHAPE:
+        return None
+    _C.check(rc, "mxq_quantize_transposed")
+    stats["quantize_transposed"] += 1
     return MXTensor(scales, codes, elem_dtype, 32, torch.bfloat16)

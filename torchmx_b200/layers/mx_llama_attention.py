@@ -249,7 +249,12 @@ class _MXAttentionMixin:
         groups = self.num_key_value_groups
         q_mx = MXTensor.to_mx(query_states.contiguous(), qc.query_config.elem_dtype, qc.query_config.block_size)
         k_one = MXTensor.to_mx(key_states.contiguous(), qc.key_config.elem_dtype, qc.key_config.block_size)
-        vt_one = MXTensor.to_mx(value_states.transpose(2, 3).contiguous(), qc.value_config.elem_dtype, qc.value_config.block_size)
+        # V is quantized along the sequence axis (reference :205-212: transpose, quantize, transpose back): K5d reads the
+        # [bs, heads, kv, head_dim] tensor in place; the strided copy of the whole value cache it replaces was the largest
+        # single launch of a decode step (38 us of a 230 us layer at batch 32)
+        vt_one = glue_ops.quantize_transposed(value_states, qc.value_config.elem_dtype, qc.value_config.block_size)
+        if vt_one is None:
+            vt_one = MXTensor.to_mx(value_states.transpose(2, 3).contiguous(), qc.value_config.elem_dtype, qc.value_config.block_size)
         pc = qc.attention_weights_config
         q_len, kv_len = q_mx.shape[-2], k_one.shape[-2]
         mask, causal = None, False
