@@ -337,7 +337,11 @@ MXQ_API int mxq_rmsnorm(const mxq_rmsnorm_args_t *args, int device, void *stream
  *     out = (x * cos) + (rotate_half(x) * sin), every product and the sum rounded to bf16 as the tensor ops round them
  *   q / k   : bf16, element (b, t, h, d) at  base + b*batch_stride + t*tok_stride + h*head_dim + d  (the projection output, read in place)
  *   cos/sin : bf16 [batch | 1, tokens, head_dim] (batch stride 0 broadcasts)
- *   q_out / k_out : bf16 [batch, heads, tokens, head_dim] contiguous
+ *   q_out / k_out : bf16 [batch, heads, tokens, head_dim], contiguous when the three *_out_*_stride fields are 0, else element
+ *             (b, h, t, d) at  base + b*out_batch_stride + h*out_head_stride + t*out_tok_stride + d  -- the rotated keys can land in
+ *             place in a KV cache (the cache update of the reference's call site, mx_llama_attention.py:189-193, folded in)
+ *   v / v_out : optional (NULL): a third tensor with k's geometry, copied unrotated with the same addressing (the value heads on
+ *             their way from the projection output into the cache)
  */
 typedef struct {
     const void *q; int64_t q_tok_stride, q_batch_stride; int q_heads;
@@ -345,6 +349,10 @@ typedef struct {
     const void *cos; const void *sin; int64_t cs_tok_stride, cs_batch_stride;
     int64_t batch, tokens; int head_dim;
     void *q_out; void *k_out;
+    int64_t q_out_batch_stride, q_out_head_stride, q_out_tok_stride;
+    int64_t k_out_batch_stride, k_out_head_stride, k_out_tok_stride;
+    const void *v; int64_t v_tok_stride, v_batch_stride;
+    void *v_out; int64_t v_out_batch_stride, v_out_head_stride, v_out_tok_stride;
 } mxq_rope_args_t;
 MXQ_API int mxq_rope(const mxq_rope_args_t *args, int device, void *stream);
 

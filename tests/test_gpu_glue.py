@@ -93,6 +93,35 @@ def test_rope_is_bit_identical_to_apply_rotary_pos_emb(b, t, hq, hk, d, stacked)
         assert_bits_equal(bits_of(got[1]), bits_of(want[1]), "k")
 
 
+@pytest.mark.parametrize("b,t,hq,hk,d,pos,cache_len", [(32, 1, 32, 8, 128, 77, 160), (1, 300, 8, 2, 128, 0, 300), (2, 5, 4, 4, 64, 9, 40)])
+def test_rope_writes_keys_and_values_straight_into_a_cache(b, t, hq, hk, d, pos, cache_len):
+    """K5b with `k_out` / `v` / `v_out`: the rotated keys land in place in a cache slice and the value heads are copied beside
+    them by the same launch == rope, then `index_copy_` of k and v (the cache update of the reference's call site,
+    torchmx/layers/mx_llama_attention.py:189-193); everything else in the caches is left alone"""
+    import torchmx  # noqa: F401
+    from torchmx_b200 import glue_ops
+    g = torch.Generator(device=DEV).manual_seed(b * t + pos)
+    qkv = torch.randn(b, t, (hq + 2 * hk) * d, device=DEV, dtype=torch.bfloat16, generator=g)
+    q2, k2, v2 = qkv.split([hq * d, hk * d, hk * d], dim=-1)
+    q, k, v = (x.view(b, t, -1, d).transpose(1, 2) for x in (q2, k2, v2))
+    ang = torch.rand(b, t, d // 2, device=DEV, generator=g) * 100
+    emb = torch.cat([ang, ang], -1)
+    cos, sin = emb.cos().to(torch.bfloat16), emb.sin().to(torch.bfloat16)
+    kc = torch.randn(b, hk, cache_len, d, device=DEV, dtype=torch.bfloat16, generator=g)
+    vc = torch.randn(b, hk, cache_len, d, device=DEV, dtype=torch.bfloat16, generator=g)
+    kc_want, vc_want = kc.clone(), vc.clone()
+    q_want, k_want = glue_ops.rope(q, k, cos, sin)
+    idx = torch.arange(pos, pos + t, device=DEV)
+    kc_want.index_copy_(2, idx, k_want)
+    vc_want.index_copy_(2, idx, v)
+    got = glue_ops.rope(q, k, cos, sin, k_out=kc[:, :, pos:pos + t], v=v, v_out=vc[:, :, pos:pos + t])
+    assert got is not None and got[1].data_ptr() == kc[:, :, pos:pos + t].data_ptr()
+    assert_bits_equal(bits_of(got[0]), bits_of(q_want), "q")
+    assert_bits_equal(bits_of(kc), bits_of(kc_want), "key cache")
+    assert_bits_equal(bits_of(vc), bits_of(vc_want), "value cache")
+    assert glue_ops.rope(q, k, cos, sin, v=v) is None  # v without v_out
+
+
 @pytest.mark.parametrize("elem", ELEMS + ["float8_e5m2"])
 @pytest.mark.parametrize("shape", [(1, 32, 2048, 128), (32, 8, 1, 128), (2, 3, 77, 64), (1, 2, 5, 32)])
 def test_quantize_heads_is_k1_of_the_transposed_tensor(elem, shape):

@@ -42,6 +42,7 @@ def rms_norm(x, w, eps=1e-5):
     return F.rms_norm(x, (x.shape[-1],), w, eps)
 
 
+CACHE_IN_ROPE = os.environ.get("TP_CACHE_IN_ROPE", "1") != "0"
 GLUE = True  # --no-glue: RMSNorm / rotary / SiLU as plain PyTorch ops, one launch per projection
 
 
@@ -122,11 +123,18 @@ class TPDecoderLayer(torch.nn.Module):
         q = q.view(B, T, self.nh_local, self.hd).transpose(1, 2)
         k = k.view(B, T, self.nkv_local, self.hd).transpose(1, 2)
         v = v.view(B, T, self.nkv_local, self.hd).transpose(1, 2)
-        r = glue_ops.rope(q, k, cs[2], cs[3])
-        assert r is not None, "the rotary kernel declined the projection output"
-        q, k = r
-        kc.index_copy_(2, pos, k)
-        vc.index_copy_(2, pos, v)
+        # rotary embedding, and the KV-cache update folded into the same launch: the rotated keys are written in place into the
+        # cache slice, the value heads copied beside them (tokens go to positions p0 .. p0 + T - 1, which is what `pos` holds)
+        p0 = 0 if T > 1 else cache_len
+        r = glue_ops.rope(q, k, cs[2], cs[3], k_out=kc[:, :, p0:p0 + T], v=v, v_out=vc[:, :, p0:p0 + T]) if CACHE_IN_ROPE else None
+        if r is not None:
+            q, k = r
+        else:
+            r = glue_ops.rope(q, k, cs[2], cs[3])
+            assert r is not None, "the rotary kernel declined the projection output"
+            q, k = r
+            kc.index_copy_(2, pos, k)
+            vc.index_copy_(2, pos, v)
         if T > 1:  # prefill from an empty cache: causal attention over the new tokens
             a = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True)
         else:      # decode: attend to the first cache_len + 1 cache positions

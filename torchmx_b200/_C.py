@@ -14,7 +14,7 @@ HP_BF16, HP_F32 = 0, 1
 FLAG_HW_EXACT = 1
 FLAG_OPERAND_LAYOUT = 2
 GEMM_B_STATIC, GEMM_WIDE_TILES, GEMM_NO_PDL, GEMM_NO_MXF4 = 1, 2, 4, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_DIMS = 6
 
 EXPORTS = ("mxq_quantize", "mxq_dequantize", "mxq_dequantize_strided", "mxq_gemm", "mxq_gemm_dequant", "mxq_gemm_bf16", "mxq_transcode_to_e4m3", "mxq_pack_operand", "mxq_unpack_operand",
@@ -102,6 +102,10 @@ class RopeArgs(ctypes.Structure):
         ("cos", ctypes.c_void_p), ("sin", ctypes.c_void_p), ("cs_tok_stride", ctypes.c_int64), ("cs_batch_stride", ctypes.c_int64),
         ("batch", ctypes.c_int64), ("tokens", ctypes.c_int64), ("head_dim", ctypes.c_int),
         ("q_out", ctypes.c_void_p), ("k_out", ctypes.c_void_p),
+        ("q_out_batch_stride", ctypes.c_int64), ("q_out_head_stride", ctypes.c_int64), ("q_out_tok_stride", ctypes.c_int64),
+        ("k_out_batch_stride", ctypes.c_int64), ("k_out_head_stride", ctypes.c_int64), ("k_out_tok_stride", ctypes.c_int64),
+        ("v", ctypes.c_void_p), ("v_tok_stride", ctypes.c_int64), ("v_batch_stride", ctypes.c_int64),
+        ("v_out", ctypes.c_void_p), ("v_out_batch_stride", ctypes.c_int64), ("v_out_head_stride", ctypes.c_int64), ("v_out_tok_stride", ctypes.c_int64),
     ]
 
 

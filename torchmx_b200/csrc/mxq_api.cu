@@ -87,7 +87,7 @@ int waves_override() { static int v = env_int("MXQ_WAVES"); return v > 0 ? v : 0
 extern "C" {
 
 const char* mxq_last_error(void) { return g_err; }
-int mxq_version(void) { return 2; }
+int mxq_version(void) { return 3; }
 int mxq_arch(void) { return 1000; }
 
 int mxq_quantize(const void* src, int src_dtype, int64_t n_blocks, int block_size, int elem, unsigned flags, void* codes, uint8_t* scales,

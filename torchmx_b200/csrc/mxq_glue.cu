@@ -126,9 +126,10 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const NormParams 
 }
 
 struct RopeParams {
-    const uint16_t* in[2]; uint16_t* out[2];
-    int64_t in_tok_stride[2], in_batch_stride[2];
-    int heads[2];
+    const uint16_t* in[3]; uint16_t* out[3];  // q, k and (optional, unrotated) v
+    int64_t in_tok_stride[3], in_batch_stride[3];
+    int64_t out_batch_stride[3], out_head_stride[3], out_tok_stride[3];
+    int heads[3];
     const uint16_t* cos; const uint16_t* sin;
     int64_t cs_batch_stride, cs_tok_stride;
     int64_t batch, tokens; int head_dim;
@@ -138,11 +139,11 @@ struct RopeParams {
 __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
     pdl_launch_dependents();
     const int half_chunks = p.head_dim / 16;  // 8-element chunks per half head
-    const int64_t per_tok[2] = {(int64_t)p.heads[0] * half_chunks, (int64_t)p.heads[1] * half_chunks};
-    const int64_t n0 = p.batch * p.tokens * per_tok[0], n1 = p.batch * p.tokens * per_tok[1];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += (int64_t)gridDim.x * blockDim.x) {
-        const int which = i >= n0;
-        int64_t r = which ? i - n0 : i;
+    const int64_t n0 = p.batch * p.tokens * p.heads[0] * half_chunks, n1 = p.batch * p.tokens * p.heads[1] * half_chunks;
+    const int64_t n2 = p.in[2] != nullptr ? p.batch * p.tokens * p.heads[2] * half_chunks : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1 + n2; i += (int64_t)gridDim.x * blockDim.x) {
+        const int which = i >= n0 + n1 ? 2 : (i >= n0 ? 1 : 0);
+        int64_t r = which == 2 ? i - n0 - n1 : (which ? i - n0 : i);
         const int c = (int)(r % half_chunks); r /= half_chunks;
         const int h = (int)(r % p.heads[which]); r /= p.heads[which];
         const int64_t t = r % p.tokens, b = r / p.tokens;
@@ -150,6 +151,12 @@ __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
         const uint16_t* pc = p.cos + b * p.cs_batch_stride + t * p.cs_tok_stride + c * 8;
         const uint16_t* ps = p.sin + b * p.cs_batch_stride + t * p.cs_tok_stride + c * 8;
         const int hd2 = p.head_dim / 2;
+        uint16_t* dst = p.out[which] + b * p.out_batch_stride[which] + (int64_t)h * p.out_head_stride[which] + t * p.out_tok_stride[which] + c * 8;
+        if (which == 2) {  // the value heads: a plain copy into their (cache) layout
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+            *reinterpret_cast<uint4*>(dst + hd2) = *reinterpret_cast<const uint4*>(src + hd2);
+            continue;
+        }
         const uint4 x1 = *reinterpret_cast<const uint4*>(src), x2 = *reinterpret_cast<const uint4*>(src + hd2);
         const uint4 c1 = *reinterpret_cast<const uint4*>(pc), c2 = *reinterpret_cast<const uint4*>(pc + hd2);
         const uint4 s1 = *reinterpret_cast<const uint4*>(ps), s2 = *reinterpret_cast<const uint4*>(ps + hd2);
@@ -167,7 +174,6 @@ __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
             o1[j] = pack_bf16x2(lo1, hi1);
             o2[j] = pack_bf16x2(lo2, hi2);
         }
-        uint16_t* dst = p.out[which] + ((b * p.heads[which] + h) * p.tokens + t) * p.head_dim + c * 8;
         *reinterpret_cast<uint4*>(dst) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
         *reinterpret_cast<uint4*>(dst + hd2) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
     }
@@ -324,16 +330,32 @@ int launch_rope(const mxq_rope_args_t* a, int sm_count, cudaStream_t stream, cha
         snprintf(msg, msg_len, "needs head_dim %% 16 == 0 and 16-byte aligned heads");
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
+    const bool has_v = a->v != nullptr;
+    const int64_t out_strides[9] = {a->q_out_batch_stride, a->q_out_head_stride, a->q_out_tok_stride, a->k_out_batch_stride, a->k_out_head_stride,
+                                    a->k_out_tok_stride, a->v_out_batch_stride, a->v_out_head_stride, a->v_out_tok_stride};
+    for (int i = 0; i < 9; ++i)
+        if (out_strides[i] % 8) { snprintf(msg, msg_len, "output strides must be multiples of 8 elements"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
+    if (has_v && (!a->v_out || !al16(a->v) || !al16(a->v_out) || (a->v_tok_stride % 8) || (a->v_batch_stride % 8))) {
+        snprintf(msg, msg_len, "v needs v_out and 16-byte aligned heads");
+        return MXQ_ERR_UNSUPPORTED_SHAPE;
+    }
     RopeParams p;
-    p.in[0] = (const uint16_t*)a->q; p.in[1] = (const uint16_t*)a->k;
-    p.out[0] = (uint16_t*)a->q_out; p.out[1] = (uint16_t*)a->k_out;
-    p.in_tok_stride[0] = a->q_tok_stride; p.in_tok_stride[1] = a->k_tok_stride;
-    p.in_batch_stride[0] = a->q_batch_stride; p.in_batch_stride[1] = a->k_batch_stride;
-    p.heads[0] = a->q_heads; p.heads[1] = a->k_heads;
+    p.in[0] = (const uint16_t*)a->q; p.in[1] = (const uint16_t*)a->k; p.in[2] = (const uint16_t*)a->v;
+    p.out[0] = (uint16_t*)a->q_out; p.out[1] = (uint16_t*)a->k_out; p.out[2] = (uint16_t*)a->v_out;
+    p.in_tok_stride[0] = a->q_tok_stride; p.in_tok_stride[1] = a->k_tok_stride; p.in_tok_stride[2] = a->v_tok_stride;
+    p.in_batch_stride[0] = a->q_batch_stride; p.in_batch_stride[1] = a->k_batch_stride; p.in_batch_stride[2] = a->v_batch_stride;
+    p.heads[0] = a->q_heads; p.heads[1] = a->k_heads; p.heads[2] = a->k_heads;
+    for (int w = 0; w < 3; ++w) {  // 0 / 0 / 0 = contiguous [batch, heads, tokens, head_dim]
+        const int64_t bs = out_strides[3 * w], hs = out_strides[3 * w + 1], ts = out_strides[3 * w + 2];
+        const bool contiguous = bs == 0 && hs == 0 && ts == 0;
+        p.out_tok_stride[w] = contiguous ? a->head_dim : ts;
+        p.out_head_stride[w] = contiguous ? a->tokens * a->head_dim : hs;
+        p.out_batch_stride[w] = contiguous ? (int64_t)p.heads[w] * a->tokens * a->head_dim : bs;
+    }
     p.cos = (const uint16_t*)a->cos; p.sin = (const uint16_t*)a->sin;
     p.cs_batch_stride = a->cs_batch_stride; p.cs_tok_stride = a->cs_tok_stride;
     p.batch = a->batch; p.tokens = a->tokens; p.head_dim = a->head_dim;
-    const int64_t n = a->batch * a->tokens * (int64_t)(a->q_heads + a->k_heads) * (a->head_dim / 16);
+    const int64_t n = a->batch * a->tokens * (int64_t)(a->q_heads + a->k_heads * (has_v ? 2 : 1)) * (a->head_dim / 16);
     const int64_t want = (n + 255) / 256, cap = (int64_t)sm_count * 16;
     rope_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(p);
     const cudaError_t e = cudaGetLastError();

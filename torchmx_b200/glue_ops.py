@@ -95,9 +95,21 @@ def _head_view(t: torch.Tensor, head_dim: int):
     return (t.stride(0) if t.shape[0] > 1 else 0), (t.stride(2) if t.shape[2] > 1 else t.shape[1] * head_dim)
 
 
-def rope(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+def _out_view(t: torch.Tensor, like: torch.Tensor):
+    """a caller-provided output [batch, heads, tokens, head_dim] (e.g. a slice of a KV cache): its three leading strides, or None"""
+    if not _plain_bf16(t, like.device) or t.shape != like.shape or t.stride(3) != 1 or t.data_ptr() % 16 or any(st % 8 for st in t.stride()[:3]):
+        return None
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def rope(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, k_out: Optional[torch.Tensor] = None,
+         v: Optional[torch.Tensor] = None, v_out: Optional[torch.Tensor] = None) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
     """q / k: [batch, heads, tokens, head_dim] (transposed views of the [batch, tokens, heads * head_dim] projection outputs);
-    cos / sin: bf16 [batch | 1, tokens, head_dim] -> rotated (q, k), contiguous [batch, heads, tokens, head_dim]"""
+    cos / sin: bf16 [batch | 1, tokens, head_dim] -> rotated (q, k), contiguous [batch, heads, tokens, head_dim].
+
+    `k_out` (optional): where the rotated keys go instead of a fresh tensor -- any [batch, heads, tokens, head_dim] view with unit
+    last stride, e.g. `key_cache[:, :, pos : pos + tokens]`, so the cache update needs no launch of its own.  `v` / `v_out`
+    (optional, together): the value heads (k's geometry) are copied unrotated into `v_out` by the same launch."""
     if not _ENABLED or not _plain_bf16(q) or not _plain_bf16(k, q.device) or not _plain_bf16(cos, q.device) or not _plain_bf16(sin, q.device):
         return None
     if q.dim() != 4 or k.dim() != 4 or q.numel() == 0 or k.numel() == 0:
@@ -117,7 +129,22 @@ def rope(q: torch.Tensor, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor)
     a.cs_batch_stride = cos.stride(0) if cos.shape[0] > 1 else 0
     a.batch, a.tokens, a.head_dim = b, t, d
     q_out = torch.empty((b, hq, t, d), dtype=torch.bfloat16, device=q.device)
-    k_out = torch.empty((b, k.shape[1], t, d), dtype=torch.bfloat16, device=q.device)
+    if k_out is None:
+        k_out = torch.empty((b, k.shape[1], t, d), dtype=torch.bfloat16, device=q.device)
+    else:
+        ko = _out_view(k_out, k)
+        if ko is None:
+            return None
+        a.k_out_batch_stride, a.k_out_head_stride, a.k_out_tok_stride = ko
+    if (v is None) != (v_out is None):
+        return None
+    if v is not None:
+        vv, vo = (_head_view(v, d) if _plain_bf16(v, q.device) and v.shape == k.shape else None), _out_view(v_out, k)
+        if vv is None or vo is None:
+            return None
+        a.v, a.v_batch_stride, a.v_tok_stride = v.data_ptr(), vv[0], vv[1]
+        a.v_out = v_out.data_ptr()
+        a.v_out_batch_stride, a.v_out_head_stride, a.v_out_tok_stride = vo
     a.q_out, a.k_out = q_out.data_ptr(), k_out.data_ptr()
     rc = _C.lib().mxq_rope(a, q.device.index, _stream_ptr(q))
     if rc == _C.ERR_UNSUPPORTED_SHAPE:
