@@ -16,7 +16,9 @@ There is no CPU implementation: tensors must live on a CUDA device, otherwise th
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import threading
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -41,6 +43,40 @@ def _stream_ptr(t: torch.Tensor) -> int:
 
 
 # ------------------------------------------------------------------------------------------------
+# where the scale tensors of a whole-model quantization live
+# ------------------------------------------------------------------------------------------------
+# The E8M0 scales of most transformer weights are smaller than 1 MiB (q_proj of Llama-8B: 512 KiB, k_proj: 128 KiB), which is the
+# caching allocator's SMALL pool: 2 MiB segments of their own, each a cudaMalloc -- and on a box with tens of GB mapped one such call
+# was measured at 1-18 ms, 20+ of them per `quantize_linear_` (tools/quantize_linear_diag.py), while the memory of the bf16 weights
+# being released sits unused in the large pool.  Inside `small_scale_arena()` scale tensors below 1 MiB are carved out of large-pool
+# chunks instead (views, 256-byte aligned; a chunk lives as long as any scale in it).  Values and layouts are unchanged.
+_arena_state = threading.local()
+
+
+@contextlib.contextmanager
+def small_scale_arena(chunk_bytes: int = 32 << 20):
+    prev = getattr(_arena_state, "cur", None)
+    _arena_state.cur = {"buf": None, "off": 0, "chunk": int(chunk_bytes)}
+    try:
+        yield
+    finally:
+        _arena_state.cur = prev
+
+
+def _empty_scales(shape, device) -> torch.Tensor:
+    n = math.prod(shape)
+    a = getattr(_arena_state, "cur", None)
+    if a is None or n == 0 or n >= (1 << 20) or torch.cuda.is_current_stream_capturing():
+        return torch.empty(shape, dtype=torch.uint8, device=device)
+    need = (n + 255) & ~255
+    if a["buf"] is None or a["buf"].device != device or a["off"] + need > a["buf"].numel():
+        a["buf"], a["off"] = torch.empty(max(a["chunk"], need), dtype=torch.uint8, device=device), 0
+    out = a["buf"][a["off"]:a["off"] + n].view(shape)
+    a["off"] += need
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # custom ops
 # ------------------------------------------------------------------------------------------------
 def _quantize_mx_impl(data_hp: torch.Tensor, elem_dtype_name: str, block_size: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -61,7 +97,7 @@ def _quantize_mx_impl(data_hp: torch.Tensor, elem_dtype_name: str, block_size: i
     x = data_hp.contiguous()
     shape = tuple(x.shape)
     n_blocks = x.numel() // block_size
-    scales = torch.empty(shape[:-1] + (shape[-1] // block_size,), dtype=torch.uint8, device=x.device)
+    scales = _empty_scales(shape[:-1] + (shape[-1] // block_size,), x.device)
     if elem == dtypes.float4_e2m1:
         assert shape[-1] % 2 == 0  # pack_uint4's requirement (utils.py:143)
         codes = torch.empty(shape[:-1] + (shape[-1] // 2,), dtype=torch.uint8, device=x.device)

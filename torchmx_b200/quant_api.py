@@ -15,6 +15,7 @@ import torch
 
 from .config import QAttentionConfig, QLinearConfig
 from .layers.mx_linear import MXInferenceLinear
+from .mx_tensor import small_scale_arena
 from .utils import get_logger
 
 logger = get_logger(__name__)
@@ -51,12 +52,13 @@ def quantize_linear_(model: torch.nn.Module, qconfig: QLinearConfig, layer_filte
         on_visit = lambda fqn: bar.update(1)  # noqa: E731
     except Exception:  # tqdm is optional
         bar, on_visit = None, None
-    _swap_children(
-        model,
-        replacement_fn=lambda mod: MXInferenceLinear.from_float(mod, qconfig),
-        filter_fn=lambda mod, fqn: type(mod) is torch.nn.Linear and (layer_filter is None or layer_filter(fqn)),
-        on_visit=on_visit,
-    )
+    with small_scale_arena():  # (sub-MiB scale tensors share large-pool chunks: no 2 MiB cudaMalloc per handful of layers)
+        _swap_children(
+            model,
+            replacement_fn=lambda mod: MXInferenceLinear.from_float(mod, qconfig),
+            filter_fn=lambda mod, fqn: type(mod) is torch.nn.Linear and (layer_filter is None or layer_filter(fqn)),
+            on_visit=on_visit,
+        )
     if bar is not None:
         bar.close()
 
@@ -124,7 +126,8 @@ def quantize_llm_(model: torch.nn.Module, qattention_config: QAttentionConfig, q
         cls = table[type(mod)]
         return cls.from_float(mod, qattention_config if type(mod) in ATTENTION_LAYERS else qmlp_config)
 
-    _swap_children(model, replacement_fn=replace, filter_fn=lambda mod, fqn: type(mod) in table)
+    with small_scale_arena():
+        _swap_children(model, replacement_fn=replace, filter_fn=lambda mod, fqn: type(mod) in table)
     quantize_linear_(model, qmlp_config)
     if fuse_rmsnorm:
         _fuse_norms_(model)
