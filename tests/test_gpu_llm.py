@@ -327,3 +327,28 @@ def test_decode_under_sdpa_groups_query_heads_instead_of_repeating_kv(tiny_llama
         assert mlp_ops.stats["fused_silu_mul"] - n0 == 2 * 9  # prefill + 8 decode steps, two layers: gating + quantization in one launch
         outs.append(torch.cat(steps, 1))
     assert _sqnr(outs[1], outs[0]) > 35, _sqnr(outs[1], outs[0])
+
+
+def test_additive_mask_cache_does_not_leak_graph_pool_tensors():
+    """the boolean -> additive mask conversion is shared by the layers of one forward pass, also while a CUDA graph is captured,
+    but a tensor made during a capture (it lives in the graph's pool) is never handed to a later eager call or capture"""
+    import torchmx  # noqa: F401
+    from torchmx.layers import mx_llama_attention as mla
+    mask = torch.ones(2, 1, 4, 64, dtype=torch.bool, device=DEV).tril_(32)
+    a0 = mla._additive_mask(mask, torch.bfloat16, 0)
+    assert mla._additive_mask(mask, torch.bfloat16, 1) is a0          # eager: one conversion per mask object
+    g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(g, stream=st):
+            c0 = mla._additive_mask(mask, torch.bfloat16, 0)
+            c1 = mla._additive_mask(mask, torch.bfloat16, 1)
+            c5 = mla._additive_mask(mask, torch.bfloat16, 5)
+    assert c0 is not a0 and c1 is c0 and c5 is c0                    # the capture makes its own, once
+    e = mla._additive_mask(mask, torch.bfloat16, 3)
+    assert e is not c0                                               # ... and it does not escape the capture
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(g2, stream=st):
+            d0 = mla._additive_mask(mask, torch.bfloat16, 0)
+    assert d0 is not c0 and d0 is not e
+    assert torch.equal(e, torch.zeros_like(e).masked_fill_(~mask, torch.finfo(torch.bfloat16).min))

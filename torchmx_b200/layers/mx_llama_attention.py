@@ -182,18 +182,31 @@ def _repeat_heads(t: MXTensor, n_rep: int) -> MXTensor:
 _mask_cache = (None, None)  # (weakref to the boolean mask tensor, its additive form): one conversion per forward, not per layer
 
 
-def _additive_mask(mask: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    global _mask_cache
+_mask_cache_layer = None  # layer index of the block that filled the cache while a CUDA graph was being captured
+
+
+def _additive_mask(mask: torch.Tensor, dtype: torch.dtype, layer_idx: Optional[int] = None) -> torch.Tensor:
+    """One conversion per forward, not per layer.  Outside graph capture the entry is keyed by the mask object and its version.
+    A tensor made WHILE a graph is captured lives in that graph's memory pool and must not be handed out after the capture: during
+    capture an entry is therefore only reused by blocks with a HIGHER layer index than the one that made it (the later layers of
+    the same forward pass); the first block of the next pass makes a new one."""
+    global _mask_cache, _mask_cache_layer
     import weakref
+    capturing = torch.cuda.is_current_stream_capturing()
     ref, add = _mask_cache
-    if ref is not None and ref[0]() is mask and ref[1] == mask._version and add.dtype == dtype and not torch.cuda.is_current_stream_capturing():
-        return add
+    if ref is not None and ref[0]() is mask and ref[1] == mask._version and add.dtype == dtype:
+        if not capturing and _mask_cache_layer is None:
+            return add
+        if capturing and _mask_cache_layer is not None and layer_idx is not None and layer_idx > _mask_cache_layer:
+            return add
     # finfo.min, not -inf (what transformers' eager mask and the reference's 4.44 causal mask use): a query row that may attend
     # to nothing -- left padding under the sdpa mask interface -- then softmaxes to a uniform row instead of NaN, and NaN would
     # spread to every token of the batch through the next layer's K / V
     add = torch.zeros_like(mask, dtype=dtype).masked_fill_(~mask, torch.finfo(dtype).min)
-    if not torch.cuda.is_current_stream_capturing():
-        _mask_cache = ((weakref.ref(mask), mask._version), add)
+    if not capturing:
+        _mask_cache, _mask_cache_layer = ((weakref.ref(mask), mask._version), add), None
+    elif layer_idx is not None:
+        _mask_cache, _mask_cache_layer = ((weakref.ref(mask), mask._version), add), layer_idx
     return add
 
 
@@ -261,7 +274,7 @@ class _MXAttentionMixin:
         if attention_mask is not None:  # no matter the length, we just slice it (reference :218-220)
             mask = attention_mask[:, :, :, :kv_len]
             if mask.dtype == torch.bool:  # the sdpa mask interface hands out "may attend" booleans instead of an additive mask
-                mask = _additive_mask(attention_mask, dtype)[:, :, :, :kv_len]
+                mask = _additive_mask(attention_mask, dtype, getattr(self, "layer_idx", None))[:, :, :, :kv_len]
         elif q_len > 1 and getattr(self, "is_causal", True):
             causal = True  # mask creation was skipped because the attention function is expected to apply is_causal itself
         dropout = self.training and getattr(self, "attention_dropout", 0.0)
