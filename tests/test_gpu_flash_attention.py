@@ -84,6 +84,11 @@ CASES = [
     (1, 2, 2, 300, 416, "mask+pad"),
     (1, 2, 2, 5, 352, "none"),
     (1, 2, 2, 64, 1000 // 32 * 32, "causal"),
+    # at most 128 query rows per (batch, head): the one-tile variant of the kernel (two CTAs per SM)
+    (2, 4, 2, 100, 640, "mask+pad"),
+    (1, 2, 2, 128, 512, "mask+causal"),
+    (2, 8, 2, 1, 1024, "mask"),         # decode against a long cache
+    (32, 32, 8, 1, 256, "mask"),        # the decode step of BASELINE configs[3]: batch 32, four query heads per key / value head
 ]
 
 

@@ -26,6 +26,7 @@
 //                (128 channels x 128 keys)
 //   warp 17      MMA issuer (one elected lane): S = Q K^T as two N = 64 halves per 128-key chunk, O += P V per chunk
 //   warp 18      scale-factor loader: Q / K / V E8M0 scales from their reference layout into the tcgen05.cp chunk layout
+// (At most 128 query rows per (batch, head) -- decode -- run a one-tile variant: eight softmax warps, two CTAs per SM; see Cfg.)
 // Causal attention without an explicit mask skips the key chunks a query tile's rows cannot see; with an explicit additive mask
 // pass A records the largest score of every (row, chunk) and passes B / C skip the chunks that are dead for a whole tile.
 // The key axis may be any multiple of 32 (a ragged last chunk is zero-filled by TMA and hidden).
@@ -41,42 +42,53 @@ namespace fa {
 constexpr int QT = 128;     // query rows per warpgroup
 constexpr int KC = 128;     // keys per chunk: four MX blocks of P = one 32-bit scale word per row
 constexpr int HD = 128;     // head_dim
-constexpr int K_STAGES = 3, V_STAGES = 2;
-constexpr int kSoftmaxWarps = 16;
-constexpr int kThreads = kSoftmaxWarps * 32 + 96;
 constexpr int kWgThreads = 256;  // softmax threads per query tile: two per row
 constexpr int TILE_BYTES = 128 * 128;
 
-struct Smem {
+// TILES = query tiles (of 128 rows) per CTA.  2: the prefill configuration described above, one CTA per SM.  1: queries of at most
+// 128 rows per (batch, head) -- decode, where the grouped query heads of a key / value head are the rows -- with eight softmax
+// warps, shallower K / V rings and half the tensor memory, so that TWO CTAs share an SM: a decode step is hundreds of small CTAs
+// whose time is a chain of barrier round trips, not bandwidth.
+template <int TILES>
+struct Cfg {
+    static constexpr int K_STAGES = TILES == 2 ? 3 : 2, V_STAGES = TILES == 2 ? 2 : 1;
+    static constexpr int kSoftmaxWarps = 8 * TILES;
+    static constexpr int kThreads = kSoftmaxWarps * 32 + 96;
+    // TMEM columns
+    static constexpr uint32_t TM_S = 0;                       // + 64 * wg
+    static constexpr uint32_t TM_O = 64 * TILES;              // + 128 * wg
+    static constexpr uint32_t TM_SFQ = TM_O + 128 * TILES;    // + 4 * wg
+    static constexpr uint32_t TM_SFK = TM_SFQ + 4 * TILES;    // + 8 * (chunk & 1) + 4 * half
+    static constexpr uint32_t TM_SFP = TM_SFK + 16;           // + 4 * wg
+    static constexpr uint32_t TM_SFV = TM_SFP + 4 * TILES;    // + 4 * (chunk & 1)
+    static constexpr int TMEM_COLS = TILES == 2 ? 512 : 256;
+    static_assert(TM_SFV + 8 <= TMEM_COLS, "tensor memory budget");
+};
+
+template <int TILES>
+struct SmemT {
+    static constexpr int K_STAGES = Cfg<TILES>::K_STAGES, V_STAGES = Cfg<TILES>::V_STAGES;
     static constexpr int OFF_Q = 0;
-    static constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;
+    static constexpr int OFF_K = OFF_Q + TILES * TILE_BYTES;
     static constexpr int OFF_V = OFF_K + K_STAGES * TILE_BYTES;
     static constexpr int OFF_P = OFF_V + V_STAGES * TILE_BYTES;
-    static constexpr int OFF_SFQ = OFF_P + 2 * TILE_BYTES;
-    static constexpr int OFF_SFK = OFF_SFQ + 2 * 512;             // per stage: two 512-byte chunks (keys 0..63, 64..127)
+    static constexpr int OFF_SFQ = OFF_P + TILES * TILE_BYTES;
+    static constexpr int OFF_SFK = OFF_SFQ + TILES * 512;             // per stage: two 512-byte chunks (keys 0..63, 64..127)
     static constexpr int OFF_SFV = OFF_SFK + K_STAGES * 1024;
     static constexpr int OFF_SFP = OFF_SFV + V_STAGES * 512;
-    static constexpr int OFF_CMAX = OFF_SFP + 2 * 512;            // [wg][chunk <= 64][row] bf16: largest score of the chunk, from pass A
-    static constexpr int OFF_LIVE = OFF_CMAX + 2 * 64 * 128 * 2;  // [wg][2] words: chunks with a row that still counts after the row maximum is known
-    static constexpr int OFF_XCH = OFF_LIVE + 16;                 // [wg][parity 2][sub 2][value 2][row 128] fp32: what a row's two threads exchange per chunk
-    static constexpr int OFF_XMAX = OFF_XCH + 2 * 1024 * 4;       // [wg][sub][row] fp32: partial row maxima
-    static constexpr int OFF_BAR = OFF_XMAX + 2 * 256 * 4;
+    static constexpr int OFF_CMAX = OFF_SFP + TILES * 512;            // [wg][chunk <= 64][row] bf16: largest score of the chunk, from pass A
+    static constexpr int OFF_LIVE = OFF_CMAX + TILES * 64 * 128 * 2;  // [wg][2] words: chunks with a row that still counts after the row maximum is known
+    static constexpr int OFF_XCH = OFF_LIVE + 16;                     // [wg][parity 2][sub 2][value 2][row 128] fp32: what a row's two threads exchange per chunk
+    static constexpr int OFF_XMAX = OFF_XCH + TILES * 1024 * 4;       // [wg][sub][row] fp32: partial row maxima
+    static constexpr int OFF_BAR = OFF_XMAX + TILES * 256 * 4;
     // q_full, qsf_full, k_full/ksf_full/k_empty[K_STAGES], v_full/vsf_full/v_empty[V_STAGES], sa_full/sa_free[2][2],
     // sc_full/sc_free/p_full/p_free/o_full[2]
     static constexpr int NUM_BARS = 2 + 3 * K_STAGES + 3 * V_STAGES + 18 + 2;
     static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM_PTR + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
-    static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(DYN_BYTES <= (TILES == 2 ? 227 : 113) * 1024, "shared memory budget");
 };
-
-// TMEM columns (512 allocated)
-constexpr uint32_t TM_S = 0;       // + 64 * wg
-constexpr uint32_t TM_O = 128;     // + 128 * wg
-constexpr uint32_t TM_SFQ = 384;   // + 4 * wg
-constexpr uint32_t TM_SFK = 392;   // + 8 * (chunk & 1) + 4 * half
-constexpr uint32_t TM_SFP = 408;   // + 4 * wg
-constexpr uint32_t TM_SFV = 416;   // + 4 * (chunk & 1)
 
 struct Params {
     const uint8_t* q_sf; const uint8_t* k_sf; const uint8_t* v_sf;
@@ -123,9 +135,13 @@ __device__ __forceinline__ void container_bytes(const uint32_t (&out)[(ELEM == M
     }
 }
 
-template <int ELEM, bool TABLE>
-__global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                                                                         const __grid_constant__ CUtensorMap map_v, const Params p) {
+template <int ELEM, bool TABLE, int TILES>
+__global__ void __launch_bounds__(Cfg<TILES>::kThreads, TILES == 2 ? 1 : 2)
+mx_flash_attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, const Params p) {
+    using C = Cfg<TILES>;
+    using Smem = SmemT<TILES>;
+    constexpr int K_STAGES = C::K_STAGES, V_STAGES = C::V_STAGES, kSoftmaxWarps = C::kSoftmaxWarps;
+    constexpr uint32_t TM_S = C::TM_S, TM_O = C::TM_O, TM_SFQ = C::TM_SFQ, TM_SFK = C::TM_SFK, TM_SFP = C::TM_SFP, TM_SFV = C::TM_SFV;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);
@@ -155,11 +171,11 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     const int b = bh / p.heads, h = bh - b * p.heads;
     const int bhk = b * p.kv_heads + h / (p.heads / p.kv_heads);  // grouped-query attention: the key / value head of this query head
     const int n_total = (p.kv_len + KC - 1) / KC;  // (kv_len % 32 == 0; the last chunk may hold 1..3 blocks: the rest reads as zero and is hidden)
-    int nv[2];
-    bool active[2];
+    int nv[2] = {0, 0};
+    bool active[2] = {false, false};
 #pragma unroll
-    for (int wg = 0; wg < 2; ++wg) {
-        const int q0 = qt * 2 * QT + wg * QT;
+    for (int wg = 0; wg < TILES; ++wg) {
+        const int q0 = qt * TILES * QT + wg * QT;
         active[wg] = q0 < p.q_len;
         const int last_row = min(q0 + QT - 1, p.q_len - 1);
         nv[wg] = !active[wg] ? 0 : (p.skip_hidden_chunks ? min(n_total, (last_row + p.causal_offset) / KC + 1) : n_total);
@@ -184,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         for (int i = 0; i < 4; ++i) live_words[i] = 0;
         fence_barrier_init();
     }
-    if (warp == kSoftmaxWarps + 2) tmem_alloc<512>(tmem_ptr);
+    if (warp == kSoftmaxWarps + 2) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -195,8 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     // rows of a warpgroup are skipped by passes B and C -- by the softmax threads, the tensor core and the loaders alike.
     constexpr bool use_table = TABLE;  // (launched with TABLE == (mask != nullptr): the implied-causal path carries none of this)
     auto live_chunks = [&](uint64_t (&live)[2]) {  // (callers other than the softmax threads: waits for pass A of both warpgroups)
+        live[0] = live[1] = 0;
 #pragma unroll
-        for (int wg = 0; wg < 2; ++wg) {
+        for (int wg = 0; wg < TILES; ++wg) {
             if (!active[wg]) { live[wg] = 0; continue; }
             if (use_table) {
                 mbar_wait(&scan_done[wg], 0);
@@ -216,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         // barrier of the 256 threads of the query tile.
         const int wg = warp >> 3, sub = (warp >> 2) & 1, quad = warp & 3;
         const int r = quad * 32 + lane;                 // row inside the warpgroup's tile = TMEM lane
-        const int q = qt * 2 * QT + wg * QT + r;        // query row
+        const int q = qt * TILES * QT + wg * QT + r;        // query row
         const bool row_live = active[wg] && q < p.q_len;
         const int my_n = nv[wg];
         const uint32_t tm_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -500,9 +517,9 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     } else if (warp == kSoftmaxWarps) {
         // ================= TMA producer =================
         if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, (active[1] ? 2 : 1) * TILE_BYTES);
-            tma_load_3d(&map_q, q_full, smem + Smem::OFF_Q, 0, qt * 2 * QT, bh);  // rows past q_len read as zero
-            if (active[1]) tma_load_3d(&map_q, q_full, smem + Smem::OFF_Q + TILE_BYTES, 0, qt * 2 * QT + QT, bh);
+            mbar_arrive_expect_tx(q_full, (TILES == 2 && active[1] ? 2 : 1) * TILE_BYTES);
+            tma_load_3d(&map_q, q_full, smem + Smem::OFF_Q, 0, qt * TILES * QT, bh);  // rows past q_len read as zero
+            if (TILES == 2 && active[1]) tma_load_3d(&map_q, q_full, smem + Smem::OFF_Q + TILE_BYTES, 0, qt * TILES * QT + QT, bh);
             uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
             uint64_t need = ~0ull;
             for (int pass = 0; pass < 3; ++pass) {
@@ -537,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         tc_fence_after();
         if (elect_one()) {
             tc_copy_sf(tmem_base + TM_SFQ, smem_desc(smem_u32(smem + Smem::OFF_SFQ), 128, kLayoutNone));
-            tc_copy_sf(tmem_base + TM_SFQ + 4, smem_desc(smem_u32(smem + Smem::OFF_SFQ + 512), 128, kLayoutNone));
+            if (TILES == 2) tc_copy_sf(tmem_base + TM_SFQ + 4, smem_desc(smem_u32(smem + Smem::OFF_SFQ + 512), 128, kLayoutNone));
         }
         __syncwarp();
         // O[wg] += P[wg] (chunk jj) x V (chunk jj)
@@ -553,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             if (elect_one()) tc_copy_sf(tm_sfv, smem_desc(smem_u32(smem + Smem::OFF_SFV + vs * 512), 128, kLayoutNone));
             __syncwarp();
 #pragma unroll
-            for (int wg = 0; wg < 2; ++wg) {
+            for (int wg = 0; wg < TILES; ++wg) {
                 if (!active[wg] || jj >= nv[wg] || !((live[wg] >> jj) & 1)) continue;
                 mbar_wait(&p_full[wg], pfull_par[wg]);
                 pfull_par[wg] ^= 1;
@@ -583,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
             if (pass == 1) {
                 live_chunks(live);
 #pragma unroll
-                for (int wg = 0; wg < 2; ++wg) {
+                for (int wg = 0; wg < TILES; ++wg) {
                     const uint64_t m = live[wg] & (nv[wg] >= 64 ? ~0ull : ((1ull << nv[wg]) - 1));
                     last_live[wg] = m ? 63 - __clzll((long long)m) : -1;
                 }
@@ -602,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-                    for (int wg = 0; wg < 2; ++wg) {
+                    for (int wg = 0; wg < TILES; ++wg) {
                         if (!active[wg] || j >= nv[wg] || (pass > 0 && !((live[wg] >> j) & 1))) continue;
                         uint32_t tm_s;
                         uint64_t* full_bar;
@@ -653,10 +670,10 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
         {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(p.q_sf) + (int64_t)bh * p.q_len;
 #pragma unroll
-            for (int wg = 0; wg < 2; ++wg) {
+            for (int wg = 0; wg < TILES; ++wg) {
                 uint32_t w[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) w[i] = src[min(qt * 2 * QT + wg * QT + i * 32 + lane, p.q_len - 1)];
+                for (int i = 0; i < 4; ++i) w[i] = src[min(qt * TILES * QT + wg * QT + i * 32 + lane, p.q_len - 1)];
                 *reinterpret_cast<uint4*>(smem + Smem::OFF_SFQ + wg * 512 + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
             }
             publish(qsf_full);
@@ -712,7 +729,7 @@ __global__ void __launch_bounds__(kThreads, 1) mx_flash_attention_kernel(const _
     __syncthreads();
     if (warp == kSoftmaxWarps + 2) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -744,7 +761,8 @@ int launch_flash_attention(const mxq_attention_args_t* a, int device, cudaStream
         return MXQ_ERR_UNSUPPORTED_SHAPE;
     }
     const int64_t bh = a->batch * a->heads, bhk = a->batch * a->kv_heads;
-    const int64_t q_tiles = (a->q_len + 2 * QT - 1) / (2 * QT);
+    const int tiles = a->q_len <= QT ? 1 : 2;  // query tiles per CTA: one (two CTAs per SM) when a (batch, head) has at most 128 query rows
+    const int64_t q_tiles = (a->q_len + tiles * QT - 1) / (tiles * QT);
     if (bh * q_tiles > 0x7FFFFFFF || a->q_len > 0x3FFFFFFF || a->kv_len > 0x3FFFFFFF) { snprintf(msg, msg_len, "extent too large"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
     CUtensorMap map_q, map_k, map_v;
     if (!cached_operand_map(&map_q, a->q_codes, HD, a->q_len, bh, HD, a->q_len * HD, 128, a->q_format, device) ||
@@ -773,15 +791,16 @@ int launch_flash_attention(const mxq_attention_args_t* a, int device, cudaStream
     p.flags = a->flags;
     p.q_tiles = (int)q_tiles;
     const unsigned grid = (unsigned)(bh * q_tiles);
-#define MXQ_FA_LAUNCH(E, T)                                                                                                         \
+#define MXQ_FA_LAUNCH(E, T, TL)                                                                                                     \
     {                                                                                                                               \
-        cudaError_t e = ensure_smem_attr((const void*)mx_flash_attention_kernel<E, T>, Smem::DYN_BYTES, device);                     \
+        cudaError_t e = ensure_smem_attr((const void*)mx_flash_attention_kernel<E, T, TL>, SmemT<TL>::DYN_BYTES, device);            \
         if (e != cudaSuccess) { snprintf(msg, msg_len, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }   \
-        mx_flash_attention_kernel<E, T><<<grid, fa::kThreads, Smem::DYN_BYTES, stream>>>(map_q, map_k, map_v, p);                    \
+        mx_flash_attention_kernel<E, T, TL><<<grid, Cfg<TL>::kThreads, SmemT<TL>::DYN_BYTES, stream>>>(map_q, map_k, map_v, p);      \
     }
 #define MXQ_FA_CASE(E)                                                                                                              \
     case E:                                                                                                                         \
-        if (a->mask != nullptr) MXQ_FA_LAUNCH(E, true) else MXQ_FA_LAUNCH(E, false)                                                  \
+        if (tiles == 1) { if (a->mask != nullptr) MXQ_FA_LAUNCH(E, true, 1) else MXQ_FA_LAUNCH(E, false, 1) }                        \
+        else { if (a->mask != nullptr) MXQ_FA_LAUNCH(E, true, 2) else MXQ_FA_LAUNCH(E, false, 2) }                                   \
         break;
     switch (a->p_elem) {
         MXQ_FA_CASE(MXQ_ELEM_E4M3) MXQ_FA_CASE(MXQ_ELEM_E3M2) MXQ_FA_CASE(MXQ_ELEM_E2M3) MXQ_FA_CASE(MXQ_ELEM_E2M1) MXQ_FA_CASE(MXQ_ELEM_E5M2)
