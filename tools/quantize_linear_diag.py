@@ -25,3 +25,26 @@ for trial in range(3):
           f"allocated {s0['allocated_bytes.all.current']/1e9:.2f} -> {s1['allocated_bytes.all.current']/1e9:.2f} GB, alloc retries {s1['num_alloc_retries']-s0['num_alloc_retries']}", flush=True)
     del model
     torch.cuda.empty_cache()
+
+if os.environ.get("MXQ_DIAG_LLM") == "1":  # the same for quantize_llm_ (MX attention / MLP blocks, fused norms), with a host profile
+    import cProfile, pstats, io
+    from torchmx_b200.config import QAttentionConfig
+    from torchmx_b200.quant_api import quantize_llm_
+    for trial in range(3):
+        with torch.no_grad():
+            model, cfg, info = lb.build("8b", None, "float6_e3m2", "float8_e4m3", quantize=False)
+        torch.cuda.synchronize()
+        s0 = torch.cuda.memory_stats()
+        pr = cProfile.Profile() if trial == 2 else None
+        t0 = time.perf_counter()
+        if pr: pr.enable()
+        quantize_llm_(model, QAttentionConfig(projection_config=qc), qc, fuse_rmsnorm=True)
+        if pr: pr.disable()
+        t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+        s1 = torch.cuda.memory_stats()
+        print(f"llm trial {trial}: host issue {1e3*(t1-t0):.1f} ms, with sync {1e3*(t2-t0):.1f} ms, cudaMalloc calls {s1['num_device_alloc']-s0['num_device_alloc']}, "
+              f"reserved +{(s1['reserved_bytes.all.current']-s0['reserved_bytes.all.current'])/1e9:.2f} GB", flush=True)
+        if pr:
+            st = pstats.Stats(pr); st.sort_stats("tottime"); buf = io.StringIO(); st.stream = buf; st.print_stats(12); print(buf.getvalue())
+        del model
+        torch.cuda.empty_cache()

@@ -94,6 +94,55 @@ def _fuse_linears(mods) -> Optional[MXInferenceLinear]:
     return fused
 
 
+def _stacked_from_float(srcs, qconfig: QLinearConfig):
+    """What `MXInferenceLinear.from_float` on every module of `srcs` followed by `_fuse_linears` gives -- (stacked layer, [per-module
+    layers whose weights are row slices of its storage]) -- with every weight quantized STRAIGHT into its rows of the stacked codes /
+    scales: no per-projection tensors, no concatenation (and, across the layers of a model, the stacked gate/up codes are exactly
+    the size of a bf16 projection weight being released, so the caching allocator serves them without going to the driver).  Same
+    kernel per projection, same bytes.  None when the modules do not qualify (the caller converts them one by one)."""
+    from ..mx_tensor import _empty_scales, _quantize_into
+    wc = qconfig.weights_config
+    ws = [getattr(m, "weight", None) for m in srcs]
+    w0 = ws[0]
+    if not all(type(m) is nn.Linear and isinstance(w, torch.Tensor) and not isinstance(w, MXTensor) and w.is_cuda and w.dtype == torch.bfloat16 and w.dim() == 2
+               and w.is_contiguous() and w.shape[1] == w0.shape[1] and w.device == w0.device for m, w in zip(srcs, ws)):
+        return None
+    K, bs, elem = w0.shape[1], wc.block_size, wc.elem_dtype
+    if K % bs or (elem.name == "float4_e2m1" and K % 2) or len({m.bias is None for m in srcs}) != 1:
+        return None
+    if srcs[0].bias is not None and any(m.bias.dtype != torch.bfloat16 or m.bias.device != w0.device for m in srcs):
+        return None
+    rows = [w.shape[0] for w in ws]
+    codes = torch.empty((sum(rows), K // 2 if elem.name == "float4_e2m1" else K), dtype=torch.int8 if elem.name == "int8" else torch.uint8, device=w0.device)
+    scales = _empty_scales((sum(rows), K // bs), w0.device)
+    layers, row = [], 0
+    bias_all = torch.cat([m.bias.data for m in srcs], 0) if srcs[0].bias is not None else None
+    for m, w, n in zip(srcs, ws, rows):
+        _quantize_into(w.data, elem, bs, codes[row:row + n], scales[row:row + n])
+        lin = MXInferenceLinear.__new__(MXInferenceLinear)
+        nn.Module.__init__(lin)
+        lin.in_features, lin.out_features, lin.qconfig = m.in_features, m.out_features, qconfig
+        lin.weight = nn.Parameter(MXTensor(scales[row:row + n], codes[row:row + n], elem, bs, torch.bfloat16), requires_grad=False)
+        mx_gemm.mark_static(lin.weight)
+        if bias_all is None:
+            lin.register_parameter("bias", None)
+        else:
+            lin.bias = nn.Parameter(bias_all[row:row + n], requires_grad=False)
+        layers.append(lin)
+        row += n
+    fused = MXInferenceLinear.__new__(MXInferenceLinear)
+    nn.Module.__init__(fused)
+    fused.in_features, fused.out_features, fused.qconfig = srcs[0].in_features, sum(rows), qconfig
+    fused.weight = nn.Parameter(MXTensor(scales, codes, elem, bs, torch.bfloat16), requires_grad=False)
+    mx_gemm.mark_static(fused.weight)
+    if bias_all is None:
+        fused.register_parameter("bias", None)
+    else:
+        fused.bias = nn.Parameter(bias_all, requires_grad=False)
+    fused._split = rows
+    return fused, layers
+
+
 GROUPED_DECODE_SDPA = os.environ.get("MXQ_GROUPED_DECODE_SDPA", "1") != "0"  # decode under sdpa: no repeat_kv copies (see forward)
 # q/k/v as ONE launch on the row-stacked weights at every size.  Round 1 stacked only decode-sized activations: the column slices
 # of a stacked output made every following elementwise kernel and copy strided (prefill 27.1 -> 29.3 ms).  Since K5b (rotary)
@@ -217,6 +266,12 @@ class _MXMLPMixin:
         assert isinstance(mod, cls.__mro__[2]), f"mod must be an instance of {cls.__mro__[2].__name__}, but got {type(mod)}"
         new = _shell_like(cls, mod, skip=("gate_proj", "up_proj", "down_proj"))
         new.qconfig = qconfig
+        stacked = _stacked_from_float([mod.gate_proj, mod.up_proj], qconfig) if FUSE_PROJECTIONS else None
+        if stacked is not None:
+            new.gate_proj, new.up_proj = stacked[1]
+            _swap_linears(new, mod, ("down_proj",), qconfig)
+            object.__setattr__(new, "_gate_up", stacked[0])
+            return new
         _swap_linears(new, mod, ("gate_proj", "up_proj", "down_proj"), qconfig)
         object.__setattr__(new, "_gate_up", _fuse_linears([new.gate_proj, new.up_proj]) if FUSE_PROJECTIONS else None)
         return new
@@ -248,6 +303,12 @@ class _MXAttentionMixin:
         assert isinstance(mod, cls.__mro__[2]), f"mod must be an instance of {cls.__mro__[2].__name__}, but got {type(mod)}"
         new = _shell_like(cls, mod, skip=("q_proj", "k_proj", "v_proj", "o_proj"))
         new.qconfig = qconfig
+        stacked = _stacked_from_float([mod.q_proj, mod.k_proj, mod.v_proj], qconfig.projection_config) if FUSE_PROJECTIONS else None
+        if stacked is not None:
+            new.q_proj, new.k_proj, new.v_proj = stacked[1]
+            _swap_linears(new, mod, ("o_proj",), qconfig.projection_config)
+            object.__setattr__(new, "_qkv", stacked[0])
+            return new
         _swap_linears(new, mod, ("q_proj", "k_proj", "v_proj", "o_proj"), qconfig.projection_config)
         object.__setattr__(new, "_qkv", _fuse_linears([new.q_proj, new.k_proj, new.v_proj]) if FUSE_PROJECTIONS else None)
         return new

@@ -113,6 +113,20 @@ def _quantize_mx_impl(data_hp: torch.Tensor, elem_dtype_name: str, block_size: i
     return scales, codes
 
 
+def _quantize_into(data_hp: torch.Tensor, elem: dtypes.DType, block_size: int, codes_out: torch.Tensor, scales_out: torch.Tensor) -> None:
+    """`_quantize_mx_impl` writing into caller-provided CONTIGUOUS code / scale tensors (internal: a block that stacks several
+    weights quantizes each of them straight into its rows of the stacked storage instead of quantizing and copying)."""
+    assert data_hp.dtype in _HP_ID and data_hp.is_contiguous() and codes_out.is_contiguous() and scales_out.is_contiguous()
+    assert data_hp.shape[-1] % block_size == 0 and scales_out.numel() * block_size == data_hp.numel()
+    assert codes_out.numel() * (2 if elem == dtypes.float4_e2m1 else 1) == data_hp.numel() and codes_out.device == data_hp.device == scales_out.device
+    _require_cuda(data_hp, "torchmx::quantize_mx")
+    flags = _C.FLAG_HW_EXACT if (elem in dtypes.SUPPORTED_FP_ELEM_DTYPES and env.MX_EXACT_QUANTIZATION == "True") else 0
+    if data_hp.numel():
+        rc = _C.lib().mxq_quantize(data_hp.data_ptr(), _HP_ID[data_hp.dtype], data_hp.numel() // block_size, block_size, dtypes.ELEM_ID[elem.name], flags,
+                                   codes_out.data_ptr(), scales_out.data_ptr(), data_hp.device.index, _stream_ptr(data_hp))
+        _C.check(rc, "torchmx::quantize_mx")
+
+
 @torch.library.custom_op("torchmx::quantize_mx", mutates_args=())
 def quantize_mx(data_hp: torch.Tensor, elem_dtype_name: str, block_size: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """The registered op (schema and semantics of the reference's, mx_tensor.py:36-96); body = `_quantize_mx_impl`."""
