@@ -616,6 +616,27 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * step_bytes(n_elems) * e2e_steps / e2e_s / 1e9 if e2e_steps else 0.0
+    # what the link itself does: the same pinned buffers copied in both directions at once, nothing else running (rank 0's number
+    # is reported; at N > 1 every rank copies at the same time, like in the e2e leg)
+    link = None
+    if e2e_steps:
+        dbuf_in, dbuf_out = torch.empty_like(xh, device=dev), torch.empty_like(xh, device=dev)
+        def duplex(reps):
+            for _ in range(reps):
+                with torch.cuda.stream(st[0]):
+                    dbuf_in.copy_(xh, non_blocking=True)
+                with torch.cuda.stream(st[1]):
+                    yhs[0].copy_(dbuf_out, non_blocking=True)
+            st[0].synchronize(); st[1].synchronize()
+        duplex(1)
+        barrier()
+        t0 = time.perf_counter()
+        duplex(6)
+        link_s = time.perf_counter() - t0
+        per_dir = 6 * xh.numel() * 2 / link_s / 1e9
+        link = {"each_direction_when_both_GBps": round(per_dir, 1), "e2e_achieved_per_direction_GBps": round(h2d * e2e_steps / e2e_s / 1e9, 1),
+                "frac": round((h2d * e2e_steps / e2e_s / 1e9) / per_dir, 3), "note": "512 MiB pinned copies, H2D and D2H at once, measured right after the e2e leg"}
+        del dbuf_in, dbuf_out
 
     extras = llama = tp70b = None
     del xs, xh, yhs, chs
@@ -652,7 +673,7 @@ def run_b200(args):
                        "parallelism": f"independent tensors per GPU x{world}, no collective"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": round(1e3 * e2e_s / max(e2e_steps, 1), 2), "note": "pinned host buffers, every PCIe copy of every step inside the timed region; four pipelined streams (H2D / D2H overlap, full-duplex PCIe), steps pipelined behind each other, one synchronize at the end of the timed region",
+                    "steps": e2e_steps, "ms_per_step": round(1e3 * e2e_s / max(e2e_steps, 1), 2), "pcie_link": link, "note": "pinned host buffers, every PCIe copy of every step inside the timed region; four pipelined streams (H2D / D2H overlap, full-duplex PCIe), steps pipelined behind each other, one synchronize at the end of the timed region",
                     "host_numa_node_of_rank0": numa},
             "gpu_launches": args.steps * 2 * len(ELEMS),
             "roofline": roofline,
