@@ -356,7 +356,9 @@ int launch_rope(const mxq_rope_args_t* a, int sm_count, cudaStream_t stream, cha
     p.cs_batch_stride = a->cs_batch_stride; p.cs_tok_stride = a->cs_tok_stride;
     p.batch = a->batch; p.tokens = a->tokens; p.head_dim = a->head_dim;
     const int64_t n = a->batch * a->tokens * (int64_t)(a->q_heads + a->k_heads * (has_v ? 2 : 1)) * (a->head_dim / 16);
-    const int64_t want = (n + 255) / 256, cap = (int64_t)sm_count * 16;
+    // one item per thread up to 64 CTAs per SM (a 2048-token prefill of Llama-8B is 2560 CTAs: capped at 16 per SM some threads took
+    // two items and the launch lasted as long as two)
+    const int64_t want = (n + 255) / 256, cap = (int64_t)sm_count * 64;
     rope_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
