@@ -19,7 +19,7 @@ def _ulps(a, b):
     return (key(a) - key(b)).abs()
 
 
-@pytest.mark.parametrize("shape", [(1, 7, 512), (3, 4096), (2, 33, 8192), (5, 96), (2, 16384)])
+@pytest.mark.parametrize("shape", [(1, 7, 512), (3, 4096), (2, 33, 8192), (5, 96), (2, 16384), (2048, 4096), (1, 1100, 512), (1024, 8192), (1030, 8224)])
 @pytest.mark.parametrize("residual", [False, True])
 def test_rmsnorm_matches_the_transformers_module(shape, residual):
     from transformers.models.llama.modeling_llama import LlamaRMSNorm
@@ -45,19 +45,20 @@ def test_rmsnorm_matches_the_transformers_module(shape, residual):
 
 @pytest.mark.parametrize("elem", ELEMS + ["float8_e5m2"])
 @pytest.mark.parametrize("mode", ["False", "True"])
-def test_rmsnorm_quantized_output_is_k1_of_its_own_bf16_output(elem, mode):
+@pytest.mark.parametrize("rows,hidden", [(67, 4096), (1500, 4096), (1024, 3072)])
+def test_rmsnorm_quantized_output_is_k1_of_its_own_bf16_output(elem, mode, rows, hidden):
     import torchmx  # noqa: F401
     from torchmx_b200 import dtypes, glue_ops
     from torchmx_b200 import env_variables as env
     from torchmx_b200.mx_tensor import MXTensor
     env.MX_EXACT_QUANTIZATION = mode
     g = torch.Generator(device=DEV).manual_seed(3)
-    x = torch.randn(67, 4096, device=DEV, dtype=torch.bfloat16, generator=g)
-    x *= torch.exp2(torch.randint(-30, 30, (67, 128), device=DEV, generator=g).float()).repeat_interleave(32, -1).to(torch.bfloat16)
+    x = torch.randn(rows, hidden, device=DEV, dtype=torch.bfloat16, generator=g)
+    x *= torch.exp2(torch.randint(-30, 30, (rows, hidden // 32), device=DEV, generator=g).float()).repeat_interleave(32, -1).to(torch.bfloat16)
     x[5, 100] = float("inf")   # the row statistic becomes inf -> rsqrt 0 -> NaN from 0 * inf: NaN blocks through the quantizer
     x[9, 7] = float("nan")
-    w = torch.randn(4096, device=DEV, dtype=torch.bfloat16, generator=g)
-    res = torch.randn(67, 4096, device=DEV, dtype=torch.bfloat16, generator=g)
+    w = torch.randn(hidden, device=DEV, dtype=torch.bfloat16, generator=g)
+    res = torch.randn(rows, hidden, device=DEV, dtype=torch.bfloat16, generator=g)
     dt = dtypes.STR_TO_ELEM_DTYPE[elem]
     y, mx, h = glue_ops.rmsnorm(x, w, 1e-6, residual=res, to_mx=dt)
     ref = MXTensor.to_mx(y, dt, 32)
