@@ -264,6 +264,41 @@ def mx_matmul_extras(dev):
     out["linear_32x14336x4096_decode"] = {"us": round(us_med, 1), "us_best": round(us_min, 1), "GB/s": round(w_bytes / us_med / 1e3, 1),
                                           "bound": "hbm (weight codes + scales read once)"}
     del X, W
+    # (3b) the same on COLD weights: a CUDA graph cycles through > 2 x L2 of distinct weight matrices, so every launch streams its
+    # weights from HBM like a decoder stack does (tools/decode_gemm_cold.py); packed bytes = what the kernel reads
+    from torchmx_b200 import mx_gemm
+    peak_gbs, _ = measured_peak_gbs()
+
+    def cold(N, K, wname):
+        wdt = getattr(dtypes, wname)
+        n_w = max(4, int(400e6 // (N * K)) + 1)
+        Xc = MXTensor.to_mx(torch.randn(32, K, device=dev, dtype=torch.bfloat16, generator=gen), dtypes.float8_e4m3, BLOCK)
+        Ws = [MXTensor.to_mx(torch.randn(N, K, device=dev, dtype=torch.bfloat16, generator=gen), wdt, BLOCK) for _ in range(n_w)]
+        for Wc in Ws:
+            mx_gemm.mark_static(Wc)
+            torch.nn.functional.linear(Xc, Wc)
+        torch.cuda.synchronize()
+        g, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for Wc in Ws:
+                    torch.nn.functional.linear(Xc, Wc)
+        ts = []
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / n_w * 1e3)
+        us = min(ts[1:])
+        bits = {"float4_e2m1": 4, "float6_e3m2": 6, "float8_e4m3": 8}[wname]
+        by = N * K * (bits / 8 + 1 / 32) + 32 * K * (1 + 1 / 32) + 32 * N * 2
+        del g, Ws
+        return {"us": round(us, 1), "GB/s_packed_bytes": round(by / us / 1e3, 1), "frac_of_hbm_peak": round(by / us / 1e3 / peak_gbs, 3),
+                "T_weight_elements/s": round(N * K / us / 1e6, 2), "distinct_weights": n_w}
+
+    out["decode_linear_cold_weights_M32"] = {f"{N}x{K}": {w: cold(N, K, w) for w in ("float8_e4m3", "float6_e3m2", "float4_e2m1")}
+                                              for (N, K) in ((4096, 4096), (14336, 4096), (57344, 8192))}
+    out["decode_linear_cold_weights_M32"]["bound"] = "hbm for one-byte codes; ~0.27 us per K block and SM whatever the element width for the packed formats (DESIGN.md K3c)"
+    torch.cuda.empty_cache()
     # (4) the chain between the two attention matmuls as one kernel (K4a): scale + causal rule + softmax + to_mx(P, e4m3)
     from torchmx_b200 import attention_ops, mlp_ops
     scores = (torch.randn(1, 32, 2048, 2048, device=dev, generator=gen) * 11).to(torch.bfloat16)
