@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) silu_mul_quantize_kernel(const uint16_t* 
                                                                  int blocks_per_row, int64_t ld_gate, int64_t ld_up, uint8_t* __restrict__ codes,
                                                                  uint8_t* __restrict__ scales, uint32_t flags) {
     pdl_launch_dependents();
+    pdl_wait();
     constexpr int NO = (ELEM == MXQ_ELEM_E2M1) ? 4 : 8;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_blocks; c += stride) {
@@ -69,12 +70,12 @@ cudaError_t launch_silu_mul_quantize(const void* gate, const void* up, int64_t r
     const uint16_t* u = (const uint16_t*)up;
     uint8_t* c8 = (uint8_t*)codes;
     switch (elem) {
-    case MXQ_ELEM_E4M3: silu_mul_quantize_kernel<MXQ_ELEM_E4M3><<<grid, 256, 0, stream>>>(g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, flags); break;
-    case MXQ_ELEM_E3M2: silu_mul_quantize_kernel<MXQ_ELEM_E3M2><<<grid, 256, 0, stream>>>(g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, flags); break;
-    case MXQ_ELEM_E2M3: silu_mul_quantize_kernel<MXQ_ELEM_E2M3><<<grid, 256, 0, stream>>>(g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, flags); break;
-    case MXQ_ELEM_E2M1: silu_mul_quantize_kernel<MXQ_ELEM_E2M1><<<grid, 256, 0, stream>>>(g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, flags); break;
-    case MXQ_ELEM_INT8: silu_mul_quantize_kernel<MXQ_ELEM_INT8><<<grid, 256, 0, stream>>>(g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, flags); break;
-    case MXQ_ELEM_E5M2: silu_mul_quantize_kernel<MXQ_ELEM_E5M2><<<grid, 256, 0, stream>>>(g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, flags); break;
+    case MXQ_ELEM_E4M3: launch_pdl(silu_mul_quantize_kernel<MXQ_ELEM_E4M3>, dim3(grid), dim3(256), 0, stream, g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, (uint32_t)flags); break;
+    case MXQ_ELEM_E3M2: launch_pdl(silu_mul_quantize_kernel<MXQ_ELEM_E3M2>, dim3(grid), dim3(256), 0, stream, g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, (uint32_t)flags); break;
+    case MXQ_ELEM_E2M3: launch_pdl(silu_mul_quantize_kernel<MXQ_ELEM_E2M3>, dim3(grid), dim3(256), 0, stream, g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, (uint32_t)flags); break;
+    case MXQ_ELEM_E2M1: launch_pdl(silu_mul_quantize_kernel<MXQ_ELEM_E2M1>, dim3(grid), dim3(256), 0, stream, g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, (uint32_t)flags); break;
+    case MXQ_ELEM_INT8: launch_pdl(silu_mul_quantize_kernel<MXQ_ELEM_INT8>, dim3(grid), dim3(256), 0, stream, g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, (uint32_t)flags); break;
+    case MXQ_ELEM_E5M2: launch_pdl(silu_mul_quantize_kernel<MXQ_ELEM_E5M2>, dim3(grid), dim3(256), 0, stream, g, u, n_blocks, bpr, ld_gate, ld_up, c8, scales, (uint32_t)flags); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

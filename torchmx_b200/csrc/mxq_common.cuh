@@ -6,6 +6,7 @@
 //   dequantize: out = RNE_target( decode(code) * 2^(s-127) )   (product exact in fp32)
 // No fast-math, no FTZ: fp32 subnormals carry real values at the ends of the E8M0 range.
 #pragma once
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -124,6 +125,26 @@ __device__ __forceinline__ float f16hi_to_f32(uint32_t h2) {
 // wrote (or may still read).  pdl_launch_dependents() lets a following such grid be scheduled early.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Host side: launch `kernel` with the programmatic-serialization attribute (it starts while its predecessor in the stream drains
+// and must call pdl_wait() before touching global memory).  The small row-wise / elementwise kernels between the MX linears of a
+// decoder layer last 3-6 us at decode sizes, of which the launch itself is a good part: started early, their set-up overlaps the
+// predecessor's tail.  MXQ_GLUE_PDL=0 (read once) launches them the ordinary way.
+inline bool glue_pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("MXQ_GLUE_PDL"); return !(v && v[0] == '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = glue_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float first, float second) {
     uint32_t r;

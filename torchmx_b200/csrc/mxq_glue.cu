@@ -39,6 +39,7 @@ struct NormParams {
 template <int ELEM, bool QUANT>
 __global__ void __launch_bounds__(kNormThreads) rmsnorm_kernel(const NormParams p) {
     pdl_launch_dependents();
+    pdl_wait();  // (launched with programmatic serialization: nothing the predecessor wrote is read before this)
     __shared__ float warp_sums[kNormThreads / 32];
     const int64_t row = blockIdx.x;
     const int n_chunks = p.hidden / 16;
@@ -138,6 +139,7 @@ struct RopeParams {
 // one thread = 8 elements of the first half of a head and their 8 partners in the second half
 __global__ void __launch_bounds__(256) rope_kernel(const RopeParams p) {
     pdl_launch_dependents();
+    pdl_wait();  // (launched with programmatic serialization: nothing the predecessor wrote is read before this)
     const int half_chunks = p.head_dim / 16;  // 8-element chunks per half head
     const int64_t n0 = p.batch * p.tokens * p.heads[0] * half_chunks, n1 = p.batch * p.tokens * p.heads[1] * half_chunks;
     const int64_t n2 = p.in[2] != nullptr ? p.batch * p.tokens * p.heads[2] * half_chunks : 0;
@@ -187,6 +189,7 @@ template <int ELEM>
 __global__ void __launch_bounds__(256) heads_quantize_kernel(const uint16_t* __restrict__ src, uint8_t* __restrict__ codes, uint8_t* __restrict__ scales,
                                                              int64_t n_blocks, int heads, int64_t tokens, int dblocks, uint32_t flags) {
     pdl_launch_dependents();
+    pdl_wait();  // (launched with programmatic serialization: nothing the predecessor wrote is read before this)
     const int64_t o = (int64_t)blockIdx.x * 256 + threadIdx.x;  // block index in output order: ((b * T + t) * H + h) * dblocks + db
     if (o >= n_blocks) return;
     const int db = (int)(o % dblocks);
@@ -231,6 +234,7 @@ struct TransposedQuantParams {
 template <int ELEM>
 __global__ void __launch_bounds__(256) transposed_quantize_kernel(const TransposedQuantParams p) {
     pdl_launch_dependents();
+    pdl_wait();  // (launched with programmatic serialization: nothing the predecessor wrote is read before this)
     constexpr int TR = 128, TC = 64;
     __shared__ __align__(16) uint16_t tile[TR][TC + 8];  // (+8: rows stay 16-byte aligned, column reads of a warp hit 16 distinct words)
     const int64_t slice = blockIdx.z;
@@ -276,7 +280,7 @@ int launch_heads_quantize(const void* src, int64_t batch, int64_t heads, int64_t
     const int64_t n_blocks = batch * heads * tokens * (head_dim / 32);
     const int64_t grid = (n_blocks + 255) / 256;
     if (grid > 0x7FFFFFFF) { snprintf(msg, msg_len, "too many blocks"); return MXQ_ERR_UNSUPPORTED_SHAPE; }
-#define MXQ_HQ_CASE(E) case E: heads_quantize_kernel<E><<<(unsigned)grid, 256, 0, stream>>>((const uint16_t*)src, (uint8_t*)codes, scales, n_blocks, (int)heads, tokens, (int)(head_dim / 32), flags); break;
+#define MXQ_HQ_CASE(E) case E: launch_pdl(heads_quantize_kernel<E>, dim3((unsigned)grid), dim3(256), 0, stream, (const uint16_t*)src, (uint8_t*)codes, scales, n_blocks, (int)heads, tokens, (int)(head_dim / 32), (uint32_t)flags); break;
     switch (elem) {
         MXQ_HQ_CASE(MXQ_ELEM_E4M3) MXQ_HQ_CASE(MXQ_ELEM_E3M2) MXQ_HQ_CASE(MXQ_ELEM_E2M3) MXQ_HQ_CASE(MXQ_ELEM_E2M1) MXQ_HQ_CASE(MXQ_ELEM_INT8) MXQ_HQ_CASE(MXQ_ELEM_E5M2)
     default: snprintf(msg, msg_len, "unknown element type %d", elem); return MXQ_ERR_INVALID;
@@ -306,9 +310,9 @@ int launch_rmsnorm(const mxq_rmsnorm_args_t* a, cudaStream_t stream, char* msg, 
     p.y = (uint16_t*)a->y; p.ldy = a->ldy;
     p.codes = (uint8_t*)a->codes; p.scales = a->scales; p.flags = a->flags;
     const unsigned grid = (unsigned)a->rows;
-#define MXQ_NORM_CASE(E) case E: rmsnorm_kernel<E, true><<<grid, kNormThreads, 0, stream>>>(p); break;
+#define MXQ_NORM_CASE(E) case E: launch_pdl(rmsnorm_kernel<E, true>, dim3(grid), dim3(kNormThreads), 0, stream, p); break;
     if (!quant) {
-        rmsnorm_kernel<MXQ_ELEM_E4M3, false><<<grid, kNormThreads, 0, stream>>>(p);
+        launch_pdl(rmsnorm_kernel<MXQ_ELEM_E4M3, false>, dim3(grid), dim3(kNormThreads), 0, stream, p);
     } else {
         switch (a->elem) {
             MXQ_NORM_CASE(MXQ_ELEM_E4M3) MXQ_NORM_CASE(MXQ_ELEM_E3M2) MXQ_NORM_CASE(MXQ_ELEM_E2M3) MXQ_NORM_CASE(MXQ_ELEM_E2M1) MXQ_NORM_CASE(MXQ_ELEM_INT8)
@@ -359,7 +363,7 @@ int launch_rope(const mxq_rope_args_t* a, int sm_count, cudaStream_t stream, cha
     // one item per thread up to 64 CTAs per SM (a 2048-token prefill of Llama-8B is 2560 CTAs: capped at 16 per SM some threads took
     // two items and the launch lasted as long as two)
     const int64_t want = (n + 255) / 256, cap = (int64_t)sm_count * 64;
-    rope_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(p);
+    launch_pdl(rope_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, stream, p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msg_len, "launch: %s", cudaGetErrorString(e)); return MXQ_ERR_CUDA; }
     return MXQ_OK;
@@ -379,7 +383,7 @@ int launch_transposed_quantize(const mxq_transposed_quantize_args_t* a, cudaStre
     p.n1 = a->n1; p.rows = a->rows; p.cols = a->cols;
     p.codes = (uint8_t*)a->codes; p.scales = a->scales; p.flags = a->flags;
     const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)slices);
-#define MXQ_TQ_CASE(E) case E: transposed_quantize_kernel<E><<<grid, 256, 0, stream>>>(p); break;
+#define MXQ_TQ_CASE(E) case E: launch_pdl(transposed_quantize_kernel<E>, grid, dim3(256), 0, stream, p); break;
     switch (a->elem) {
         MXQ_TQ_CASE(MXQ_ELEM_E4M3) MXQ_TQ_CASE(MXQ_ELEM_E3M2) MXQ_TQ_CASE(MXQ_ELEM_E2M3) MXQ_TQ_CASE(MXQ_ELEM_E2M1) MXQ_TQ_CASE(MXQ_ELEM_INT8) MXQ_TQ_CASE(MXQ_ELEM_E5M2)
     default: snprintf(msg, msg_len, "unknown element type %d", a->elem); return MXQ_ERR_INVALID;
