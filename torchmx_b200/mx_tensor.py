@@ -66,7 +66,7 @@ def small_scale_arena(chunk_bytes: int = 32 << 20):
 def _empty_scales(shape, device) -> torch.Tensor:
     n = math.prod(shape)
     a = getattr(_arena_state, "cur", None)
-    if a is None or n == 0 or n >= (1 << 20) or torch.cuda.is_current_stream_capturing():
+    if a is None or n == 0 or n >= (1 << 20) or (torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing()):
         return torch.empty(shape, dtype=torch.uint8, device=device)
     need = (n + 255) & ~255
     if a["buf"] is None or a["buf"].device != device or a["off"] + need > a["buf"].numel():
