@@ -88,9 +88,11 @@ __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t cluster_addr) {
 }
 
 #ifdef MXQ_DEV
+#define SK_EXP(bit) ((p.exp & (bit)) != 0)  // timing experiments of developer builds (wrong results); compiled out of the shipped library
 __device__ __forceinline__ long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; }
 #define SK_TRACE(i) if (p.trace != nullptr) { p.trace[blockIdx.x * 16 + (i)] = gtimer(); p.trace[blockIdx.x * 16 + 8 + (i)] = clock64(); }
 #else
+#define SK_EXP(bit) false
 #define SK_TRACE(i)
 #endif
 
@@ -226,13 +228,13 @@ __global__ void __launch_bounds__(kThreads, STAGES <= 4 ? 2 : 1) mx_gemm_skinny_
                             const uint32_t w_lo = w_lo0 + stage * (L::W_STAGE >> 4), x_lo = x_lo0 + stage * (L::X_STAGE >> 4);
                             const uint32_t sf_off = sfs * (L::SF_STAGE >> 4) + j * (SF_KB_BYTES >> 4);
                             const uint32_t tm_sfw = tm_sf0 + sf_sel * SF_BUF_COLS, tm_sfx = tm_sfw + 4;
-                            if (!(p.exp & 8)) {
+                            if (!SK_EXP(8)) {
                             tc_copy_sf(tm_sfw, HI_SF | (sfw_lo0 + sf_off));
                             tc_copy_sf(tm_sfx, HI_SF | (sfx_lo0 + sf_off));
                             }
 #pragma unroll
                             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                                if (!(p.exp & 8))
+                                if (!SK_EXP(8))
                                 tc_mma_mx(tm_acc, HI_OPERAND | (w_lo + k * (UMMA_K >> 4)), HI_OPERAND | (x_lo + k * (UMMA_K >> 4)), idesc_with_sf(idesc, k, k),
                                           !(first && k == 0), tm_sfw, tm_sfx);
                             if (!BATCH_COMMITS) tc_commit(&empty[stage]);
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, STAGES <= 4 ? 2 : 1) mx_gemm_skinny_
 #pragma unroll
                         for (int j = me; j < SF_KB; j += ISSUERS) {
                             const int kb = g * SF_KB + j;
-                            if (kb < k_blocks) { if (p.exp & 16) mbar_arrive(&empty[kb % STAGES]); else tc_commit(&empty[kb % STAGES]); }
+                            if (kb < k_blocks) { if (SK_EXP(16)) mbar_arrive(&empty[kb % STAGES]); else tc_commit(&empty[kb % STAGES]); }
                         }
                     }
                     tc_commit(&sf_empty[sfs]);
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, STAGES <= 4 ? 2 : 1) mx_gemm_skinny_
         // ================= epilogue, part 2: fixed-order reduction of the S partials through DSMEM =================
         __syncwarp();
         cluster_sync_all();  // every CTA's partials are written (and every MMA has retired, so the W ring was free to reuse)
-        MXQ_DEV_ONLY(if (threadIdx.x == 128 && (p.exp & 32)) { SK_TRACE(1) })
+        MXQ_DEV_ONLY(if (threadIdx.x == 128 && SK_EXP(32)) { SK_TRACE(1) })
         if (warp >= 4 && warp < 8) {
             // This CTA finishes tokens split, split + S, ...  One work item = one token x four consecutive weight rows: the S
             // partials -- already here when the variant pushes; otherwise S 16-byte DSMEM loads, all in flight together (a remote
@@ -456,11 +458,11 @@ __global__ void __launch_bounds__(kThreads, STAGES <= 4 ? 2 : 1) mx_gemm_skinny_
                 }
             }
         }
-        MXQ_DEV_ONLY(if (threadIdx.x == 128 && (p.exp & 32)) { SK_TRACE(2) })
+        MXQ_DEV_ONLY(if (threadIdx.x == 128 && SK_EXP(32)) { SK_TRACE(2) })
         __syncwarp();
         if constexpr (L::PUSH) __syncthreads();  // (after the barrier above nobody touches a peer's shared memory any more)
         else cluster_sync_all();                // nobody exits while a peer may still read its partials
-        MXQ_DEV_ONLY(if (threadIdx.x == 128 && (p.exp & 32)) { SK_TRACE(3) })
+        MXQ_DEV_ONLY(if (threadIdx.x == 128 && SK_EXP(32)) { SK_TRACE(3) })
     } else {
         __syncwarp();
         __syncthreads();
