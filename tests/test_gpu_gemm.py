@@ -447,6 +447,34 @@ def test_packed_linear_is_bit_identical_and_round_trips(wdt, rows):
     assert torch.equal(back(x), want)
 
 
+@pytest.mark.parametrize("adt", ["float6_e3m2", "float4_e2m1"])
+@pytest.mark.parametrize("wdt", ["float6_e3m2", "float4_e2m1"])
+def test_packed_linear_with_4_and_6_bit_activations(adt, wdt):
+    """a weight held only as its packed operand, activations quantized to 4 / 6 bits: K1 writes the packed activation stream
+    (no pack launch), and the result equals the reference-layout layer's, bit for bit"""
+    import torchmx  # noqa: F401
+    from torchmx import mx_gemm
+    from torchmx.config import MXConfig, QLinearConfig
+    from torchmx.layers.mx_linear import MXInferenceLinear
+    from torchmx.layers.packed_linear import PackedMXLinear
+    torch.manual_seed(2)
+    lin = torch.nn.Linear(512, 384, bias=True, device=DEV, dtype=torch.bfloat16)
+    qc = QLinearConfig(weights_config=MXConfig(wdt, 32), activations_config=MXConfig(adt, 32))
+    ref = MXInferenceLinear.from_float(lin, qc)
+    x = torch.randn(3, 100, 512, device=DEV, dtype=torch.bfloat16) * 2
+    real = mx_gemm.linear_packed_act_quant
+    mx_gemm.linear_packed_act_quant = lambda *a, **k: None  # the reference-layout layer on the three-launch path
+    try:
+        want = ref(x)
+    finally:
+        mx_gemm.linear_packed_act_quant = real
+    packed = PackedMXLinear.from_mx_linear(ref, keep_source=True)
+    n0, t0 = mx_gemm.stats.get("packed_act_quant", 0), mx_gemm.stats["transcode"]
+    got = packed(x)
+    assert mx_gemm.stats.get("packed_act_quant", 0) == n0 + 1 and mx_gemm.stats["transcode"] == t0
+    assert torch.equal(got, want)
+
+
 def test_pack_linear_on_a_model_and_what_it_leaves_alone():
     import torchmx  # noqa: F401
     from torchmx.config import MXConfig, QLinearConfig

@@ -548,6 +548,18 @@ def linear_packed_weight(x, b_e: torch.Tensor, sfb: torch.Tensor, b_fmt: int, bi
             stats["tensor_core"] += 1
             stats["fused_act_quant"] = stats.get("fused_act_quant", 0) + 1
             return out
+    if (not isinstance(x, MXTensor) and _USE_PACKED and act_elem.name in _PACKED_FORMAT and type(x) is torch.Tensor and x.dtype == torch.bfloat16
+            and x.is_contiguous() and x.data_ptr() % 32 == 0):
+        # 4 / 6-bit activation config: K1 writes the packed operand stream itself (see linear_packed_act_quant)
+        a_fmt = _PACKED_FORMAT[act_elem.name]
+        a_e = torch.empty((rows, K * _PACKED_BITS[a_fmt] // 8), dtype=torch.uint8, device=x.device)
+        sfa = torch.empty((rows, K // 32), dtype=torch.uint8, device=x.device)
+        rc = _C.lib().mxq_quantize(x.data_ptr(), _C.HP_BF16, rows * (K // 32), 32, dtypes.ELEM_ID[act_elem.name],
+                                   _C.FLAG_OPERAND_LAYOUT | (_C.FLAG_HW_EXACT if hw_exact else 0), a_e.data_ptr(), sfa.data_ptr(), x.device.index, _stream_ptr(x))
+        if rc == _C.OK and _launch(a_e, sfa, b_e, sfb, bias, 1, rows, N, K, 0, 0, 0, 0, out, a_fmt, b_fmt, 0, static_b=static_b):
+            stats["tensor_core"] += 1
+            stats["packed_act_quant"] = stats.get("packed_act_quant", 0) + 1
+            return out
     x_mx = x if isinstance(x, MXTensor) else MXTensor.to_mx(x, act_elem, 32)
     assert _qualifies(x_mx) and x_mx._block_dim == x_mx._data.dim() - 1 and x_mx._data.is_contiguous(), "activation cannot run on the tensor-core path"
     a_codes, sfa = x_mx._data.reshape(rows, -1), x_mx._scale_e8m0.reshape(rows, -1)
